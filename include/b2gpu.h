@@ -1,0 +1,128 @@
+/* b2gpu.h — C ABI of the B200-native BZip2 block encoder that stands behind Zip-Ada's
+ * `BZip2.Encoding.Encode` (reference: zip_lib/bzip2-encoding.ads:38-56).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.  The Ada body of
+ * `BZip2.Encoding` binds these entry points with `pragma Import (C, ...)` over Interfaces.C
+ * (the binding is shown in INTEGRATION.md and zip-ada_b200/ada/bzip2-encoding.adb); the C++ and
+ * Python hosts in this repository use the same symbols.
+ *
+ * Every function returns 0 on success and a non-zero B2_ERR_* otherwise; b2_last_error() gives a
+ * human-readable message for the calling thread.  There is NO CPU fallback: if no CUDA device is
+ * usable, b2_create fails.
+ *
+ * Threading: one host thread per handle at a time; handles are independent (no global mutable
+ * state), matching the reference's "can be used ad libitum in parallel processing"
+ * (doc/zipada.txt:26).
+ */
+#ifndef B2GPU_H
+#define B2GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2_OK 0
+#define B2_ERR_ARGUMENT 1
+#define B2_ERR_OUTPUT_TOO_SMALL 2
+#define B2_ERR_ALLOC 3
+#define B2_ERR_CUDA 10
+#define B2_ERR_INTERNAL 11
+
+/* Compression_Option (bzip2-encoding.ads:40-43): block_100k / block_400k / block_900k.
+ * Zip.Compress.BZip2_E maps BZip2_1/2/3 to them (zip-compress-bzip2_e.adb:122-126). */
+#define B2_BLOCK_100K 1
+#define B2_BLOCK_400K 4
+#define B2_BLOCK_900K 9
+
+/* Stream_Size_Type / unknown_size (bzip2-encoding.ads:45-47). */
+#define B2_UNKNOWN_SIZE (-1)
+
+typedef struct b2_encoder b2_encoder;
+
+/* Creates an encoder bound to CUDA device `device` (0-based).  `level` is one of B2_BLOCK_*.
+ * Replaces: the per-call heap allocations of Encode (bzip2-encoding.adb:162, :263, :272, :372,
+ * :1157) — the handle owns all device workspaces and reuses them across calls. */
+int b2_create(int level, int device, b2_encoder **out);
+
+/* Releases everything the handle owns.  Mirrors the exception-path clean-up of
+ * bzip2-encoding.adb:1128-1133, :1351-1357, :1377-1381: the Ada body calls it from a handler. */
+void b2_destroy(b2_encoder *enc);
+
+/* Upper bound of the encoded size for `n` input bytes (for sizing `out`). */
+uint64_t b2_bound(uint64_t n);
+
+/* Whole-stream encode, host buffers: produces exactly the bytes that
+ * `Encode (option, size_hint)` sends through Write_Byte for the bytes that Read_Byte/More_Bytes
+ * deliver (bzip2-encoding.adb:1413-1431): "BZh<level>", blocks, footer.
+ * `size_hint` is the reference's size_hint (B2_UNKNOWN_SIZE = -1): it changes the cutting of the
+ * last two chunks (bzip2-encoding.adb:1416-1424).  Copies in -> device and device -> out. */
+int b2_encode_stream(b2_encoder *enc, const uint8_t *in, uint64_t n, int64_t size_hint,
+                     uint8_t *out, uint64_t out_cap, uint64_t *out_len);
+
+/* Same, with input and output already in device memory of the handle's device (no PCIe traffic;
+ * used to measure the kernels alone).  `d_in` needs 64 readable bytes of slack after `n`;
+ * `d_out` must be 4-byte aligned. */
+int b2_encode_stream_device(b2_encoder *enc, const uint8_t *d_in, uint64_t n, int64_t size_hint,
+                            uint8_t *d_out, uint64_t out_cap, uint64_t *out_len);
+
+/* Last error message of the calling thread (never NULL). */
+const char *b2_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Measurement taps (bench.py).  Times are CUDA-event times on the handle's stream. */
+typedef struct b2_stats {
+  uint64_t streams;              /* b2_encode_stream* calls since the last reset */
+  uint64_t input_bytes;
+  uint64_t chunks;               /* Read_and_Split_Block calls (bzip2-encoding.adb:1144) */
+  uint64_t blocks;               /* Encode_Block calls after de-duplication (:148) */
+  uint64_t block_bytes;          /* post-RLE1 bytes sorted (sum of N over blocks) */
+  uint64_t kernel_launches;      /* kernels launched */
+  uint64_t sort_rounds;          /* doubling rounds, summed over batches */
+  uint64_t sort_elems_round0;    /* suffixes entering round 0 */
+  uint64_t sort_elems_later;     /* sum over later rounds of suffixes re-sorted */
+  uint64_t scatter_launches;     /* radix scatter launches */
+  uint64_t scatter_elems;        /* elements moved by them */
+  double scatter_ms;             /* their summed duration (only with b2_set_timing(enc, 1)) */
+  double stage_ms[8];            /* cut+segment, rle1, sort, mtf, entropy, pack, concat, copies (timing on) */
+} b2_stats;
+
+int b2_set_timing(b2_encoder *enc, int on);
+int b2_get_stats(b2_encoder *enc, b2_stats *out);
+int b2_reset_stats(b2_encoder *enc);
+
+/* ---------------------------------------------------------------------------------------------
+ * Parity taps (tests only): the intermediates the reference prints at verbosity `detailed` /
+ * `super_detailed` (bzip2-encoding.adb:109-140, :205-209, :282-289, :337, :956-960). */
+typedef struct b2_block_info {
+  uint32_t n_rle, origin, crc, n_mtf, eob, n_used, n_sel, ec_count, max_len, sample_width, cost, pad;
+  uint64_t bits;
+} b2_block_info;
+
+/* One Encode_Block (bzip2-encoding.adb:148) on the device.  Any output pointer may be NULL.
+ * rle_out/bwt_out: >= len*5/4+64 bytes; mtf_out: >= len*5/4+64 uint16; sel_out: >= 18002;
+ * lens_out: 6*258 bytes; bits_out: the block's bitstream from bit 0. */
+int b2_dbg_block(b2_encoder *enc, const uint8_t *raw, uint32_t len,
+                 uint8_t *rle_out, uint8_t *bwt_out, uint16_t *mtf_out, uint8_t *sel_out,
+                 uint8_t *lens_out, uint8_t *bits_out, uint64_t bits_cap, b2_block_info *info);
+
+typedef struct b2_chunk_trace {
+  uint64_t start;
+  uint32_t len, dyn_capacity;
+  int32_t winner;                /* 0 single, 1 parts_4, 2 segmented_1, 3 segmented_2 (:1217) */
+  uint32_t n_seg1, n_seg2, pad;
+  uint64_t bytes[4];             /* destination_index of each tactic (:1319-1325) */
+  uint64_t bits[4];
+} b2_chunk_trace;
+
+/* Trace of the last b2_encode_stream* call: one record per chunk. */
+int b2_get_trace(b2_encoder *enc, b2_chunk_trace *out, uint64_t cap, uint64_t *n);
+
+/* Segment_by_Entropy cut list of one chunk of the last call (profile 0 = segmented_1, 1 = segmented_2). */
+int b2_get_segments(b2_encoder *enc, uint64_t chunk, int profile, uint32_t *cuts, uint32_t cap, uint32_t *n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

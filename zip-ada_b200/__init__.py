@@ -1,0 +1,183 @@
+"""Python host of the b2gpu C ABI (include/b2gpu.h).
+
+Mirrors the reference's operator interface for the BZip2 path: `Encoder(option).encode(data,
+size_hint)` is `BZip2.Encoding.Encode (option, size_hint)` (zip_lib/bzip2-encoding.ads:47-56)
+with Read_Byte/More_Bytes/Write_Byte replaced by whole buffers; `encode_callbacks` keeps the
+three-callback generic shape.  All computing happens in libb2gpu.so (CUDA, sm_100a).  There is no
+CPU fallback: if the library or a GPU is missing, construction raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libb2gpu.so")
+
+block_100k, block_400k, block_900k = 1, 4, 9     # Compression_Option (bzip2-encoding.ads:40-43)
+unknown_size = -1                                # bzip2-encoding.ads:47
+
+
+class B2Error(RuntimeError):
+    pass
+
+
+class Stats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in
+                ("streams", "input_bytes", "chunks", "blocks", "block_bytes", "kernel_launches", "sort_rounds",
+                 "sort_elems_round0", "sort_elems_later", "scatter_launches", "scatter_elems")] + \
+               [("scatter_ms", C.c_double), ("stage_ms", C.c_double * 8)]
+
+
+class BlockInfo(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in
+                ("n_rle", "origin", "crc", "n_mtf", "eob", "n_used", "n_sel", "ec_count", "max_len",
+                 "sample_width", "cost", "pad")] + [("bits", C.c_uint64)]
+
+
+class ChunkTrace(C.Structure):
+    _fields_ = [("start", C.c_uint64), ("len", C.c_uint32), ("dyn_capacity", C.c_uint32),
+                ("winner", C.c_int32), ("n_seg1", C.c_uint32), ("n_seg2", C.c_uint32), ("pad", C.c_uint32),
+                ("bytes", C.c_uint64 * 4), ("bits", C.c_uint64 * 4)]
+
+
+EXPORTS = ["b2_create", "b2_destroy", "b2_bound", "b2_encode_stream", "b2_encode_stream_device", "b2_last_error",
+           "b2_set_timing", "b2_get_stats", "b2_reset_stats", "b2_dbg_block", "b2_get_trace", "b2_get_segments"]
+
+_lib = None
+
+
+def lib():
+    """Loads libb2gpu.so (built in-tree by __graft_entry__.build()).  Raises if it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            raise B2Error("libb2gpu.so is not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(b2gpu has no CPU fallback)")
+        _lib = C.CDLL(_SO)
+        _lib.b2_bound.restype = C.c_uint64
+        _lib.b2_bound.argtypes = [C.c_uint64]
+        _lib.b2_last_error.restype = C.c_char_p
+        _lib.b2_create.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        _lib.b2_destroy.argtypes = [C.c_void_p]
+        _lib.b2_destroy.restype = None
+        _lib.b2_encode_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int64, C.c_void_p, C.c_uint64,
+                                          C.POINTER(C.c_uint64)]
+        _lib.b2_encode_stream_device.argtypes = _lib.b2_encode_stream.argtypes
+        _lib.b2_set_timing.argtypes = [C.c_void_p, C.c_int]
+        _lib.b2_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+        _lib.b2_reset_stats.argtypes = [C.c_void_p]
+        _lib.b2_dbg_block.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32] + [C.c_void_p] * 6 + [C.c_uint64, C.POINTER(BlockInfo)]
+        _lib.b2_get_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+        _lib.b2_get_segments.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise B2Error("b2gpu error %d: %s" % (rc, lib().b2_last_error().decode()))
+
+
+def _u8(buf):
+    if isinstance(buf, np.ndarray):
+        return np.ascontiguousarray(buf, dtype=np.uint8)
+    return np.frombuffer(bytes(buf), dtype=np.uint8)
+
+
+class Encoder:
+    """One encoder handle on one CUDA device."""
+
+    def __init__(self, option=block_900k, device=0):
+        self._h = C.c_void_p()
+        self.option = option
+        _check(lib().b2_create(int(option), int(device), C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().b2_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- BZip2.Encoding.Encode (option, size_hint) over whole buffers ---------------------------
+    def encode(self, data, size_hint=unknown_size, out=None):
+        a = _u8(data)
+        n = a.size
+        cap = lib().b2_bound(n) + 1024 * (n // 40000 + 16)
+        if out is None:
+            out = np.empty(cap, dtype=np.uint8)
+        out_len = C.c_uint64(0)
+        _check(lib().b2_encode_stream(self._h, a.ctypes.data, n, int(size_hint), out.ctypes.data, out.size, C.byref(out_len)))
+        return out[:out_len.value]
+
+    def encode_ptr(self, in_ptr, n, size_hint, out_ptr, out_cap):
+        """Host pointers (e.g. pinned torch tensors); returns the encoded length."""
+        out_len = C.c_uint64(0)
+        _check(lib().b2_encode_stream(self._h, in_ptr, n, int(size_hint), out_ptr, out_cap, C.byref(out_len)))
+        return out_len.value
+
+    def encode_device_ptr(self, d_in, n, size_hint, d_out, out_cap):
+        """Device pointers on this handle's device; returns the encoded length."""
+        out_len = C.c_uint64(0)
+        _check(lib().b2_encode_stream_device(self._h, d_in, n, int(size_hint), d_out, out_cap, C.byref(out_len)))
+        return out_len.value
+
+    # -- generic shape of the reference: Read_Byte / More_Bytes / Write_Byte --------------------
+    def encode_callbacks(self, read_byte, more_bytes, write_byte, size_hint=unknown_size):
+        buf = bytearray()
+        while more_bytes():
+            buf.append(read_byte())
+        for b in self.encode(bytes(buf), size_hint).tobytes():
+            write_byte(b)
+
+    # -- measurement / parity taps ----------------------------------------------------------------
+    def set_timing(self, on):
+        _check(lib().b2_set_timing(self._h, 1 if on else 0))
+
+    def stats(self):
+        s = Stats()
+        _check(lib().b2_get_stats(self._h, C.byref(s)))
+        return s
+
+    def reset_stats(self):
+        _check(lib().b2_reset_stats(self._h))
+
+    def trace(self):
+        n = C.c_uint64(0)
+        _check(lib().b2_get_trace(self._h, None, 0, C.byref(n)))
+        arr = (ChunkTrace * max(1, n.value))()
+        _check(lib().b2_get_trace(self._h, arr, n.value, C.byref(n)))
+        return [arr[i] for i in range(n.value)]
+
+    def segments(self, chunk, profile):
+        cuts = np.zeros(2304, np.uint32)
+        n = C.c_uint32(0)
+        _check(lib().b2_get_segments(self._h, chunk, profile, cuts.ctypes.data, cuts.size, C.byref(n)))
+        return cuts[:n.value].copy()
+
+    def dbg_block(self, data):
+        a = _u8(data)
+        n = a.size
+        cap = n * 5 // 4 + 64
+        rle = np.zeros(cap, np.uint8)
+        bwt = np.zeros(cap, np.uint8)
+        mtf = np.zeros(cap + 16, np.uint16)
+        sel = np.zeros(18004, np.uint8)
+        lens = np.zeros(6 * 258, np.uint8)
+        bits = np.zeros(n * 2 + 1_000_000, np.uint8)
+        info = BlockInfo()
+        _check(lib().b2_dbg_block(self._h, a.ctypes.data, n, rle.ctypes.data, bwt.ctypes.data, mtf.ctypes.data,
+                                  sel.ctypes.data, lens.ctypes.data, bits.ctypes.data, bits.size, C.byref(info)))
+        return dict(rle=rle[:info.n_rle].copy(), bwt=bwt[:info.n_rle].copy(), mtf=mtf[:info.n_mtf].copy(),
+                    sel=sel[:info.n_sel].copy(), lens=lens.reshape(6, 258).copy(),
+                    bits=bits[:(info.bits + 7) // 8].copy(), info=info)

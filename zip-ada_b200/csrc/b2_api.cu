@@ -1,0 +1,591 @@
+// Host orchestration + the C ABI of include/b2gpu.h.
+//
+// Mirrors the stream level of the reference, zip_lib/bzip2-encoding.adb:1136-1431:
+//   Write_Stream_Header (:1384-1391) -> { Read_and_Split_Block (:1144) }* -> Write_Stream_Footer (:1395-1407)
+// with Block_Split_Parallel's four tactics (:1214-1359) expanded into a de-duplicated list of
+// blocks ("jobs") that are encoded in batches on the device.  The only serial cross-chunk data are
+// scalars — incoming bit offset, winner, combined CRC — replayed here in O(#chunks).
+#include "b2_common.cuh"
+#include "b2_kernels.h"
+#include "../../include/b2gpu.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+static thread_local std::string g_last_error = "";
+void b2_set_error(const char *file, int line, const char *msg) {
+  char buf[512];
+  snprintf(buf, sizeof buf, "%s:%d: %s", file, line, msg);
+  g_last_error = buf;
+}
+#define B2_FAIL(code, msg) do { b2_set_error(__FILE__, __LINE__, msg); return code; } while (0)
+#define B2_TRY(x) do { int rc_ = (x); if (rc_) return rc_; } while (0)
+
+namespace {
+
+template <class T> struct DevBuf {
+  T *p = nullptr; size_t cap = 0;
+  int ensure(size_t n) {
+    if (n <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = n + n / 8 + 256;
+    cudaError_t e = cudaMalloc((void **)&p, want * sizeof(T));
+    if (e != cudaSuccess) { b2_set_error(__FILE__, __LINE__, cudaGetErrorString(e)); return B2_ERR_ALLOC; }
+    cap = want;
+    return 0;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct HostJob {           // host mirror of a block
+  u64 raw_off; u32 raw_len;
+};
+
+struct ChunkPlan {
+  u64 start; u32 len; u32 cap;
+  std::vector<u32> tactic_jobs[4];   // global job ids, in stream order
+  u32 n_seg[2];
+  int n_tactics;
+};
+
+}  // namespace
+
+struct b2_encoder {
+  int level = 9, device = 0;
+  cudaStream_t st = nullptr;
+  bool timing = false;
+  // constants
+  DevBuf<B2CrcTables> d_ct;
+  DevBuf<double> d_T;
+  // stream-level
+  DevBuf<u8> d_in;
+  DevBuf<u32> d_out;
+  DevBuf<B2Chunk> d_chunks;
+  DevBuf<u32> d_scalars;     // [0] n_chunks, [2..3] total_words (u64)
+  DevBuf<u32> d_seg, d_nseg;
+  // batch workspace
+  DevBuf<B2Job> d_jobs;
+  DevBuf<u8> d_text, d_bwt, d_idx;
+  DevBuf<u64> d_keysA, d_keysB;
+  DevBuf<u32> d_valsA, d_valsB, d_rank, d_grp;
+  DevBuf<B2SortTile> d_tiles, d_mtiles;
+  DevBuf<B2SortJob> d_sj;
+  DevBuf<u32> d_hist;
+  DevBuf<i32> d_tile_head, d_carry;
+  DevBuf<u32> d_unsorted;
+  DevBuf<u16> d_mtf;
+  DevBuf<u32> d_rank3, d_rank4;
+  DevBuf<u8> d_sel, d_selpos, d_lens;
+  DevBuf<unsigned long long> d_gcost;
+  DevBuf<u32> d_cost, d_low;
+  DevBuf<u32> d_bits;
+  DevBuf<B2ConcatItem> d_items;
+  u32 *h_unsorted = nullptr; size_t h_unsorted_cap = 0;
+  // host state of the last call
+  std::vector<B2Chunk> chunks;
+  std::vector<u32> nseg, seg;
+  std::vector<b2_chunk_trace> trace;
+  std::vector<B2Job> batch_jobs;      // jobs of the last batch, as read back
+  b2_stats stats;
+  B2SortStats sort_stats;
+  size_t batch_positions = 96u << 20;   // positions per batch (env B2GPU_BATCH_POSITIONS)
+  size_t batch_jobs_max = 4096;
+  // timing
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+};
+
+namespace {
+
+struct StageTimer {
+  b2_encoder *e; int stage; bool on;
+  StageTimer(b2_encoder *e_, int s) : e(e_), stage(s), on(e_->timing) { if (on) cudaEventRecord(e->ev[0], e->st); }
+  ~StageTimer() {
+    if (on) {
+      cudaEventRecord(e->ev[1], e->st);
+      cudaEventSynchronize(e->ev[1]);
+      float ms = 0; cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]);
+      e->stats.stage_ms[stage] += ms;
+    }
+  }
+};
+
+void balance_window(int level, i64 &lo, i64 &hi) {
+  // Float (stream_rest) in Float (block_capacity) * (1.0 + 0.05) .. Float (block_capacity) * (1.0 + 0.30)
+  // evaluated in IEEE single precision (bzip2-encoding.adb:1410-1418).
+  volatile float fcap = (float)(100000 * level);
+  volatile float flo = fcap * 1.05f, fhi = fcap * 1.30f;
+  lo = -1; hi = -2;
+  i64 base = 100000ll * level;
+  for (i64 v = base; v <= 2 * base; v++) {
+    volatile float f = (float)v;
+    if (f >= flo && f <= fhi) { if (lo < 0) lo = v; hi = v; }
+  }
+}
+
+int ensure_batch_workspace(b2_encoder *e, size_t T, size_t J) {
+  const size_t max_tiles = T / B2_SORT_TILE + J + 8;
+  const size_t max_mtiles = T / B2_MTF_TILE + J + 8;
+  const size_t GT = T / B2_GROUP_SIZE + 2 * J + 8;
+  B2_TRY(e->d_jobs.ensure(J));
+  B2_TRY(e->d_text.ensure(T + 64)); B2_TRY(e->d_bwt.ensure(T + 64)); B2_TRY(e->d_idx.ensure(T + 64));
+  B2_TRY(e->d_keysA.ensure(T)); B2_TRY(e->d_keysB.ensure(T));
+  B2_TRY(e->d_valsA.ensure(T)); B2_TRY(e->d_valsB.ensure(T));
+  B2_TRY(e->d_rank.ensure(T)); B2_TRY(e->d_grp.ensure(T));
+  B2_TRY(e->d_tiles.ensure(max_tiles)); B2_TRY(e->d_mtiles.ensure(max_mtiles));
+  B2_TRY(e->d_sj.ensure(J));
+  B2_TRY(e->d_hist.ensure(max_tiles * 256));
+  B2_TRY(e->d_tile_head.ensure(max_tiles)); B2_TRY(e->d_carry.ensure(max_tiles));
+  B2_TRY(e->d_unsorted.ensure(J));
+  B2_TRY(e->d_mtf.ensure(T + 16 * J + 64));
+  B2_TRY(e->d_rank3.ensure(GT)); B2_TRY(e->d_rank4.ensure(GT));
+  B2_TRY(e->d_sel.ensure(GT * B2_N_TRIPLES)); B2_TRY(e->d_selpos.ensure(GT));
+  B2_TRY(e->d_gcost.ensure(GT * B2_N_TRIPLES));
+  B2_TRY(e->d_lens.ensure(J * B2_N_TRIPLES * B2_MAX_CODERS * B2_MAX_ALPHA));
+  B2_TRY(e->d_cost.ensure(J * B2_N_TRIPLES)); B2_TRY(e->d_low.ensure(J * B2_N_TRIPLES));
+  B2_TRY(e->d_items.ensure(J));
+  if (J > e->h_unsorted_cap) {
+    if (e->h_unsorted) cudaFreeHost(e->h_unsorted);
+    B2_CUDA_CHECK(cudaMallocHost((void **)&e->h_unsorted, (J + 64) * sizeof(u32)));
+    e->h_unsorted_cap = J + 64;
+  }
+  return 0;
+}
+
+struct BatchLayout { u32 T; u32 GT; u32 max_g; };
+
+// Assigns arena offsets to jobs[0..J) (host), returns totals.
+BatchLayout layout_jobs(std::vector<B2Job> &jobs, int level) {
+  u64 pos = 0, mpos = 0;
+  for (auto &j : jobs) {
+    u64 cap = std::min<u64>((u64)j.raw_len * 5 / 4 + 8, (u64)level * 100000 + 64);
+    cap = (cap + 15) & ~15ull;
+    j.pos_off = (u32)pos; j.cap = (u32)cap;
+    pos += cap;
+    j.mtf_off = (u32)mpos;
+    mpos += (cap + 2 + 7) & ~7ull;
+  }
+  return BatchLayout{(u32)pos, 0, 0};
+}
+
+// Runs one batch through RLE1 -> BWT -> MTF/RLE2 -> entropy search -> bit packing.
+// On return e->batch_jobs holds the device's view of the jobs (n, crc, origin, nbits, bits_off ...).
+int run_batch(b2_encoder *e, const u8 *d_in, std::vector<B2Job> &jobs) {
+  const u32 J = (u32)jobs.size();
+  if (J == 0) return 0;
+  BatchLayout L = layout_jobs(jobs, e->level);
+  B2_TRY(ensure_batch_workspace(e, (size_t)L.T + 64, J));
+  cudaStream_t st = e->st;
+  B2_CUDA_CHECK(cudaMemcpyAsync(e->d_jobs.p, jobs.data(), J * sizeof(B2Job), cudaMemcpyHostToDevice, st));
+  {
+    StageTimer tm(e, 1);
+    B2_TRY(b2k_rle1(st, d_in, e->d_jobs.p, J, e->d_text.p, e->d_ct.p));
+    e->stats.kernel_launches += 1;
+  }
+  e->batch_jobs.resize(J);
+  B2_CUDA_CHECK(cudaMemcpyAsync(e->batch_jobs.data(), e->d_jobs.p, J * sizeof(B2Job), cudaMemcpyDeviceToHost, st));
+  B2_CUDA_CHECK(cudaStreamSynchronize(st));
+  // group arena offsets need n (M <= n + 1)
+  u32 gpos = 0, max_g = 1;
+  std::vector<u32> ids(J), ns(J);
+  std::vector<B2SortTile> mtiles;
+  for (u32 j = 0; j < J; j++) {
+    B2Job &b = e->batch_jobs[j];
+    if (b.n > b.cap) B2_FAIL(B2_ERR_INTERNAL, "RLE1 output exceeds its slot");
+    u32 gmax = b.n / B2_GROUP_SIZE + 2;
+    b.grp_off = gpos; gpos += gmax;
+    max_g = std::max(max_g, gmax);
+    ids[j] = j; ns[j] = b.n;
+    for (u32 s = 0; s < b.n; s += B2_MTF_TILE) mtiles.push_back(B2SortTile{j, s});
+    e->stats.block_bytes += b.n;
+  }
+  e->stats.blocks += J;
+  // write grp_off back (only field changed on the host)
+  B2_CUDA_CHECK(cudaMemcpyAsync(e->d_jobs.p, e->batch_jobs.data(), J * sizeof(B2Job), cudaMemcpyHostToDevice, st));
+  {
+    StageTimer tm(e, 2);
+    B2SortCtx cx;
+    cx.keysA = e->d_keysA.p; cx.keysB = e->d_keysB.p; cx.valsA = e->d_valsA.p; cx.valsB = e->d_valsB.p;
+    cx.rank = e->d_rank.p; cx.grp = e->d_grp.p; cx.d_tiles = e->d_tiles.p; cx.d_sj = e->d_sj.p;
+    cx.d_hist = e->d_hist.p; cx.d_tile_head = e->d_tile_head.p; cx.d_carry = e->d_carry.p;
+    cx.d_unsorted = e->d_unsorted.p; cx.h_unsorted = e->h_unsorted;
+    cx.max_tiles = e->d_tiles.cap; cx.max_jobs = e->d_sj.cap; cx.timing = e->timing;
+    cx.stats = e->sort_stats;
+    int rc = b2k_bwt_batch(&cx, st, e->d_jobs.p, ids, ns, e->d_text.p, e->d_bwt.p);
+    e->sort_stats = cx.stats;
+    if (rc) return rc;
+  }
+  {
+    StageTimer tm(e, 3);
+    if (!mtiles.empty())
+      B2_CUDA_CHECK(cudaMemcpyAsync(e->d_mtiles.p, mtiles.data(), mtiles.size() * sizeof(B2SortTile), cudaMemcpyHostToDevice, st));
+    B2_TRY(b2k_mtf(st, e->d_jobs.p, J, e->d_mtiles.p, (u32)mtiles.size(), e->d_bwt.p, e->d_idx.p, e->d_mtf.p));
+    e->stats.kernel_launches += 2;
+  }
+  const u32 total_groups = gpos;
+  {
+    StageTimer tm(e, 4);
+    B2_TRY(b2k_entropy(st, e->d_jobs.p, J, max_g, total_groups, e->d_mtf.p, e->d_rank3.p, e->d_rank4.p, e->d_sel.p,
+                       e->d_gcost.p, e->d_lens.p, e->d_cost.p, e->d_low.p, e->level));
+    e->stats.kernel_launches += 4;
+  }
+  {
+    StageTimer tm(e, 5);
+    u64 *d_total = (u64 *)(e->d_scalars.p + 2);
+    B2_TRY(b2k_bits_layout(st, e->d_jobs.p, J, d_total));
+    u64 total_words = 0;
+    B2_CUDA_CHECK(cudaMemcpyAsync(&total_words, d_total, sizeof(u64), cudaMemcpyDeviceToHost, st));
+    B2_CUDA_CHECK(cudaStreamSynchronize(st));
+    B2_TRY(e->d_bits.ensure(total_words + 64));
+    B2_CUDA_CHECK(cudaMemsetAsync(e->d_bits.p, 0, (total_words + 8) * sizeof(u32), st));
+    B2_TRY(b2k_pack(st, e->d_jobs.p, J, e->d_mtf.p, e->d_sel.p, e->d_lens.p, e->d_selpos.p, e->d_bits.p, e->level, total_groups));
+    e->stats.kernel_launches += 2;
+  }
+  B2_CUDA_CHECK(cudaMemcpyAsync(e->batch_jobs.data(), e->d_jobs.p, J * sizeof(B2Job), cudaMemcpyDeviceToHost, st));
+  B2_CUDA_CHECK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+inline u32 rotl1(u32 x) { return (x << 1) | (x >> 31); }
+
+// The whole stream, input resident on the device.  Output words land in e->d_out.
+int encode_device(b2_encoder *e, const u8 *d_in, u64 n, i64 size_hint, u64 *out_len) {
+  cudaStream_t st = e->st;
+  const int level = e->level;
+  e->stats.streams++; e->stats.input_bytes += n;
+  e->trace.clear(); e->chunks.clear(); e->nseg.clear(); e->seg.clear();
+  i64 win_lo, win_hi;
+  balance_window(level, win_lo, win_hi);
+  // ---- A1 chunk cutting, A3 segmentation -----------------------------------------------------
+  const u32 max_chunks = (u32)(n / (40000ull * level) + 16);
+  u32 n_chunks = 0;
+  {
+    StageTimer tm(e, 0);
+    B2_TRY(e->d_chunks.ensure(max_chunks));
+    B2_TRY(b2k_cut(st, d_in, n, size_hint, level, win_lo, win_hi, e->d_chunks.p, e->d_scalars.p, max_chunks));
+    B2_CUDA_CHECK(cudaMemcpyAsync(&n_chunks, e->d_scalars.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
+    B2_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (n_chunks > max_chunks) B2_FAIL(B2_ERR_INTERNAL, "chunk table overflow");
+    e->chunks.resize(n_chunks);
+    B2_CUDA_CHECK(cudaMemcpyAsync(e->chunks.data(), e->d_chunks.p, n_chunks * sizeof(B2Chunk), cudaMemcpyDeviceToHost, st));
+    if (level == 9) {
+      B2_TRY(e->d_seg.ensure((size_t)n_chunks * 2 * B2_MAX_SEG));
+      B2_TRY(e->d_nseg.ensure((size_t)n_chunks * 2));
+      B2_TRY(b2k_segment(st, d_in, e->d_chunks.p, n_chunks, e->d_T.p, e->d_seg.p, e->d_nseg.p));
+      e->nseg.resize((size_t)n_chunks * 2);
+      e->seg.resize((size_t)n_chunks * 2 * B2_MAX_SEG);
+      B2_CUDA_CHECK(cudaMemcpyAsync(e->nseg.data(), e->d_nseg.p, e->nseg.size() * sizeof(u32), cudaMemcpyDeviceToHost, st));
+      B2_CUDA_CHECK(cudaMemcpyAsync(e->seg.data(), e->d_seg.p, e->seg.size() * sizeof(u32), cudaMemcpyDeviceToHost, st));
+      e->stats.kernel_launches += 1;
+    }
+    B2_CUDA_CHECK(cudaStreamSynchronize(st));
+    e->stats.kernel_launches += 1;
+  }
+  e->stats.chunks += n_chunks;
+  // ---- output buffer -------------------------------------------------------------------------
+  const u64 out_bound = b2_bound(n) + 1024ull * n_chunks;
+  B2_TRY(e->d_out.ensure(out_bound / 4 + 16));
+  B2_CUDA_CHECK(cudaMemsetAsync(e->d_out.p, 0, (out_bound / 4 + 8) * sizeof(u32), st));
+  // ---- plan: tactics -> de-duplicated jobs ------------------------------------
+  std::vector<ChunkPlan> plans(n_chunks);
+  for (u32 c = 0; c < n_chunks; c++) {
+    ChunkPlan &P = plans[c];
+    P.start = e->chunks[c].start; P.len = e->chunks[c].len; P.cap = e->chunks[c].cap;
+    P.n_seg[0] = P.n_seg[1] = 0;
+  }
+  // ---- batches of whole chunks ---------------------------------------------------------------
+  u64 cur_bit = 32;               // after "BZh<level>"
+  u32 combined_crc = 0;
+  u32 c0 = 0;
+  while (c0 < n_chunks) {
+    std::vector<B2Job> jobs;
+    u64 positions = 0;
+    u32 c1 = c0;
+    while (c1 < n_chunks) {
+      ChunkPlan &P = plans[c1];
+      // slices of this chunk per tactic: (start, len) relative to the chunk
+      std::vector<std::pair<u32, u32>> slices[4];
+      int nt = 1;
+      slices[0].push_back({0, P.len});                                   // single (:1236, slices = 1)
+      if (level == 9) {
+        nt = 4;
+        u32 size = P.len / 4, stop = 0;                                  // parts_4 (:1238-1254)
+        for (u32 count = 1; count <= 4; count++) {
+          u32 start = stop;
+          stop = (count == 4) ? P.len : count * size;
+          slices[1].push_back({start, stop - start});
+        }
+        for (int k = 0; k < 2; k++) {                                    // segmented_1/2 (:1266-1291)
+          u32 ns = e->nseg[2 * c1 + k];
+          if (ns > B2_MAX_SEG) B2_FAIL(B2_ERR_INTERNAL, "segment table overflow");
+          P.n_seg[k] = ns;
+          const u32 *cuts = &e->seg[(size_t)(2 * c1 + k) * B2_MAX_SEG];
+          if (ns == 0) slices[2 + k].push_back({0, 0});                  // seg.Is_Empty -> one empty block (:1283-1284)
+          u32 index_start = 0;
+          for (u32 s = 0; s < ns; s++) { slices[2 + k].push_back({index_start, cuts[s] - index_start}); index_start = cuts[s]; }
+        }
+      }
+      // would this chunk overflow the batch?
+      std::map<std::pair<u32, u32>, u32> seen;
+      std::vector<B2Job> add;
+      u64 addpos = 0;
+      for (int t = 0; t < nt; t++) {
+        P.tactic_jobs[t].clear();
+        for (auto &sl : slices[t]) {
+          auto it = seen.find(sl);
+          u32 id;
+          if (it == seen.end()) {
+            id = (u32)(jobs.size() + add.size());
+            seen[sl] = id;
+            B2Job j; memset(&j, 0, sizeof j);
+            j.raw_off = P.start + sl.first; j.raw_len = sl.second;
+            add.push_back(j);
+            addpos += std::min<u64>((u64)sl.second * 5 / 4 + 24, (u64)level * 100000 + 80);
+          } else id = it->second;
+          P.tactic_jobs[t].push_back(id);
+        }
+      }
+      P.n_tactics = nt;
+      if (!jobs.empty() && (positions + addpos > e->batch_positions || jobs.size() + add.size() > e->batch_jobs_max)) break;
+      jobs.insert(jobs.end(), add.begin(), add.end());
+      positions += addpos;
+      c1++;
+    }
+    B2_TRY(run_batch(e, d_in, jobs));
+    // ---- serial resolve of winners over the chunks of this batch (:1305-1345) -----------------
+    std::vector<B2ConcatItem> items;
+    for (u32 c = c0; c < c1; c++) {
+      ChunkPlan &P = plans[c];
+      b2_chunk_trace tr; memset(&tr, 0, sizeof tr);
+      tr.start = P.start; tr.len = P.len; tr.dyn_capacity = P.cap; tr.n_seg1 = P.n_seg[0]; tr.n_seg2 = P.n_seg[1];
+      int best = 0;
+      const u32 in_bits = (u32)(cur_bit & 7);
+      for (int t = 0; t < P.n_tactics; t++) {
+        u64 bits = 0;
+        for (u32 id : P.tactic_jobs[t]) bits += e->batch_jobs[id].nbits;
+        tr.bits[t] = bits;
+        tr.bytes[t] = (in_bits + bits) >> 3;      // destination_index: whole bytes flushed
+      }
+      for (int t = 0; t < P.n_tactics; t++) if (tr.bytes[t] < tr.bytes[best]) best = t;
+      tr.winner = best;
+      for (u32 id : P.tactic_jobs[best]) {
+        const B2Job &b = e->batch_jobs[id];
+        items.push_back(B2ConcatItem{b.bits_off, b.nbits, cur_bit});
+        cur_bit += b.nbits;
+        combined_crc = rotl1(combined_crc) ^ b.crc;     // (:990)
+      }
+      e->trace.push_back(tr);
+    }
+    if ((cur_bit + 128) / 8 > out_bound) B2_FAIL(B2_ERR_INTERNAL, "output bound exceeded");
+    {
+      StageTimer tm(e, 6);
+      B2_TRY(e->d_items.ensure(items.size()));
+      B2_CUDA_CHECK(cudaMemcpyAsync(e->d_items.p, items.data(), items.size() * sizeof(B2ConcatItem), cudaMemcpyHostToDevice, st));
+      B2_TRY(b2k_concat(st, e->d_items.p, (u32)items.size(), e->d_bits.p, e->d_out.p));
+      B2_CUDA_CHECK(cudaStreamSynchronize(st));
+      e->stats.kernel_launches += 1;
+    }
+    c0 = c1;
+  }
+  // ---- header and footer (:1384-1407): 4 + 10 bytes, written through a tiny host staging ------
+  {
+    u8 head[4] = {'B', 'Z', 'h', (u8)('0' + level)};
+    // footer bits: 48-bit magic 0x177245385090 + 32-bit combined CRC at bit offset cur_bit
+    u8 foot[16]; memset(foot, 0, sizeof foot);
+    u64 first_byte = cur_bit >> 3;
+    u32 sh = (u32)(cur_bit & 7);
+    const u8 fm[10] = {0x17, 0x72, 0x45, 0x38, 0x50, 0x90, (u8)(combined_crc >> 24), (u8)(combined_crc >> 16),
+                       (u8)(combined_crc >> 8), (u8)combined_crc};
+    for (int i = 0; i < 10; i++) {
+      foot[i] |= (u8)(fm[i] >> sh);
+      if (sh) foot[i + 1] |= (u8)(fm[i] << (8 - sh));
+    }
+    u64 total_bits = cur_bit + 80;
+    u64 total_bytes = (total_bits + 7) >> 3;
+    // merge the partial first footer byte with the last data byte already on the device
+    u8 last = 0;
+    u8 *d_out8 = (u8 *)e->d_out.p;
+    if (sh) B2_CUDA_CHECK(cudaMemcpyAsync(&last, d_out8 + first_byte, 1, cudaMemcpyDeviceToHost, st));
+    B2_CUDA_CHECK(cudaStreamSynchronize(st));
+    foot[0] |= last;
+    B2_CUDA_CHECK(cudaMemcpyAsync(d_out8 + first_byte, foot, (size_t)(total_bytes - first_byte), cudaMemcpyHostToDevice, st));
+    B2_CUDA_CHECK(cudaMemcpyAsync(d_out8, head, 4, cudaMemcpyHostToDevice, st));
+    B2_CUDA_CHECK(cudaStreamSynchronize(st));
+    *out_len = total_bytes;
+  }
+  e->stats.sort_rounds = e->sort_stats.rounds;
+  e->stats.sort_elems_round0 = e->sort_stats.sorted_elems_round0;
+  e->stats.sort_elems_later = e->sort_stats.sorted_elems_later;
+  e->stats.scatter_launches = e->sort_stats.scatter_launches;
+  e->stats.scatter_elems = e->sort_stats.scatter_elems;
+  e->stats.scatter_ms = e->sort_stats.scatter_ms;
+  return 0;
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+const char *b2_last_error(void) { return g_last_error.c_str(); }
+
+uint64_t b2_bound(uint64_t n) { return n + n / 50 + 4096; }
+
+int b2_create(int level, int device, b2_encoder **out) {
+  if (!out) B2_FAIL(B2_ERR_ARGUMENT, "out is NULL");
+  *out = nullptr;
+  if (level != 1 && level != 4 && level != 9) B2_FAIL(B2_ERR_ARGUMENT, "level must be 1, 4 or 9");
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0) B2_FAIL(B2_ERR_CUDA, "no CUDA device available (b2gpu has no CPU fallback)");
+  if (device < 0 || device >= ndev) B2_FAIL(B2_ERR_ARGUMENT, "bad device index");
+  B2_CUDA_CHECK(cudaSetDevice(device));
+  b2_encoder *e = new b2_encoder();
+  e->level = level; e->device = device;
+  memset(&e->stats, 0, sizeof e->stats);
+  memset(&e->sort_stats, 0, sizeof e->sort_stats);
+  if (const char *s = getenv("B2GPU_BATCH_POSITIONS")) { long long v = atoll(s); if (v >= (1 << 20)) e->batch_positions = (size_t)v; }
+  if (const char *s = getenv("B2GPU_BATCH_JOBS")) { long long v = atoll(s); if (v >= 8) e->batch_jobs_max = (size_t)v; }
+  B2_CUDA_CHECK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
+  B2_CUDA_CHECK(cudaEventCreate(&e->ev[0])); B2_CUDA_CHECK(cudaEventCreate(&e->ev[1]));
+  // constant tables
+  B2CrcTables *ct = new B2CrcTables();
+  b2k_make_crc_tables(ct);
+  int rc = e->d_ct.ensure(1);
+  if (!rc) { cudaMemcpy(e->d_ct.p, ct, sizeof(B2CrcTables), cudaMemcpyHostToDevice); }
+  delete ct;
+  if (rc) { b2_destroy(e); return rc; }
+  // T[c] = -(p * Log (p)), p = Real (c) * inv_window_size, window 16_000 (data_segmentation.adb:44-50)
+  std::vector<double> T(16002, 0.0);
+  const double inv = 1.0 / 16000.0;
+  for (int c = 1; c <= 16001; c++) { double p = (double)c * inv; T[c] = -(p * std::log(p)); }
+  rc = e->d_T.ensure(T.size());
+  if (!rc) cudaMemcpy(e->d_T.p, T.data(), T.size() * sizeof(double), cudaMemcpyHostToDevice);
+  if (!rc) rc = e->d_scalars.ensure(16);
+  if (rc) { b2_destroy(e); return rc; }
+  *out = e;
+  return 0;
+}
+
+void b2_destroy(b2_encoder *e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  if (e->st) cudaStreamSynchronize(e->st);
+  e->d_ct.release(); e->d_T.release(); e->d_in.release(); e->d_out.release(); e->d_chunks.release();
+  e->d_scalars.release(); e->d_seg.release(); e->d_nseg.release(); e->d_jobs.release(); e->d_text.release();
+  e->d_bwt.release(); e->d_idx.release(); e->d_keysA.release(); e->d_keysB.release(); e->d_valsA.release();
+  e->d_valsB.release(); e->d_rank.release(); e->d_grp.release(); e->d_tiles.release(); e->d_mtiles.release();
+  e->d_sj.release(); e->d_hist.release(); e->d_tile_head.release(); e->d_carry.release(); e->d_unsorted.release();
+  e->d_mtf.release(); e->d_rank3.release(); e->d_rank4.release(); e->d_sel.release(); e->d_selpos.release();
+  e->d_lens.release(); e->d_gcost.release(); e->d_cost.release(); e->d_low.release(); e->d_bits.release();
+  e->d_items.release();
+  if (e->h_unsorted) cudaFreeHost(e->h_unsorted);
+  if (e->ev[0]) cudaEventDestroy(e->ev[0]);
+  if (e->ev[1]) cudaEventDestroy(e->ev[1]);
+  if (e->st) cudaStreamDestroy(e->st);
+  delete e;
+}
+
+int b2_encode_stream_device(b2_encoder *e, const uint8_t *d_in, uint64_t n, int64_t size_hint,
+                            uint8_t *d_out, uint64_t out_cap, uint64_t *out_len) {
+  if (!e || !out_len || (n && !d_in)) B2_FAIL(B2_ERR_ARGUMENT, "bad argument");
+  B2_CUDA_CHECK(cudaSetDevice(e->device));
+  u64 len = 0;
+  B2_TRY(encode_device(e, d_in, n, size_hint, &len));
+  *out_len = len;
+  if (len > out_cap) B2_FAIL(B2_ERR_OUTPUT_TOO_SMALL, "output buffer too small");
+  if (d_out) {
+    B2_CUDA_CHECK(cudaMemcpyAsync(d_out, e->d_out.p, len, cudaMemcpyDeviceToDevice, e->st));
+    B2_CUDA_CHECK(cudaStreamSynchronize(e->st));
+  }
+  return 0;
+}
+
+int b2_encode_stream(b2_encoder *e, const uint8_t *in, uint64_t n, int64_t size_hint,
+                     uint8_t *out, uint64_t out_cap, uint64_t *out_len) {
+  if (!e || !out_len || (n && !in)) B2_FAIL(B2_ERR_ARGUMENT, "bad argument");
+  B2_CUDA_CHECK(cudaSetDevice(e->device));
+  B2_TRY(e->d_in.ensure(n + 256));
+  {
+    StageTimer tm(e, 7);
+    if (n) B2_CUDA_CHECK(cudaMemcpyAsync(e->d_in.p, in, n, cudaMemcpyHostToDevice, e->st));
+    B2_CUDA_CHECK(cudaMemsetAsync(e->d_in.p + n, 0, 128, e->st));
+  }
+  u64 len = 0;
+  B2_TRY(encode_device(e, e->d_in.p, n, size_hint, &len));
+  *out_len = len;
+  if (len > out_cap) B2_FAIL(B2_ERR_OUTPUT_TOO_SMALL, "output buffer too small");
+  {
+    StageTimer tm(e, 7);
+    if (out) B2_CUDA_CHECK(cudaMemcpyAsync(out, e->d_out.p, len, cudaMemcpyDeviceToHost, e->st));
+    B2_CUDA_CHECK(cudaStreamSynchronize(e->st));
+  }
+  return 0;
+}
+
+int b2_set_timing(b2_encoder *e, int on) { if (!e) return B2_ERR_ARGUMENT; e->timing = on != 0; return 0; }
+int b2_get_stats(b2_encoder *e, b2_stats *out) { if (!e || !out) return B2_ERR_ARGUMENT; *out = e->stats; return 0; }
+int b2_reset_stats(b2_encoder *e) {
+  if (!e) return B2_ERR_ARGUMENT;
+  memset(&e->stats, 0, sizeof e->stats); memset(&e->sort_stats, 0, sizeof e->sort_stats);
+  return 0;
+}
+
+int b2_get_trace(b2_encoder *e, b2_chunk_trace *out, uint64_t cap, uint64_t *n) {
+  if (!e || !n) return B2_ERR_ARGUMENT;
+  *n = e->trace.size();
+  for (size_t i = 0; i < e->trace.size() && i < cap; i++) out[i] = e->trace[i];
+  return 0;
+}
+
+int b2_get_segments(b2_encoder *e, uint64_t chunk, int profile, uint32_t *cuts, uint32_t cap, uint32_t *n) {
+  if (!e || !n || profile < 0 || profile > 1) return B2_ERR_ARGUMENT;
+  if (chunk * 2 + profile >= e->nseg.size()) { *n = 0; return B2_ERR_ARGUMENT; }
+  u32 ns = e->nseg[chunk * 2 + profile];
+  *n = ns;
+  for (u32 i = 0; i < ns && i < cap && i < B2_MAX_SEG; i++) cuts[i] = e->seg[(chunk * 2 + profile) * B2_MAX_SEG + i];
+  return 0;
+}
+
+int b2_dbg_block(b2_encoder *e, const uint8_t *raw, uint32_t len, uint8_t *rle_out, uint8_t *bwt_out,
+                 uint16_t *mtf_out, uint8_t *sel_out, uint8_t *lens_out, uint8_t *bits_out, uint64_t bits_cap,
+                 b2_block_info *info) {
+  if (!e || (len && !raw)) B2_FAIL(B2_ERR_ARGUMENT, "bad argument");
+  B2_CUDA_CHECK(cudaSetDevice(e->device));
+  B2_TRY(e->d_in.ensure((size_t)len + 256));
+  if (len) B2_CUDA_CHECK(cudaMemcpyAsync(e->d_in.p, raw, len, cudaMemcpyHostToDevice, e->st));
+  B2_CUDA_CHECK(cudaMemsetAsync(e->d_in.p + len, 0, 128, e->st));
+  std::vector<B2Job> jobs(1);
+  memset(&jobs[0], 0, sizeof(B2Job));
+  jobs[0].raw_off = 0; jobs[0].raw_len = len;
+  B2_TRY(run_batch(e, e->d_in.p, jobs));
+  const B2Job &b = e->batch_jobs[0];
+  cudaStream_t st = e->st;
+  if (rle_out && b.n) B2_CUDA_CHECK(cudaMemcpyAsync(rle_out, e->d_text.p + b.pos_off, b.n, cudaMemcpyDeviceToHost, st));
+  if (bwt_out && b.n) B2_CUDA_CHECK(cudaMemcpyAsync(bwt_out, e->d_bwt.p + b.pos_off, b.n, cudaMemcpyDeviceToHost, st));
+  if (mtf_out) B2_CUDA_CHECK(cudaMemcpyAsync(mtf_out, e->d_mtf.p + b.mtf_off, (size_t)b.n_mtf * 2, cudaMemcpyDeviceToHost, st));
+  const u32 total_groups = b.n / B2_GROUP_SIZE + 2;   // single job: grp arena size == its own bound
+  if (sel_out) B2_CUDA_CHECK(cudaMemcpyAsync(sel_out, e->d_sel.p + (size_t)b.best * total_groups + b.grp_off, b.n_groups, cudaMemcpyDeviceToHost, st));
+  if (lens_out) B2_CUDA_CHECK(cudaMemcpyAsync(lens_out, e->d_lens.p + (size_t)b.best * (B2_MAX_CODERS * B2_MAX_ALPHA), B2_MAX_CODERS * B2_MAX_ALPHA, cudaMemcpyDeviceToHost, st));
+  u64 nbytes = (b.nbits + 7) >> 3;
+  if (bits_out) {
+    if (nbytes > bits_cap) B2_FAIL(B2_ERR_OUTPUT_TOO_SMALL, "bits_out too small");
+    B2_CUDA_CHECK(cudaMemcpyAsync(bits_out, (u8 *)(e->d_bits.p + b.bits_off), nbytes, cudaMemcpyDeviceToHost, st));
+  }
+  B2_CUDA_CHECK(cudaStreamSynchronize(st));
+  if (info) {
+    int max_len, sw, ec;
+    b2_triple(e->level, (int)b.best, max_len, sw, ec);
+    info->n_rle = b.n; info->origin = b.origin; info->crc = b.crc; info->n_mtf = b.n_mtf; info->eob = b.n_used + 1;
+    info->n_used = b.n_used; info->n_sel = b.n_groups; info->ec_count = (u32)ec; info->max_len = (u32)max_len;
+    info->sample_width = (u32)sw; info->cost = b.best_cost; info->pad = 0; info->bits = b.nbits;
+  }
+  return 0;
+}
+
+}  // extern "C"

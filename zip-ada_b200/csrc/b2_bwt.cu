@@ -1,0 +1,430 @@
+// Stage A6: Burrows-Wheeler rotation sort for a batch of blocks.
+//
+// Reference: zip_lib/bzip2-encoding.adb:219-296.  The reference heap-sorts rotation offsets with
+// an O(N) comparator that is a total order (:229-255), so the sorted matrix, its last column and
+// the origin pointer are unique functions of the block; any sort is admissible.
+//
+// Here: cyclic prefix doubling.  Round 0 sorts every rotation by its first 8 bytes (64-bit key,
+// 8 LSD radix passes of 8 bits); round r >= 1 sorts by the 40-bit key (rank[i] << 20 | rank[(i+h)
+// mod n]) with 5 passes, h = 8, 16, ...  A rank is the row index of the first row of a class, so
+// equal prefixes share a rank and a block is finished when every class is a single row or when the
+// compared prefix covers the whole rotation (periodic blocks: the classes are then sets of EQUAL
+// rotations; their last-column bytes coincide and the origin pointer is the first row of the class
+// of rotation 0, because the reference orders equal rotations by offset and rotation 0 has offset
+// 0, :254, :276-279).  All blocks of a batch are sorted together: every radix pass is segmented by
+// block through a tile table, so no block id is needed in the key.
+//
+// Radix pass = histogram (8 B/elt read) + per-block scan (tiny) + scatter (12 B/elt read, 12 B/elt
+// write, staged through shared memory so the writes leave as runs).
+#include "b2_common.cuh"
+#include "b2_kernels.h"
+
+#define ST_THREADS 256
+#define ST_ITEMS 16
+#define ST_TILE (ST_THREADS * ST_ITEMS)
+#define ST_WARPS (ST_THREADS / 32)
+#define ST_WCHUNK (32 * ST_ITEMS)      // elements per warp
+
+// ---- round-0 keys: first 8 bytes of each rotation, cyclic ------------------------------------
+__global__ void __launch_bounds__(ST_THREADS)
+k_keys0(const B2SortTile *__restrict__ tiles, const B2Job *__restrict__ jobs, const u8 *__restrict__ text,
+        u64 *__restrict__ keys, u32 *__restrict__ vals) {
+  const B2SortTile tl = tiles[blockIdx.x];
+  const B2Job &job = jobs[tl.job];
+  const u32 n = job.n, off = job.pos_off;
+  const u8 *tx = text + off;
+#pragma unroll 4
+  for (int k = 0; k < ST_ITEMS; k++) {
+    u32 i = tl.start + threadIdx.x + k * ST_THREADS;
+    if (i < n) {
+      u64 key = 0;
+      if (i + 8 <= n) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) key = (key << 8) | tx[i + j];
+      } else {
+        u32 p = i;
+#pragma unroll
+        for (int j = 0; j < 8; j++) { key = (key << 8) | tx[p]; p++; if (p >= n) p = 0; }
+      }
+      keys[off + i] = key;
+      vals[off + i] = i;
+    }
+  }
+}
+
+// ---- histogram of one digit per tile -----------------------------------------------------------
+__global__ void __launch_bounds__(ST_THREADS)
+k_hist(const B2SortTile *__restrict__ tiles, const B2Job *__restrict__ jobs, const u64 *__restrict__ keys,
+       int shift, u32 *__restrict__ hist) {
+  __shared__ u32 h[256];
+  const B2SortTile tl = tiles[blockIdx.x];
+  const B2Job &job = jobs[tl.job];
+  const u32 n = job.n;
+  const u64 *kp = keys + job.pos_off;
+  h[threadIdx.x] = 0;
+  __syncthreads();
+#pragma unroll 4
+  for (int k = 0; k < ST_ITEMS; k++) {
+    u32 i = tl.start + threadIdx.x + k * ST_THREADS;
+    if (i < n) atomicAdd(&h[(u32)(kp[i] >> shift) & 255u], 1u);
+  }
+  __syncthreads();
+  hist[(size_t)blockIdx.x * 256 + threadIdx.x] = h[threadIdx.x];
+}
+
+// ---- per-block exclusive scan over (digit major, tile minor) ------------------------------------
+__global__ void __launch_bounds__(256)
+k_scan(const B2SortJob *__restrict__ sj, u32 *__restrict__ hist) {
+  __shared__ u32 sm[40];
+  const B2SortJob s = sj[blockIdx.x];
+  const u32 d = threadIdx.x;
+  u32 total = 0;
+  for (u32 t = 0; t < s.ntiles; t++) {
+    size_t idx = (size_t)(s.tile0 + t) * 256 + d;
+    u32 c = hist[idx];
+    hist[idx] = total;
+    total += c;
+  }
+  u32 base = block_excl_add(total, sm, nullptr);
+  for (u32 t = 0; t < s.ntiles; t++) hist[(size_t)(s.tile0 + t) * 256 + d] += base;
+}
+
+// ---- stable scatter of one digit ---------------------------------------------------------------
+// Dynamic shared memory: keys[ST_TILE] u64, vals[ST_TILE] u32, warp_cnt[ST_WARPS][256] u32,
+// tile_start[256] u32, g_off[256] u32, scan scratch.
+struct ScatterSmem {
+  u64 keys[ST_TILE];
+  u32 vals[ST_TILE];
+  u32 warp_cnt[ST_WARPS][256];
+  u32 tile_start[256];
+  u32 g_off[256];
+  u32 scan[40];
+};
+
+__global__ void __launch_bounds__(ST_THREADS, 2)
+k_scatter(const B2SortTile *__restrict__ tiles, const B2Job *__restrict__ jobs,
+          const u64 *__restrict__ keys_in, const u32 *__restrict__ vals_in,
+          u64 *__restrict__ keys_out, u32 *__restrict__ vals_out, int shift, const u32 *__restrict__ hist) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ScatterSmem &S = *reinterpret_cast<ScatterSmem *>(smem_raw);
+  const B2SortTile tl = tiles[blockIdx.x];
+  const B2Job &job = jobs[tl.job];
+  const u32 n = job.n, off = job.pos_off;
+  const u32 tid = threadIdx.x, w = warp_id(), l = lane_id();
+  const u32 lt_mask = (1u << l) - 1u;
+  for (int i = tid; i < ST_WARPS * 256; i += ST_THREADS) (&S.warp_cnt[0][0])[i] = 0;
+  S.g_off[tid] = hist[(size_t)blockIdx.x * 256 + tid];
+  __syncthreads();
+  u64 key[ST_ITEMS];
+  u32 val[ST_ITEMS];
+  u32 rk[ST_ITEMS];   // rank within (warp, digit) | digit << 16 ; 0xFFFFFFFF = invalid
+  const u32 wbase = tl.start + w * ST_WCHUNK;
+#pragma unroll
+  for (int k = 0; k < ST_ITEMS; k++) {
+    u32 i = wbase + k * 32 + l;
+    if (i < n) { key[k] = keys_in[off + i]; val[k] = vals_in[off + i]; }
+    else { key[k] = 0; val[k] = 0; }
+  }
+#pragma unroll
+  for (int k = 0; k < ST_ITEMS; k++) {
+    u32 i = wbase + k * 32 + l;
+    bool valid = i < n;
+    u32 d = (u32)(key[k] >> shift) & 255u;
+    u32 mk = valid ? d : (256u + l);
+    u32 peers = __match_any_sync(0xffffffffu, mk);
+    u32 r = __popc(peers & lt_mask);
+    u32 base = valid ? S.warp_cnt[w][d] : 0;
+    __syncwarp();
+    if (valid && r == 0) S.warp_cnt[w][d] = base + __popc(peers);
+    __syncwarp();
+    rk[k] = valid ? ((base + r) | (d << 16)) : 0xFFFFFFFFu;
+  }
+  __syncthreads();
+  // per digit: exclusive over warps, tile count
+  {
+    u32 run = 0;
+#pragma unroll
+    for (int ww = 0; ww < ST_WARPS; ww++) { u32 c = S.warp_cnt[ww][tid]; S.warp_cnt[ww][tid] = run; run += c; }
+    u32 ts = block_excl_add(run, S.scan, nullptr);
+    S.tile_start[tid] = ts;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < ST_ITEMS; k++) {
+    if (rk[k] != 0xFFFFFFFFu) {
+      u32 d = rk[k] >> 16;
+      u32 lp = S.tile_start[d] + S.warp_cnt[w][d] + (rk[k] & 0xFFFFu);
+      S.keys[lp] = key[k];
+      S.vals[lp] = val[k];
+    }
+  }
+  __syncthreads();
+  const u32 cnt = (n - tl.start) < ST_TILE ? (n - tl.start) : ST_TILE;
+#pragma unroll 4
+  for (int k = 0; k < ST_ITEMS; k++) {
+    u32 q = tid + k * ST_THREADS;
+    if (q < cnt) {
+      u64 kk = S.keys[q];
+      u32 d = (u32)(kk >> shift) & 255u;
+      u32 dst = off + S.g_off[d] + (q - S.tile_start[d]);
+      keys_out[dst] = kk;
+      vals_out[dst] = S.vals[q];
+    }
+  }
+}
+
+// ---- class heads -> ranks ---------------------------------------------------------------------
+__global__ void __launch_bounds__(ST_THREADS)
+k_heads(const B2SortTile *__restrict__ tiles, const B2Job *__restrict__ jobs, const u64 *__restrict__ keys,
+        i32 *__restrict__ tile_head) {
+  __shared__ i32 last;
+  const B2SortTile tl = tiles[blockIdx.x];
+  const B2Job &job = jobs[tl.job];
+  const u32 n = job.n;
+  const u64 *kp = keys + job.pos_off;
+  if (threadIdx.x == 0) last = -1;
+  __syncthreads();
+  i32 mine = -1;
+#pragma unroll 4
+  for (int k = 0; k < ST_ITEMS; k++) {
+    u32 i = tl.start + threadIdx.x + k * ST_THREADS;
+    if (i < n && (i == 0 || kp[i] != kp[i - 1])) mine = (i32)i;
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) mine = max(mine, __shfl_xor_sync(0xffffffffu, mine, o));
+  if (lane_id() == 0 && mine >= 0) atomicMax(&last, mine);
+  __syncthreads();
+  if (threadIdx.x == 0) tile_head[blockIdx.x] = last;
+}
+
+__global__ void k_scan_heads(const B2SortJob *__restrict__ sj, u32 n_sj, B2Job *jobs,
+                             const i32 *__restrict__ tile_head, i32 *__restrict__ carry_in) {
+  u32 s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_sj) return;
+  const B2SortJob j = sj[s];
+  i32 run = -1;
+  for (u32 t = 0; t < j.ntiles; t++) {
+    carry_in[j.tile0 + t] = run;
+    i32 h = tile_head[j.tile0 + t];
+    if (h >= 0) run = h;
+  }
+  jobs[j.job].unsorted = 0;
+}
+
+__global__ void __launch_bounds__(ST_THREADS)
+k_ranks(const B2SortTile *__restrict__ tiles, B2Job *jobs, const u64 *__restrict__ keys,
+        const u32 *__restrict__ sa, const i32 *__restrict__ carry_in, u32 *__restrict__ rank, u32 *__restrict__ grp) {
+  __shared__ i32 wl[ST_WARPS];
+  __shared__ u32 nonhead;
+  const B2SortTile tl = tiles[blockIdx.x];
+  B2Job &job = jobs[tl.job];
+  const u32 n = job.n, off = job.pos_off;
+  const u64 *kp = keys + off;
+  const u32 w = warp_id(), l = lane_id();
+  const u32 wbase = tl.start + w * ST_WCHUNK;
+  if (threadIdx.x == 0) nonhead = 0;
+  u32 masks[ST_ITEMS];
+  i32 wlast = -1;
+  u32 nh = 0;
+#pragma unroll
+  for (int k = 0; k < ST_ITEMS; k++) {
+    u32 i = wbase + k * 32 + l;
+    bool valid = i < n;
+    bool flag = valid && (i == 0 || kp[i] != kp[i - 1]);
+    u32 m = __ballot_sync(0xffffffffu, flag);
+    masks[k] = m;
+    if (m) wlast = (i32)(wbase + k * 32 + (31 - __clz(m)));
+    if (valid && !flag) nh++;
+  }
+  if (l == 0) wl[w] = wlast;
+  __syncthreads();
+  i32 carry = carry_in[blockIdx.x];
+  for (u32 ww = 0; ww < w; ww++) carry = max(carry, wl[ww]);
+  const u32 le_mask = 0xFFFFFFFFu >> (31 - l);
+#pragma unroll
+  for (int k = 0; k < ST_ITEMS; k++) {
+    u32 i = wbase + k * 32 + l;
+    u32 m = masks[k];
+    u32 mm = m & le_mask;
+    i32 head = mm ? (i32)(wbase + k * 32 + (31 - __clz(mm))) : carry;
+    if (m) carry = (i32)(wbase + k * 32 + (31 - __clz(m)));
+    if (i < n) {
+      rank[off + sa[off + i]] = (u32)head;
+      grp[off + i] = (u32)head;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) nh += __shfl_xor_sync(0xffffffffu, nh, o);
+  if (l == 0 && nh) atomicAdd(&nonhead, nh);
+  __syncthreads();
+  if (threadIdx.x == 0 && nonhead) atomicAdd(&job.unsorted, nonhead);
+}
+
+__global__ void k_collect_unsorted(const B2SortJob *__restrict__ sj, u32 n_sj, const B2Job *__restrict__ jobs,
+                                   u32 *__restrict__ out) {
+  u32 s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < n_sj) out[s] = jobs[sj[s].job].unsorted;
+}
+
+// ---- doubling keys ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(ST_THREADS)
+k_keys(const B2SortTile *__restrict__ tiles, const B2Job *__restrict__ jobs, const u32 *__restrict__ sa,
+       const u32 *__restrict__ grp, const u32 *__restrict__ rank, u64 *__restrict__ keys, u32 h) {
+  const B2SortTile tl = tiles[blockIdx.x];
+  const B2Job &job = jobs[tl.job];
+  const u32 n = job.n, off = job.pos_off;
+  const u32 hh = h % n;
+#pragma unroll 4
+  for (int k = 0; k < ST_ITEMS; k++) {
+    u32 i = tl.start + threadIdx.x + k * ST_THREADS;
+    if (i < n) {
+      u32 s = sa[off + i] + hh;
+      if (s >= n) s -= n;
+      keys[off + i] = ((u64)grp[off + i] << 20) | (u64)rank[off + s];
+    }
+  }
+}
+
+// ---- last column + origin pointer (bzip2-encoding.adb:273-280) ---------------------------------
+__global__ void __launch_bounds__(ST_THREADS)
+k_bwt_out(const B2SortTile *__restrict__ tiles, B2Job *jobs, const u32 *__restrict__ sa,
+          const u8 *__restrict__ text, const u32 *__restrict__ rank, u8 *__restrict__ bwt) {
+  const B2SortTile tl = tiles[blockIdx.x];
+  B2Job &job = jobs[tl.job];
+  const u32 n = job.n, off = job.pos_off;
+#pragma unroll 4
+  for (int k = 0; k < ST_ITEMS; k++) {
+    u32 i = tl.start + threadIdx.x + k * ST_THREADS;
+    if (i < n) {
+      u32 s = sa[off + i];
+      bwt[off + i] = text[off + (s == 0 ? n - 1 : s - 1)];
+      if (i == 0) job.origin = rank[off];   // first row of the class of rotation 0
+    }
+  }
+}
+
+// =============================================================================================
+// Host driver
+// =============================================================================================
+#include <vector>
+
+static int build_tiles(const std::vector<u32> &job_ids, const std::vector<u32> &job_n,
+                       std::vector<B2SortTile> &tiles, std::vector<B2SortJob> &sj) {
+  tiles.clear(); sj.clear();
+  for (size_t k = 0; k < job_ids.size(); k++) {
+    u32 n = job_n[k];
+    if (n == 0) continue;
+    B2SortJob s; s.job = job_ids[k]; s.tile0 = (u32)tiles.size(); s.ntiles = (n + ST_TILE - 1) / ST_TILE;
+    for (u32 t = 0; t < s.ntiles; t++) tiles.push_back(B2SortTile{s.job, t * ST_TILE});
+    sj.push_back(s);
+  }
+  return 0;
+}
+
+struct EvPair { cudaEvent_t a, b; };
+
+int b2k_bwt_batch(B2SortCtx *cx, cudaStream_t st, B2Job *d_jobs, const std::vector<u32> &job_ids,
+                  const std::vector<u32> &job_n, const u8 *d_text, u8 *d_bwt) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    B2_CUDA_CHECK(cudaFuncSetAttribute(k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
+    attr_set = true;
+  }
+  std::vector<B2SortTile> tiles;
+  std::vector<B2SortJob> sj;
+  std::vector<u32> ids = job_ids, ns = job_n;
+  build_tiles(ids, ns, tiles, sj);
+  if (tiles.empty()) return 0;
+  if (tiles.size() > cx->max_tiles || sj.size() > cx->max_jobs) { b2_set_error(__FILE__, __LINE__, "sort workspace too small"); return 11; }
+  u64 *kA = cx->keysA, *kB = cx->keysB;
+  u32 *vA = cx->valsA, *vB = cx->valsB;
+  std::vector<EvPair> evs;
+  auto upload = [&]() -> int {
+    B2_CUDA_CHECK(cudaMemcpyAsync(cx->d_tiles, tiles.data(), tiles.size() * sizeof(B2SortTile), cudaMemcpyHostToDevice, st));
+    B2_CUDA_CHECK(cudaMemcpyAsync(cx->d_sj, sj.data(), sj.size() * sizeof(B2SortJob), cudaMemcpyHostToDevice, st));
+    return 0;
+  };
+  auto radix_pass = [&](int shift) -> int {
+    u32 nt = (u32)tiles.size();
+    k_hist<<<nt, ST_THREADS, 0, st>>>(cx->d_tiles, d_jobs, kA, shift, cx->d_hist);
+    k_scan<<<(u32)sj.size(), 256, 0, st>>>(cx->d_sj, cx->d_hist);
+    EvPair ev{nullptr, nullptr};
+    if (cx->timing) { cudaEventCreate(&ev.a); cudaEventCreate(&ev.b); cudaEventRecord(ev.a, st); }
+    k_scatter<<<nt, ST_THREADS, sizeof(ScatterSmem), st>>>(cx->d_tiles, d_jobs, kA, vA, kB, vB, shift, cx->d_hist);
+    if (cx->timing) { cudaEventRecord(ev.b, st); evs.push_back(ev); }
+    B2_CUDA_CHECK(cudaGetLastError());
+    std::swap(kA, kB); std::swap(vA, vB);
+    u64 el = 0;
+    for (auto &s : sj) el += ns[&s - &sj[0]];
+    cx->stats.scatter_launches++;
+    cx->stats.scatter_elems += el;
+    return 0;
+  };
+  auto ranks = [&]() -> int {
+    u32 nt = (u32)tiles.size(), nj = (u32)sj.size();
+    k_heads<<<nt, ST_THREADS, 0, st>>>(cx->d_tiles, d_jobs, kA, cx->d_tile_head);
+    k_scan_heads<<<(nj + 127) / 128, 128, 0, st>>>(cx->d_sj, nj, d_jobs, cx->d_tile_head, cx->d_carry);
+    k_ranks<<<nt, ST_THREADS, 0, st>>>(cx->d_tiles, d_jobs, kA, vA, cx->d_carry, cx->rank, cx->grp);
+    k_collect_unsorted<<<(nj + 127) / 128, 128, 0, st>>>(cx->d_sj, nj, d_jobs, cx->d_unsorted);
+    B2_CUDA_CHECK(cudaGetLastError());
+    B2_CUDA_CHECK(cudaMemcpyAsync(cx->h_unsorted, cx->d_unsorted, nj * sizeof(u32), cudaMemcpyDeviceToHost, st));
+    B2_CUDA_CHECK(cudaStreamSynchronize(st));
+    return 0;
+  };
+
+  // compact per-active-job n (ns) aligned with sj
+  {
+    std::vector<u32> ids2, ns2;
+    for (size_t k = 0; k < ids.size(); k++) if (ns[k] > 0) { ids2.push_back(ids[k]); ns2.push_back(ns[k]); }
+    ids.swap(ids2); ns.swap(ns2);
+  }
+  int rc;
+  if ((rc = upload())) return rc;
+  {
+    u64 el = 0; for (u32 x : ns) el += x;
+    cx->stats.sorted_elems_round0 += el;
+  }
+  k_keys0<<<(u32)tiles.size(), ST_THREADS, 0, st>>>(cx->d_tiles, d_jobs, d_text, kA, vA);
+  for (int p = 0; p < 8; p++) if ((rc = radix_pass(8 * p))) return rc;
+  if ((rc = ranks())) return rc;
+  cx->stats.rounds++;
+  u64 reflect = 8;
+  for (;;) {
+    // split finished / unfinished
+    std::vector<u32> fin_ids, fin_n, go_ids, go_n;
+    for (size_t k = 0; k < ids.size(); k++) {
+      bool done = cx->h_unsorted[k] == 0 || reflect >= ns[k];
+      if (done) { fin_ids.push_back(ids[k]); fin_n.push_back(ns[k]); }
+      else { go_ids.push_back(ids[k]); go_n.push_back(ns[k]); }
+    }
+    if (!fin_ids.empty()) {
+      build_tiles(fin_ids, fin_n, tiles, sj);
+      if ((rc = upload())) return rc;
+      k_bwt_out<<<(u32)tiles.size(), ST_THREADS, 0, st>>>(cx->d_tiles, d_jobs, vA, d_text, cx->rank, d_bwt);
+      B2_CUDA_CHECK(cudaGetLastError());
+    }
+    if (go_ids.empty()) break;
+    ids.swap(go_ids); ns.swap(go_n);
+    build_tiles(ids, ns, tiles, sj);
+    if ((rc = upload())) return rc;
+    {
+      u64 el = 0; for (u32 x : ns) el += x;
+      cx->stats.sorted_elems_later += el;
+    }
+    k_keys<<<(u32)tiles.size(), ST_THREADS, 0, st>>>(cx->d_tiles, d_jobs, vA, cx->grp, cx->rank, kA, (u32)(reflect));
+    for (int p = 0; p < 5; p++) if ((rc = radix_pass(8 * p))) return rc;
+    if ((rc = ranks())) return rc;
+    cx->stats.rounds++;
+    reflect *= 2;
+  }
+  if (cx->timing) {
+    B2_CUDA_CHECK(cudaStreamSynchronize(st));
+    for (auto &e : evs) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e.a, e.b);
+      cx->stats.scatter_ms += ms;
+      cudaEventDestroy(e.a); cudaEventDestroy(e.b);
+    }
+  }
+  return 0;
+}

@@ -1,0 +1,75 @@
+// Host-callable launchers of the b2gpu kernels (internal; the public boundary is include/b2gpu.h).
+#pragma once
+#include "b2_common.cuh"
+
+struct B2Chunk { u64 start; u32 len; u32 cap; u32 pad; u32 pad2; };
+
+struct B2CrcTables {
+  u32 byte_tab[256];      // bzip2.adb:34-100 table
+  u32 xp_thread[1024];    // x^(8*16*(1023-t)) mod P
+  u32 x_tile;             // x^(8*16384)
+  u32 xinv_a[1024];       // x^(-128*a)
+  u32 xinv_b[16];         // x^(-8*b)
+  u32 pw2[32];            // x^(8*2^k)
+};
+
+struct B2SortTile { u32 job; u32 start; };
+
+// statistics of the BWT sort for the roofline report
+struct B2SortStats {
+  u64 scatter_launches;        // radix scatter launches
+  u64 scatter_elems;           // elements moved by them (sum over launches)
+  double scatter_ms;           // CUDA-event time of those launches (only when timing enabled)
+  u64 rounds;                  // doubling rounds executed (sum over batches)
+  u64 sorted_elems_round0;     // suffixes entering round 0
+  u64 sorted_elems_later;      // sum over later rounds of active suffixes
+  double sort_ms;              // all sort kernels
+};
+
+// b2_cut.cu
+int b2k_cut(cudaStream_t st, const u8 *d_in, u64 n, i64 size_hint, int level, i64 win_lo, i64 win_hi,
+            B2Chunk *d_chunks, u32 *d_n_chunks, u32 max_chunks);
+int b2k_segment(cudaStream_t st, const u8 *d_in, const B2Chunk *d_chunks, u32 n_chunks, const double *d_T,
+                u32 *d_seg, u32 *d_nseg);
+// b2_rle1.cu
+void b2k_make_crc_tables(B2CrcTables *t);
+int b2k_rle1(cudaStream_t st, const u8 *d_in, B2Job *d_jobs, u32 n_jobs, u8 *d_text, const B2CrcTables *d_ct);
+
+struct B2SortJob { u32 job, tile0, ntiles, pad; };
+struct B2ConcatItem { u64 src_word; u64 nbits; u64 dst_bit; };
+
+struct B2SortCtx {
+  u64 *keysA, *keysB;
+  u32 *valsA, *valsB, *rank, *grp;
+  B2SortTile *d_tiles;
+  B2SortJob *d_sj;
+  u32 *d_hist;
+  i32 *d_tile_head, *d_carry;
+  u32 *d_unsorted, *h_unsorted;
+  size_t max_tiles, max_jobs;
+  bool timing;
+  B2SortStats stats;
+};
+
+#define LL_MAXCODE 20
+
+#ifdef __cplusplus
+#include <vector>
+// b2_bwt.cu
+int b2k_bwt_batch(B2SortCtx *cx, cudaStream_t st, B2Job *d_jobs, const std::vector<u32> &job_ids,
+                  const std::vector<u32> &job_n, const u8 *d_text, u8 *d_bwt);
+#endif
+// b2_mtf.cu  (tiles of 2048 positions)
+#define B2_MTF_TILE 2048
+#define B2_SORT_TILE 4096
+int b2k_mtf(cudaStream_t st, B2Job *d_jobs, u32 n_jobs, const B2SortTile *d_tiles, u32 n_tiles,
+            const u8 *d_bwt, u8 *d_idx, u16 *d_mtf);
+// b2_entropy.cu
+int b2k_entropy(cudaStream_t st, B2Job *d_jobs, u32 n_jobs, u32 max_groups_per_job, u32 total_groups,
+                const u16 *d_mtf, u32 *d_rank3, u32 *d_rank4, u8 *d_sel, unsigned long long *d_gcost,
+                u8 *d_lens, u32 *d_cost, u32 *d_low, int level);
+// b2_pack.cu
+int b2k_bits_layout(cudaStream_t st, B2Job *d_jobs, u32 n_jobs, u64 *d_total_words);
+int b2k_pack(cudaStream_t st, const B2Job *d_jobs, u32 n_jobs, const u16 *d_mtf, const u8 *d_sel, const u8 *d_lens,
+             u8 *d_selpos, u32 *d_bits, int level, u32 total_groups);
+int b2k_concat(cudaStream_t st, const B2ConcatItem *d_items, u32 n_items, const u32 *d_bits, u32 *d_out);
