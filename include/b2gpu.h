@@ -85,10 +85,13 @@ typedef struct b2_stats {
   uint64_t scatter_launches;     /* radix scatter launches */
   uint64_t scatter_elems;        /* elements moved by them */
   double scatter_ms;             /* their summed duration (only with b2_set_timing(enc, 1)) */
-  double stage_ms[8];            /* cut+segment, rle1, sort, mtf, entropy, pack, concat, copies (timing on) */
+  double stage_ms[8];            /* cut+segment, rle1, sort, mtf, entropy, pack, concat, copies (timing level 2) */
+  double call_ms;                /* CUDA-event time of the encode calls, first to last operation on the stream (timing >= 1) */
 } b2_stats;
 
-int b2_set_timing(b2_encoder *enc, int on);
+/* level 0: off; 1: events around every encode call and every radix scatter launch (no extra
+ * synchronisation); 2: also per-stage timers (adds stream synchronisations, diagnostic only). */
+int b2_set_timing(b2_encoder *enc, int level);
 int b2_get_stats(b2_encoder *enc, b2_stats *out);
 int b2_reset_stats(b2_encoder *enc);
 

@@ -26,7 +26,7 @@ class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in
                 ("streams", "input_bytes", "chunks", "blocks", "block_bytes", "kernel_launches", "sort_rounds",
                  "sort_elems_round0", "sort_elems_later", "scatter_launches", "scatter_elems")] + \
-               [("scatter_ms", C.c_double), ("stage_ms", C.c_double * 8)]
+               [("scatter_ms", C.c_double), ("stage_ms", C.c_double * 8), ("call_ms", C.c_double)]
 
 
 class BlockInfo(C.Structure):
@@ -142,7 +142,7 @@ class Encoder:
 
     # -- measurement / parity taps ----------------------------------------------------------------
     def set_timing(self, on):
-        _check(lib().b2_set_timing(self._h, 1 if on else 0))
+        _check(lib().b2_set_timing(self._h, int(on)))
 
     def stats(self):
         s = Stats()

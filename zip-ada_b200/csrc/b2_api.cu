@@ -59,7 +59,7 @@ struct ChunkPlan {
 struct b2_encoder {
   int level = 9, device = 0;
   cudaStream_t st = nullptr;
-  bool timing = false;
+  int timing = 0;                     // 0 off, 1 scatter + call events, 2 also per-stage timers (adds syncs)
   // constants
   DevBuf<B2CrcTables> d_ct;
   DevBuf<double> d_T;
@@ -96,15 +96,17 @@ struct b2_encoder {
   B2SortStats sort_stats;
   size_t batch_positions = 96u << 20;   // positions per batch (env B2GPU_BATCH_POSITIONS)
   size_t batch_jobs_max = 4096;
+  u64 launches_other = 0;
   // timing
   cudaEvent_t ev[2] = {nullptr, nullptr};
+  cudaEvent_t ev_call[2] = {nullptr, nullptr};
 };
 
 namespace {
 
 struct StageTimer {
   b2_encoder *e; int stage; bool on;
-  StageTimer(b2_encoder *e_, int s) : e(e_), stage(s), on(e_->timing) { if (on) cudaEventRecord(e->ev[0], e->st); }
+  StageTimer(b2_encoder *e_, int s) : e(e_), stage(s), on(e_->timing >= 2) { if (on) cudaEventRecord(e->ev[0], e->st); }
   ~StageTimer() {
     if (on) {
       cudaEventRecord(e->ev[1], e->st);
@@ -185,7 +187,7 @@ int run_batch(b2_encoder *e, const u8 *d_in, std::vector<B2Job> &jobs) {
   {
     StageTimer tm(e, 1);
     B2_TRY(b2k_rle1(st, d_in, e->d_jobs.p, J, e->d_text.p, e->d_ct.p));
-    e->stats.kernel_launches += 1;
+    e->launches_other += 1;
   }
   e->batch_jobs.resize(J);
   B2_CUDA_CHECK(cudaMemcpyAsync(e->batch_jobs.data(), e->d_jobs.p, J * sizeof(B2Job), cudaMemcpyDeviceToHost, st));
@@ -214,7 +216,7 @@ int run_batch(b2_encoder *e, const u8 *d_in, std::vector<B2Job> &jobs) {
     cx.rank = e->d_rank.p; cx.grp = e->d_grp.p; cx.d_tiles = e->d_tiles.p; cx.d_sj = e->d_sj.p;
     cx.d_hist = e->d_hist.p; cx.d_tile_head = e->d_tile_head.p; cx.d_carry = e->d_carry.p;
     cx.d_unsorted = e->d_unsorted.p; cx.h_unsorted = e->h_unsorted;
-    cx.max_tiles = e->d_tiles.cap; cx.max_jobs = e->d_sj.cap; cx.timing = e->timing;
+    cx.max_tiles = e->d_tiles.cap; cx.max_jobs = e->d_sj.cap; cx.timing = e->timing >= 1;
     cx.stats = e->sort_stats;
     int rc = b2k_bwt_batch(&cx, st, e->d_jobs.p, ids, ns, e->d_text.p, e->d_bwt.p);
     e->sort_stats = cx.stats;
@@ -225,14 +227,14 @@ int run_batch(b2_encoder *e, const u8 *d_in, std::vector<B2Job> &jobs) {
     if (!mtiles.empty())
       B2_CUDA_CHECK(cudaMemcpyAsync(e->d_mtiles.p, mtiles.data(), mtiles.size() * sizeof(B2SortTile), cudaMemcpyHostToDevice, st));
     B2_TRY(b2k_mtf(st, e->d_jobs.p, J, e->d_mtiles.p, (u32)mtiles.size(), e->d_bwt.p, e->d_idx.p, e->d_mtf.p));
-    e->stats.kernel_launches += 2;
+    e->launches_other += 2;
   }
   const u32 total_groups = gpos;
   {
     StageTimer tm(e, 4);
     B2_TRY(b2k_entropy(st, e->d_jobs.p, J, max_g, total_groups, e->d_mtf.p, e->d_rank3.p, e->d_rank4.p, e->d_sel.p,
                        e->d_gcost.p, e->d_lens.p, e->d_cost.p, e->d_low.p, e->level));
-    e->stats.kernel_launches += 4;
+    e->launches_other += 4;
   }
   {
     StageTimer tm(e, 5);
@@ -244,7 +246,7 @@ int run_batch(b2_encoder *e, const u8 *d_in, std::vector<B2Job> &jobs) {
     B2_TRY(e->d_bits.ensure(total_words + 64));
     B2_CUDA_CHECK(cudaMemsetAsync(e->d_bits.p, 0, (total_words + 8) * sizeof(u32), st));
     B2_TRY(b2k_pack(st, e->d_jobs.p, J, e->d_mtf.p, e->d_sel.p, e->d_lens.p, e->d_selpos.p, e->d_bits.p, e->level, total_groups));
-    e->stats.kernel_launches += 2;
+    e->launches_other += 2;
   }
   B2_CUDA_CHECK(cudaMemcpyAsync(e->batch_jobs.data(), e->d_jobs.p, J * sizeof(B2Job), cudaMemcpyDeviceToHost, st));
   B2_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -281,10 +283,10 @@ int encode_device(b2_encoder *e, const u8 *d_in, u64 n, i64 size_hint, u64 *out_
       e->seg.resize((size_t)n_chunks * 2 * B2_MAX_SEG);
       B2_CUDA_CHECK(cudaMemcpyAsync(e->nseg.data(), e->d_nseg.p, e->nseg.size() * sizeof(u32), cudaMemcpyDeviceToHost, st));
       B2_CUDA_CHECK(cudaMemcpyAsync(e->seg.data(), e->d_seg.p, e->seg.size() * sizeof(u32), cudaMemcpyDeviceToHost, st));
-      e->stats.kernel_launches += 1;
+      e->launches_other += 1;
     }
     B2_CUDA_CHECK(cudaStreamSynchronize(st));
-    e->stats.kernel_launches += 1;
+    e->launches_other += 1;
   }
   e->stats.chunks += n_chunks;
   // ---- output buffer -------------------------------------------------------------------------
@@ -388,7 +390,7 @@ int encode_device(b2_encoder *e, const u8 *d_in, u64 n, i64 size_hint, u64 *out_
       B2_CUDA_CHECK(cudaMemcpyAsync(e->d_items.p, items.data(), items.size() * sizeof(B2ConcatItem), cudaMemcpyHostToDevice, st));
       B2_TRY(b2k_concat(st, e->d_items.p, (u32)items.size(), e->d_bits.p, e->d_out.p));
       B2_CUDA_CHECK(cudaStreamSynchronize(st));
-      e->stats.kernel_launches += 1;
+      e->launches_other += 1;
     }
     c0 = c1;
   }
@@ -424,6 +426,7 @@ int encode_device(b2_encoder *e, const u8 *d_in, u64 n, i64 size_hint, u64 *out_
   e->stats.scatter_launches = e->sort_stats.scatter_launches;
   e->stats.scatter_elems = e->sort_stats.scatter_elems;
   e->stats.scatter_ms = e->sort_stats.scatter_ms;
+  e->stats.kernel_launches = e->launches_other + e->sort_stats.launches;
   return 0;
 }
 
@@ -453,6 +456,7 @@ int b2_create(int level, int device, b2_encoder **out) {
   if (const char *s = getenv("B2GPU_BATCH_JOBS")) { long long v = atoll(s); if (v >= 8) e->batch_jobs_max = (size_t)v; }
   B2_CUDA_CHECK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
   B2_CUDA_CHECK(cudaEventCreate(&e->ev[0])); B2_CUDA_CHECK(cudaEventCreate(&e->ev[1]));
+  B2_CUDA_CHECK(cudaEventCreate(&e->ev_call[0])); B2_CUDA_CHECK(cudaEventCreate(&e->ev_call[1]));
   // constant tables
   B2CrcTables *ct = new B2CrcTables();
   b2k_make_crc_tables(ct);
@@ -487,6 +491,8 @@ void b2_destroy(b2_encoder *e) {
   if (e->h_unsorted) cudaFreeHost(e->h_unsorted);
   if (e->ev[0]) cudaEventDestroy(e->ev[0]);
   if (e->ev[1]) cudaEventDestroy(e->ev[1]);
+  if (e->ev_call[0]) cudaEventDestroy(e->ev_call[0]);
+  if (e->ev_call[1]) cudaEventDestroy(e->ev_call[1]);
   if (e->st) cudaStreamDestroy(e->st);
   delete e;
 }
@@ -496,13 +502,14 @@ int b2_encode_stream_device(b2_encoder *e, const uint8_t *d_in, uint64_t n, int6
   if (!e || !out_len || (n && !d_in)) B2_FAIL(B2_ERR_ARGUMENT, "bad argument");
   B2_CUDA_CHECK(cudaSetDevice(e->device));
   u64 len = 0;
+  if (e->timing) cudaEventRecord(e->ev_call[0], e->st);
   B2_TRY(encode_device(e, d_in, n, size_hint, &len));
   *out_len = len;
   if (len > out_cap) B2_FAIL(B2_ERR_OUTPUT_TOO_SMALL, "output buffer too small");
-  if (d_out) {
-    B2_CUDA_CHECK(cudaMemcpyAsync(d_out, e->d_out.p, len, cudaMemcpyDeviceToDevice, e->st));
-    B2_CUDA_CHECK(cudaStreamSynchronize(e->st));
-  }
+  if (d_out) B2_CUDA_CHECK(cudaMemcpyAsync(d_out, e->d_out.p, len, cudaMemcpyDeviceToDevice, e->st));
+  if (e->timing) cudaEventRecord(e->ev_call[1], e->st);
+  B2_CUDA_CHECK(cudaStreamSynchronize(e->st));
+  if (e->timing) { float ms = 0; cudaEventElapsedTime(&ms, e->ev_call[0], e->ev_call[1]); e->stats.call_ms += ms; }
   return 0;
 }
 
@@ -511,6 +518,7 @@ int b2_encode_stream(b2_encoder *e, const uint8_t *in, uint64_t n, int64_t size_
   if (!e || !out_len || (n && !in)) B2_FAIL(B2_ERR_ARGUMENT, "bad argument");
   B2_CUDA_CHECK(cudaSetDevice(e->device));
   B2_TRY(e->d_in.ensure(n + 256));
+  if (e->timing) cudaEventRecord(e->ev_call[0], e->st);
   {
     StageTimer tm(e, 7);
     if (n) B2_CUDA_CHECK(cudaMemcpyAsync(e->d_in.p, in, n, cudaMemcpyHostToDevice, e->st));
@@ -523,16 +531,19 @@ int b2_encode_stream(b2_encoder *e, const uint8_t *in, uint64_t n, int64_t size_
   {
     StageTimer tm(e, 7);
     if (out) B2_CUDA_CHECK(cudaMemcpyAsync(out, e->d_out.p, len, cudaMemcpyDeviceToHost, e->st));
+    if (e->timing) cudaEventRecord(e->ev_call[1], e->st);
     B2_CUDA_CHECK(cudaStreamSynchronize(e->st));
   }
+  if (e->timing) { float ms = 0; cudaEventElapsedTime(&ms, e->ev_call[0], e->ev_call[1]); e->stats.call_ms += ms; }
   return 0;
 }
 
-int b2_set_timing(b2_encoder *e, int on) { if (!e) return B2_ERR_ARGUMENT; e->timing = on != 0; return 0; }
+int b2_set_timing(b2_encoder *e, int on) { if (!e) return B2_ERR_ARGUMENT; e->timing = on; return 0; }
 int b2_get_stats(b2_encoder *e, b2_stats *out) { if (!e || !out) return B2_ERR_ARGUMENT; *out = e->stats; return 0; }
 int b2_reset_stats(b2_encoder *e) {
   if (!e) return B2_ERR_ARGUMENT;
   memset(&e->stats, 0, sizeof e->stats); memset(&e->sort_stats, 0, sizeof e->sort_stats);
+  e->launches_other = 0;
   return 0;
 }
 

@@ -355,9 +355,10 @@ int b2k_bwt_batch(B2SortCtx *cx, cudaStream_t st, B2Job *d_jobs, const std::vect
     B2_CUDA_CHECK(cudaGetLastError());
     std::swap(kA, kB); std::swap(vA, vB);
     u64 el = 0;
-    for (auto &s : sj) el += ns[&s - &sj[0]];
+    for (u32 x : ns) el += x;
     cx->stats.scatter_launches++;
     cx->stats.scatter_elems += el;
+    cx->stats.launches += 3;
     return 0;
   };
   auto ranks = [&]() -> int {
@@ -366,6 +367,7 @@ int b2k_bwt_batch(B2SortCtx *cx, cudaStream_t st, B2Job *d_jobs, const std::vect
     k_scan_heads<<<(nj + 127) / 128, 128, 0, st>>>(cx->d_sj, nj, d_jobs, cx->d_tile_head, cx->d_carry);
     k_ranks<<<nt, ST_THREADS, 0, st>>>(cx->d_tiles, d_jobs, kA, vA, cx->d_carry, cx->rank, cx->grp);
     k_collect_unsorted<<<(nj + 127) / 128, 128, 0, st>>>(cx->d_sj, nj, d_jobs, cx->d_unsorted);
+    cx->stats.launches += 4;
     B2_CUDA_CHECK(cudaGetLastError());
     B2_CUDA_CHECK(cudaMemcpyAsync(cx->h_unsorted, cx->d_unsorted, nj * sizeof(u32), cudaMemcpyDeviceToHost, st));
     B2_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -385,6 +387,7 @@ int b2k_bwt_batch(B2SortCtx *cx, cudaStream_t st, B2Job *d_jobs, const std::vect
     cx->stats.sorted_elems_round0 += el;
   }
   k_keys0<<<(u32)tiles.size(), ST_THREADS, 0, st>>>(cx->d_tiles, d_jobs, d_text, kA, vA);
+  cx->stats.launches += 1;
   for (int p = 0; p < 8; p++) if ((rc = radix_pass(8 * p))) return rc;
   if ((rc = ranks())) return rc;
   cx->stats.rounds++;
@@ -402,6 +405,7 @@ int b2k_bwt_batch(B2SortCtx *cx, cudaStream_t st, B2Job *d_jobs, const std::vect
       if ((rc = upload())) return rc;
       k_bwt_out<<<(u32)tiles.size(), ST_THREADS, 0, st>>>(cx->d_tiles, d_jobs, vA, d_text, cx->rank, d_bwt);
       B2_CUDA_CHECK(cudaGetLastError());
+      cx->stats.launches += 1;
     }
     if (go_ids.empty()) break;
     ids.swap(go_ids); ns.swap(go_n);
@@ -412,6 +416,7 @@ int b2k_bwt_batch(B2SortCtx *cx, cudaStream_t st, B2Job *d_jobs, const std::vect
       cx->stats.sorted_elems_later += el;
     }
     k_keys<<<(u32)tiles.size(), ST_THREADS, 0, st>>>(cx->d_tiles, d_jobs, vA, cx->grp, cx->rank, kA, (u32)(reflect));
+    cx->stats.launches += 1;
     for (int p = 0; p < 5; p++) if ((rc = radix_pass(8 * p))) return rc;
     if ((rc = ranks())) return rc;
     cx->stats.rounds++;

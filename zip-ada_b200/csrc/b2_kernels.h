@@ -24,6 +24,7 @@ struct B2SortStats {
   u64 sorted_elems_round0;     // suffixes entering round 0
   u64 sorted_elems_later;      // sum over later rounds of active suffixes
   double sort_ms;              // all sort kernels
+  u64 launches;                // kernels launched by the sort driver
 };
 
 // b2_cut.cu
