@@ -214,3 +214,89 @@ def test_golden_regression_vectors():
         data, level, hint = make_inputs.CASES[name]()
         s = orc.encode_stream(data, level, hint)
         assert len(s) == rec["len"] and hashlib.sha256(s).hexdigest() == rec["sha256"], name
+
+
+def _ref_quick_sort(w, s):
+    """Literal restatement of the reference's Quick_sort (huffman-encoding-length_limited_coding.adb:191-223)."""
+    def qs(first, n):
+        if n < 2:
+            return
+        p = w[first + n // 2]
+        i, j = 0, n - 1
+        while True:
+            while w[first + i] < p:
+                i += 1
+            while p < w[first + j]:
+                j -= 1
+            if i >= j:
+                break
+            w[first + i], w[first + j] = w[first + j], w[first + i]
+            s[first + i], s[first + j] = s[first + j], s[first + i]
+            i += 1
+            j -= 1
+        qs(first, i)
+        qs(first + i, n - i)
+    qs(0, len(w))
+
+
+def _forward_package_merge(freq, limit):
+    """The formulation the CUDA kernel uses (zip-ada_b200/csrc/b2_entropy.cu, ll_length_limited_warp):
+    classic package-merge, package before leaf on equal weight, leaves in Quick_sort order."""
+    w = [int(f) for f in freq if f > 0]
+    s = [i for i, f in enumerate(freq) if f > 0]
+    lens = [0] * len(freq)
+    n = len(w)
+    if n == 0:
+        return lens
+    if n == 1:
+        lens[s[0]] = 1
+        return lens
+    _ref_quick_sort(w, s)
+    need = 2 * n - 2
+    levels, prev = [], None
+    for _ in range(limit):
+        if prev is None:
+            merged = [(x, 0) for x in w]
+        else:
+            pk = [prev[2 * i][0] + prev[2 * i + 1][0] for i in range(len(prev) // 2)]
+            merged, a, b = [], 0, 0
+            while len(merged) < need and (a < n or b < len(pk)):
+                if a < n and (b >= len(pk) or pk[b] > w[a]):
+                    merged.append((w[a], 0)); a += 1
+                else:
+                    merged.append((pk[b], 1)); b += 1
+        levels.append(merged)
+        prev = merged
+    k, counts = need, []
+    for lev in range(limit - 1, -1, -1):
+        m = levels[lev][:k]
+        a = sum(1 for x in m if x[1] == 0)
+        counts.append(a)
+        k = 2 * (len(m) - a)
+    for i in range(n):
+        lens[s[i]] = sum(1 for a in counts if a > i)
+    return lens
+
+
+def test_forward_package_merge_equals_boundary():
+    rng = np.random.default_rng(5)
+    for trial in range(600):
+        n = int(rng.choice([2, 3, 4, 5, 8, 17, 40, 100, 258]))
+        kind = trial % 5
+        if kind == 0:
+            f = rng.integers(0, 4, n)
+        elif kind == 1:
+            f = rng.integers(1, 3, n)
+        elif kind == 2:
+            f = (rng.pareto(0.7, n) * 3).astype(np.int64) + 1
+        elif kind == 3:
+            f = np.where(rng.random(n) < 0.7, 1, rng.integers(1, 1000, n))
+        else:
+            f = np.where(rng.random(n) < 0.5, 2, rng.integers(1, 50, n) * 2)
+        for limit in (15, 16, 17):
+            assert list(orc.llhc(f, limit)) == _forward_package_merge(list(f), limit)
+    for trial in range(400):          # tight limits
+        n = int(rng.integers(2, 40))
+        limit = int(rng.integers(max(1, int(np.ceil(np.log2(n)))), 9))
+        f = (rng.pareto(0.6, n) * 2).astype(np.int64) + 1
+        assert list(orc.llhc(f, limit)) == _forward_package_merge(list(f), limit)

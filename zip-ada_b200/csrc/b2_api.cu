@@ -72,6 +72,7 @@ struct b2_encoder {
   // batch workspace
   DevBuf<B2Job> d_jobs;
   DevBuf<u8> d_text, d_bwt, d_idx;
+  DevBuf<u32> d_segmask, d_tilemask;
   DevBuf<u64> d_keysA, d_keysB;
   DevBuf<u32> d_valsA, d_valsB, d_rank, d_grp;
   DevBuf<B2SortTile> d_tiles, d_mtiles;
@@ -140,6 +141,7 @@ int ensure_batch_workspace(b2_encoder *e, size_t T, size_t J) {
   B2_TRY(e->d_valsA.ensure(T)); B2_TRY(e->d_valsB.ensure(T));
   B2_TRY(e->d_rank.ensure(T)); B2_TRY(e->d_grp.ensure(T));
   B2_TRY(e->d_tiles.ensure(max_tiles)); B2_TRY(e->d_mtiles.ensure(max_mtiles));
+  B2_TRY(e->d_segmask.ensure((T / 64 + 2 * J + 8) * 8)); B2_TRY(e->d_tilemask.ensure(max_mtiles * 8));
   B2_TRY(e->d_sj.ensure(J));
   B2_TRY(e->d_hist.ensure(max_tiles * 256));
   B2_TRY(e->d_tile_head.ensure(max_tiles)); B2_TRY(e->d_carry.ensure(max_tiles));
@@ -166,7 +168,7 @@ BatchLayout layout_jobs(std::vector<B2Job> &jobs, int level) {
   u64 pos = 0, mpos = 0;
   for (auto &j : jobs) {
     u64 cap = std::min<u64>((u64)j.raw_len * 5 / 4 + 8, (u64)level * 100000 + 64);
-    cap = (cap + 15) & ~15ull;
+    cap = (cap + 63) & ~63ull;
     j.pos_off = (u32)pos; j.cap = (u32)cap;
     pos += cap;
     j.mtf_off = (u32)mpos;
@@ -203,6 +205,7 @@ int run_batch(b2_encoder *e, const u8 *d_in, std::vector<B2Job> &jobs) {
     b.grp_off = gpos; gpos += gmax;
     max_g = std::max(max_g, gmax);
     ids[j] = j; ns[j] = b.n;
+    b.tile0 = (u32)mtiles.size();
     for (u32 s = 0; s < b.n; s += B2_MTF_TILE) mtiles.push_back(B2SortTile{j, s});
     e->stats.block_bytes += b.n;
   }
@@ -226,8 +229,8 @@ int run_batch(b2_encoder *e, const u8 *d_in, std::vector<B2Job> &jobs) {
     StageTimer tm(e, 3);
     if (!mtiles.empty())
       B2_CUDA_CHECK(cudaMemcpyAsync(e->d_mtiles.p, mtiles.data(), mtiles.size() * sizeof(B2SortTile), cudaMemcpyHostToDevice, st));
-    B2_TRY(b2k_mtf(st, e->d_jobs.p, J, e->d_mtiles.p, (u32)mtiles.size(), e->d_bwt.p, e->d_idx.p, e->d_mtf.p));
-    e->launches_other += 2;
+    B2_TRY(b2k_mtf(st, e->d_jobs.p, J, e->d_mtiles.p, (u32)mtiles.size(), e->d_bwt.p, e->d_segmask.p, e->d_tilemask.p, e->d_idx.p, e->d_mtf.p));
+    e->launches_other += 3;
   }
   const u32 total_groups = gpos;
   {
@@ -347,7 +350,7 @@ int encode_device(b2_encoder *e, const u8 *d_in, u64 n, i64 size_hint, u64 *out_
             B2Job j; memset(&j, 0, sizeof j);
             j.raw_off = P.start + sl.first; j.raw_len = sl.second;
             add.push_back(j);
-            addpos += std::min<u64>((u64)sl.second * 5 / 4 + 24, (u64)level * 100000 + 80);
+            addpos += std::min<u64>((u64)sl.second * 5 / 4 + 72, (u64)level * 100000 + 128);
           } else id = it->second;
           P.tactic_jobs[t].push_back(id);
         }
@@ -482,7 +485,7 @@ void b2_destroy(b2_encoder *e) {
   if (e->st) cudaStreamSynchronize(e->st);
   e->d_ct.release(); e->d_T.release(); e->d_in.release(); e->d_out.release(); e->d_chunks.release();
   e->d_scalars.release(); e->d_seg.release(); e->d_nseg.release(); e->d_jobs.release(); e->d_text.release();
-  e->d_bwt.release(); e->d_idx.release(); e->d_keysA.release(); e->d_keysB.release(); e->d_valsA.release();
+  e->d_bwt.release(); e->d_idx.release(); e->d_segmask.release(); e->d_tilemask.release(); e->d_keysA.release(); e->d_keysB.release(); e->d_valsA.release();
   e->d_valsB.release(); e->d_rank.release(); e->d_grp.release(); e->d_tiles.release(); e->d_mtiles.release();
   e->d_sj.release(); e->d_hist.release(); e->d_tile_head.release(); e->d_carry.release(); e->d_unsorted.release();
   e->d_mtf.release(); e->d_rank3.release(); e->d_rank4.release(); e->d_sel.release(); e->d_selpos.release();

@@ -82,47 +82,50 @@ k_rank_sort(const B2Job *__restrict__ jobs, u32 *__restrict__ rank3, u32 *__rest
 }
 
 // ---------------------------------------------------------------------------------------------
-// Length-limited code lengths, literal restatement of the reference's boundary package-merge
-// (huffman-encoding-length_limited_coding.adb).  Serial; runs on one lane, scratch in shared
-// memory.  Recursion (:131-163) is unrolled on an explicit LIFO of list indices, which preserves
-// the depth-first order of the two recursive calls.
+// Length-limited code lengths (huffman-encoding-length_limited_coding.adb:46-280).
+//
+// The reference runs the *boundary* package-merge (lazy, recursive, :131-163).  What it computes is
+// the classic package-merge: list 1 = the sorted leaves; list l+1 = merge (leaves, pair sums of
+// consecutive items of list l); take the first 2n-2 items of the last list, then walk down: if p of
+// the first k items of a list are packages, the first 2p items of the list below are taken; a leaf
+// gets one bit per list in which it is taken (Extract_Bit_Lengths, :180-189).  The boundary
+// version's tie rule "new leaf iff sum > leaf weight" (:151) means a package goes BEFORE a leaf of
+// equal weight.  Each list is built here by one warp as a parallel merge (binary searches); the
+// equality of both formulations was checked on the CPU against the oracle's literal restatement
+// (tests/test_oracle.py::test_forward_package_merge_equals_boundary).  The leaf order comes from
+// the reference's own unstable Quick_sort (:191-223), replayed literally by lane 0 because its tie
+// order decides which of several equal-weight symbols get the longer codes.
 // ---------------------------------------------------------------------------------------------
 #define LL_MAXBITS 17
-#define LL_POOL (2 * LL_MAXBITS * (LL_MAXBITS + 1))
-#define LL_NULL 0xFFFFu
+#define LL_MAXITEMS (2 * B2_MAX_ALPHA)
+#define LL_BITWORDS 17
 
 struct LLScratch {
-  u32 leaf_w[B2_MAX_ALPHA];
-  u32 node_w[LL_POOL];
-  u16 leaf_s[B2_MAX_ALPHA];
-  u16 node_cnt[LL_POOL];
-  u16 node_tail[LL_POOL];
-  u16 lists[LL_MAXBITS][2];
-  u8 node_use[LL_POOL];
-  u8 stack[2 * LL_MAXBITS + 4];
+  u32 leaf[B2_MAX_ALPHA + 2];              // (weight << 9) | symbol
+  u32 lvl[2][LL_MAXITEMS];                 // merged weights of two consecutive lists
+  u32 pkgbits[LL_MAXBITS][LL_BITWORDS];    // bit p set <=> item p of the list is a package
 };
 
-__device__ void ll_quick_sort(LLScratch &S, i32 first, i32 n) {   // :191-223
+__device__ void ll_quick_sort(u32 *a0, i32 n0) {   // :191-223, compares weights only
   // explicit stack of (first, n) ranges; sub-ranges are disjoint so their order is irrelevant
   i32 stk_f[40], stk_n[40];
   int sp = 0;
-  stk_f[0] = first; stk_n[0] = n; sp = 1;
+  stk_f[0] = 0; stk_n[0] = n0; sp = 1;
   while (sp) {
     sp--;
     i32 f = stk_f[sp], nn = stk_n[sp];
     if (nn < 2) continue;
-    u32 pw = S.leaf_w[f + nn / 2];
+    u32 *a = a0 + f;
+    const u32 pw = a[nn / 2] >> 9;
     i32 i = 0, j = nn - 1;
     for (;;) {
-      while (S.leaf_w[f + i] < pw) i++;
-      while (pw < S.leaf_w[f + j]) j--;
+      while ((a[i] >> 9) < pw) i++;
+      while (pw < (a[j] >> 9)) j--;
       if (i >= j) break;
-      u32 tw = S.leaf_w[f + i]; S.leaf_w[f + i] = S.leaf_w[f + j]; S.leaf_w[f + j] = tw;
-      u16 ts = S.leaf_s[f + i]; S.leaf_s[f + i] = S.leaf_s[f + j]; S.leaf_s[f + j] = ts;
+      u32 t = a[i]; a[i] = a[j]; a[j] = t;
       i++; j--;
     }
-    // Quick_sort (a (first .. first+i-1)); Quick_sort (a (first+i .. last))
-    // push the larger range first so that the stack stays shallow
+    // Quick_sort (a (first .. first+i-1)); Quick_sort (a (first+i .. last)); larger range pushed first
     i32 n1 = i, n2 = nn - i;
     if (n1 > n2) {
       stk_f[sp] = f; stk_n[sp] = n1; sp++;
@@ -134,104 +137,96 @@ __device__ void ll_quick_sort(LLScratch &S, i32 first, i32 n) {   // :191-223
   }
 }
 
-__device__ u32 ll_get_free_node(LLScratch &S, int max_bits, u32 &pool_next, bool use_lists) {   // :98-122
-  const u32 pool_size = 2u * max_bits * (max_bits + 1);
-  for (;;) {
-    if (pool_next >= pool_size) {
-      for (u32 i = 0; i < pool_size; i++) S.node_use[i] = 0;
-      if (use_lists) {
-        for (int i = 0; i < max_bits * 2; i++) {
-          u32 node = S.lists[i / 2][i % 2];
-          while (node != LL_NULL) { S.node_use[node] = 1; node = S.node_tail[node]; }
-        }
-      }
-      pool_next = 0;
+// One warp.  counts[0..n-1] (already through Avoid_Zeros) -> lens[0..n-1].
+__device__ void ll_length_limited_warp(LLScratch &S, const u32 *counts, int n, int max_bits, u8 *lens) {
+  const u32 l = lane_id();
+  const u32 lt = (1u << l) - 1u;
+  int ns = 0;
+  for (int base = 0; base < n; base += 32) {                // leaves in alphabet order (:230-235)
+    const int a = base + (int)l;
+    const u32 c = a < n ? counts[a] : 0;
+    const u32 m = __ballot_sync(0xffffffffu, c > 0);
+    if (c > 0) S.leaf[ns + __popc(m & lt)] = (c << 9) | (u32)a;
+    ns += __popc(m);
+    if (a < n) lens[a] = 0;
+  }
+  __syncwarp();
+  if (ns == 0) return;
+  if (ns == 1) { if (l == 0) lens[S.leaf[0] & 511u] = 1; __syncwarp(); return; }
+  if (l == 0) ll_quick_sort(S.leaf, ns);
+  __syncwarp();
+  const int need = 2 * ns - 2;
+  for (int i = l; i < ns; i += 32) S.lvl[0][i] = S.leaf[i] >> 9;
+  if (l < LL_BITWORDS) S.pkgbits[0][l] = 0;
+  int len_prev = ns;
+  __syncwarp();
+  for (int lev = 1; lev < max_bits; lev++) {
+    const u32 *prev = S.lvl[(lev - 1) & 1];
+    u32 *cur = S.lvl[lev & 1];
+    const int npk = len_prev >> 1;
+    if (l < LL_BITWORDS) S.pkgbits[lev][l] = 0;
+    __syncwarp();
+    for (int a = l; a < ns; a += 32) {
+      const u32 w = S.leaf[a] >> 9;
+      int lo = 0, hi = npk;                                 // packages with sum <= w go before this leaf
+      while (lo < hi) { int mid = (lo + hi) >> 1; if (prev[2 * mid] + prev[2 * mid + 1] <= w) lo = mid + 1; else hi = mid; }
+      const int pos = a + lo;
+      if (pos < need) cur[pos] = w;
     }
-    if (!S.node_use[pool_next]) break;
-    pool_next++;
-  }
-  pool_next++;
-  return pool_next - 1;
-}
-
-// counts[0..n-1] (already through Avoid_Zeros) -> lens[0..n-1]
-__device__ void ll_length_limited(LLScratch &S, const u32 *counts, int n, int max_bits, u8 *lens) {
-  const u32 pool_size = 2u * max_bits * (max_bits + 1);
-  for (u32 i = 0; i < pool_size; i++) { S.node_use[i] = 0; S.node_tail[i] = LL_NULL; }
-  u32 pool_next = 0;
-  i32 num_symbols = 0;
-  for (int a = 0; a < n; a++) lens[a] = 0;
-  for (int a = 0; a < n; a++)
-    if (counts[a] > 0) { S.leaf_w[num_symbols] = counts[a]; S.leaf_s[num_symbols] = (u16)a; num_symbols++; }
-  if (num_symbols == 0) return;
-  if (num_symbols == 1) { lens[S.leaf_s[0]] = 1; return; }
-  ll_quick_sort(S, 0, num_symbols);
-  auto init_node = [&](u32 weight, u32 count, u32 tail, u32 idx) {
-    S.node_w[idx] = weight; S.node_cnt[idx] = (u16)count; S.node_tail[idx] = (u16)tail; S.node_use[idx] = 1;
-  };
-  {  // Init_Lists :167-174
-    u32 node0 = ll_get_free_node(S, max_bits, pool_next, false);
-    u32 node1 = ll_get_free_node(S, max_bits, pool_next, false);
-    init_node(S.leaf_w[0], 1, LL_NULL, node0);
-    init_node(S.leaf_w[1], 2, LL_NULL, node1);
-    for (int i = 0; i < max_bits; i++) { S.lists[i][0] = (u16)node0; S.lists[i][1] = (u16)node1; }
-  }
-  const i32 runs = 2 * num_symbols - 4;
-  for (i32 run = 1; run <= runs; run++) {
-    const bool final_top = (run == runs);
-    int sp = 0;
-    S.stack[sp++] = (u8)(max_bits - 1);
-    bool top = true;
-    while (sp) {
-      const int index = S.stack[--sp];
-      const bool final = top && final_top;
-      top = false;
-      const u32 lastcount = S.node_cnt[S.lists[index][1]];
-      if (index == 0 && (i32)lastcount >= num_symbols) continue;
-      const u32 newchain = ll_get_free_node(S, max_bits, pool_next, true);
-      const u32 oldchain = S.lists[index][1];
-      S.lists[index][0] = (u16)oldchain; S.lists[index][1] = (u16)newchain;
-      if (index == 0) {
-        init_node(S.leaf_w[lastcount], lastcount + 1, LL_NULL, newchain);
-      } else {
-        const u32 sum = S.node_w[S.lists[index - 1][0]] + S.node_w[S.lists[index - 1][1]];
-        if ((i32)lastcount < num_symbols && sum > S.leaf_w[lastcount]) {
-          init_node(S.leaf_w[lastcount], lastcount + 1, S.node_tail[oldchain], newchain);
-        } else {
-          init_node(sum, lastcount, S.lists[index - 1][1], newchain);
-          if (!final) { S.stack[sp++] = (u8)(index - 1); S.stack[sp++] = (u8)(index - 1); }
-        }
-      }
+    for (int b = l; b < npk; b += 32) {
+      const u32 pk = prev[2 * b] + prev[2 * b + 1];
+      int lo = 0, hi = ns;                                  // leaves with weight < sum go before this package
+      while (lo < hi) { int mid = (lo + hi) >> 1; if ((S.leaf[mid] >> 9) < pk) lo = mid + 1; else hi = mid; }
+      const int pos = b + lo;
+      if (pos < need) { cur[pos] = pk; atomicOr(&S.pkgbits[lev][pos >> 5], 1u << (pos & 31)); }
     }
+    len_prev = min(need, ns + npk);
+    __syncwarp();
   }
-  // Extract_Bit_Lengths :180-189
-  u32 node = S.lists[max_bits - 1][1];
-  while (node != LL_NULL) {
-    u32 c = S.node_cnt[node];
-    for (u32 i = 0; i < c; i++) lens[S.leaf_s[i]]++;
-    node = S.node_tail[node];
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// selector MTF list (:669-717, :816-835): positions 1..ec, packed 4 bits per entry
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ u32 selmtf_init(int ec) {
-  u32 v = 0;
-  for (int w = 0; w < ec; w++) v |= (u32)(w + 1) << (4 * w);
-  return v;
-}
-__device__ __forceinline__ int selmtf_pos(u32 v, int cl) {      // 1-based position of coder cl
-  int p = 1;
+  // walk down from the last list
+  u32 cnt[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  int k = need;
+  for (int lev = max_bits - 1; lev >= 0; lev--) {
+    const u32 wv = (l < LL_BITWORDS) ? S.pkgbits[lev][l] : 0u;
+    const int lo = (int)l * 32;
+    const u32 msk = (k >= lo + 32) ? 0xFFFFFFFFu : (k <= lo ? 0u : ((1u << (k - lo)) - 1u));
+    u32 p = __popc(wv & msk);
 #pragma unroll
-  for (int w = 0; w < 6; w++) { if (((v >> (4 * w)) & 15u) == (u32)cl) p = w + 1; }
-  return p;
+    for (int o = 16; o; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+    const int a = k - (int)p;                               // leaves taken in this list
+#pragma unroll
+    for (int j = 0; j < 9; j++) cnt[j] += ((int)l + 32 * j < a);
+    k = 2 * (int)p;
+  }
+#pragma unroll
+  for (int j = 0; j < 9; j++) {
+    const int i = (int)l + 32 * j;
+    if (i < ns) lens[S.leaf[i] & 511u] = (u8)cnt[j];
+  }
+  __syncwarp();
 }
-__device__ __forceinline__ u32 selmtf_front(u32 v, int pos, int cl) {   // move entry at pos to front
-  u32 lowmask = (pos >= 8) ? 0xFFFFFFFFu : ((1u << (4 * (pos - 1))) - 1u);   // entries before pos
-  u32 keep_hi = (pos >= 8) ? 0u : (v & ~((1u << (4 * pos)) - 1u));
-  return keep_hi | ((v & lowmask) << 4) | (u32)cl;
-}
+
+// ---------------------------------------------------------------------------------------------
+// selector MTF list (:669-717, :816-835) kept as positions: pos[cl] = 1-based place of coder cl+1.
+// Moving the coder at place p to the front increments every place < p and sets its own to 1.
+// ---------------------------------------------------------------------------------------------
+struct SelList {
+  u32 pos[6];
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int c = 0; c < 6; c++) pos[c] = (u32)c + 1;
+  }
+  __device__ __forceinline__ u32 place(u32 cl0) const {      // cl0 = coder - 1
+    u32 p = pos[0];
+#pragma unroll
+    for (int c = 1; c < 6; c++) p = (cl0 == (u32)c) ? pos[c] : p;
+    return p;
+  }
+  __device__ __forceinline__ void to_front(u32 cl0, u32 p) {
+#pragma unroll
+    for (int c = 0; c < 6; c++) pos[c] = (cl0 == (u32)c) ? 1u : pos[c] + (pos[c] < p ? 1u : 0u);
+  }
+};
 
 #define CT_THREADS 256
 
@@ -276,7 +271,7 @@ __device__ void ct_define_descriptors(ConstructSmem &S, const u16 *__restrict__ 
     if (zeroes > 0 && zeroes <= 100) { for (int s = l; s < A; s += 32) S.hist[w][s] = max(1u, S.hist[w][s]); }
     else if (zeroes > 100) { for (int s = l; s < A; s += 32) { u32 v = S.hist[w][s]; S.hist[w][s] = v == 0 ? 1u : v * 2u; } }
     __syncwarp();
-    if (l == 0) ll_length_limited(S.ll[w], S.hist[w], A, max_len, S.lens[w]);
+    ll_length_limited_warp(S.ll[w], S.hist[w], A, max_len, S.lens[w]);
   }
   __syncthreads();
   for (int s = tid; s < A; s += CT_THREADS) {
@@ -339,7 +334,7 @@ k_construct(const B2Job *__restrict__ jobs, const u16 *__restrict__ mtf, const u
     // Simulate_Entropy_Coding_Variants_and_Reclassify (:661-753): serial through the selector MTF list
     if (warp_id() == 0) {
       const u32 l = lane_id();
-      u32 list = selmtf_init(ec);
+      SelList L; L.init();
       u32 def = 0;
       for (u32 g0 = 0; g0 < G; g0 += 32) {
         const u32 g = g0 + l;
@@ -348,19 +343,21 @@ k_construct(const B2Job *__restrict__ jobs, const u16 *__restrict__ mtf, const u
         u32 mine = cur;
         const u32 cntk = min(32u, G - g0);
         for (u32 k = 0; k < cntk; k++) {
-          unsigned long long ck = __shfl_sync(0xffffffffu, c, k);
-          u32 clk = __shfl_sync(0xffffffffu, cur, k);
-          u32 min_bits = 0x7FFFFFFFu;
-          u32 best = clk;
+          const unsigned long long ck = __shfl_sync(0xffffffffu, c, k);
+          const u32 clk = __shfl_sync(0xffffffffu, cur, k);
+          // key = (cost << 6) | (coder0 << 3) | place: the minimum is the cheapest coder, lowest
+          // coder on ties (strict "<" scanning cl upward, :691-695), and carries its place along
+          u32 key = 0xFFFFFFFFu;
 #pragma unroll
-          for (int cl = 1; cl <= 6; cl++) {
-            if (cl <= ec) {
-              u32 cost = (u32)((ck >> (10 * (cl - 1))) & 1023u) + (u32)selmtf_pos(list, cl);
-              if (cost < min_bits) { min_bits = cost; best = (u32)cl; }
+          for (int cl = 0; cl < 6; cl++) {
+            if (cl < ec) {
+              const u32 cost = (u32)((ck >> (10 * cl)) & 1023u) + L.pos[cl];
+              key = min(key, (cost << 6) | ((u32)cl << 3) | L.pos[cl]);
             }
           }
-          if (best != clk) { def++; if (l == k) mine = best; }
-          list = selmtf_front(list, selmtf_pos(list, (int)best), (int)best);
+          const u32 best0 = (key >> 3) & 7u;
+          if (best0 + 1 != clk) { def++; if (l == k) mine = best0 + 1; }
+          L.to_front(best0, key & 7u);
         }
         if (g < G && mine != cur) sel[g] = (u8)mine;
       }
@@ -387,17 +384,17 @@ k_construct(const B2Job *__restrict__ jobs, const u16 *__restrict__ mtf, const u
   // Compute_Selectors_Cost (:815-837), serial on warp 0
   if (warp_id() == 0) {
     const u32 l = lane_id();
-    u32 list = selmtf_init(ec);
+    SelList L; L.init();
     u32 bits = 0;
     for (u32 g0 = 0; g0 < G; g0 += 32) {
       const u32 g = g0 + l;
       u32 cur = g < G ? sel[g] : 1;
       const u32 cntk = min(32u, G - g0);
       for (u32 k = 0; k < cntk; k++) {
-        u32 clk = __shfl_sync(0xffffffffu, cur, k);
-        int p = selmtf_pos(list, (int)clk);
-        bits += (u32)p;
-        list = selmtf_front(list, p, (int)clk);
+        const u32 cl0 = __shfl_sync(0xffffffffu, cur, k) - 1;
+        const u32 p = L.place(cl0);
+        bits += p;
+        L.to_front(cl0, p);
       }
     }
     if (l == 0) S.selcost = bits;
