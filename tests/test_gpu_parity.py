@@ -88,6 +88,11 @@ STREAM_CASES = {
     "zeros_2M": lambda: (np.zeros(2_000_000, np.uint8), 2_000_000),
     "random_1M": lambda: (datagen.random_bytes(1_000_000, 25), -1),
     "runs4": lambda: (np.repeat(datagen.random_bytes(300_000, 26), 4), 1_200_000),   # worst-case RLE1 expansion
+    "runs_long": lambda: (np.repeat(datagen.random_bytes(4000, 27, 0, 3), np.random.default_rng(28).integers(1, 3000, 4000)), -1),
+    "zeros_9p5M_rawcap": lambda: (np.zeros(9_500_000, np.uint8), 9_500_000),          # 10 x capacity raw limit
+    "runs259": lambda: (np.repeat(datagen.random_bytes(12_000, 29), 259), 12_000 * 259),
+    "runs260_then_text": lambda: (np.concatenate([np.repeat(datagen.random_bytes(9_000, 30), 260), datagen.text(700_000, 31)]), -1),
+    "text_then_zeros_then_text": lambda: (np.concatenate([datagen.text(880_000, 32), np.zeros(3_000_000, np.uint8), datagen.text(500_000, 33)]), 4_380_000),
 }
 
 

@@ -69,6 +69,8 @@ struct b2_encoder {
   DevBuf<B2Chunk> d_chunks;
   DevBuf<u32> d_scalars;     // [0] n_chunks, [2..3] total_words (u64)
   DevBuf<u32> d_seg, d_nseg;
+  DevBuf<u32> d_cut_first, d_cut_last, d_cut_tsum;
+  DevBuf<u64> d_cut_carry, d_cut_tincl;
   // batch workspace
   DevBuf<B2Job> d_jobs;
   DevBuf<u8> d_text, d_bwt, d_idx;
@@ -77,7 +79,7 @@ struct b2_encoder {
   DevBuf<u32> d_valsA, d_valsB, d_rank, d_grp;
   DevBuf<B2SortTile> d_tiles, d_mtiles;
   DevBuf<B2SortJob> d_sj;
-  DevBuf<u32> d_hist;
+  DevBuf<u32> d_hist, d_digit_base;
   DevBuf<i32> d_tile_head, d_carry;
   DevBuf<u32> d_unsorted;
   DevBuf<u16> d_mtf;
@@ -143,7 +145,7 @@ int ensure_batch_workspace(b2_encoder *e, size_t T, size_t J) {
   B2_TRY(e->d_tiles.ensure(max_tiles)); B2_TRY(e->d_mtiles.ensure(max_mtiles));
   B2_TRY(e->d_segmask.ensure((T / 64 + 2 * J + 8) * 8)); B2_TRY(e->d_tilemask.ensure(max_mtiles * 8));
   B2_TRY(e->d_sj.ensure(J));
-  B2_TRY(e->d_hist.ensure(max_tiles * 256));
+  B2_TRY(e->d_hist.ensure(max_tiles * 256)); B2_TRY(e->d_digit_base.ensure(J * 256));
   B2_TRY(e->d_tile_head.ensure(max_tiles)); B2_TRY(e->d_carry.ensure(max_tiles));
   B2_TRY(e->d_unsorted.ensure(J));
   B2_TRY(e->d_mtf.ensure(T + 16 * J + 64));
@@ -217,7 +219,7 @@ int run_batch(b2_encoder *e, const u8 *d_in, std::vector<B2Job> &jobs) {
     B2SortCtx cx;
     cx.keysA = e->d_keysA.p; cx.keysB = e->d_keysB.p; cx.valsA = e->d_valsA.p; cx.valsB = e->d_valsB.p;
     cx.rank = e->d_rank.p; cx.grp = e->d_grp.p; cx.d_tiles = e->d_tiles.p; cx.d_sj = e->d_sj.p;
-    cx.d_hist = e->d_hist.p; cx.d_tile_head = e->d_tile_head.p; cx.d_carry = e->d_carry.p;
+    cx.d_hist = e->d_hist.p; cx.d_digit_base = e->d_digit_base.p; cx.d_tile_head = e->d_tile_head.p; cx.d_carry = e->d_carry.p;
     cx.d_unsorted = e->d_unsorted.p; cx.h_unsorted = e->h_unsorted;
     cx.max_tiles = e->d_tiles.cap; cx.max_jobs = e->d_sj.cap; cx.timing = e->timing >= 1;
     cx.stats = e->sort_stats;
@@ -272,7 +274,12 @@ int encode_device(b2_encoder *e, const u8 *d_in, u64 n, i64 size_hint, u64 *out_
   {
     StageTimer tm(e, 0);
     B2_TRY(e->d_chunks.ensure(max_chunks));
-    B2_TRY(b2k_cut(st, d_in, n, size_hint, level, win_lo, win_hi, e->d_chunks.p, e->d_scalars.p, max_chunks));
+    const size_t ct = (size_t)(n / 2048 + 2);
+    B2_TRY(e->d_cut_first.ensure(ct)); B2_TRY(e->d_cut_last.ensure(ct)); B2_TRY(e->d_cut_tsum.ensure(ct));
+    B2_TRY(e->d_cut_carry.ensure(ct)); B2_TRY(e->d_cut_tincl.ensure(ct));
+    B2CutWork cw{e->d_cut_first.p, e->d_cut_last.p, e->d_cut_tsum.p, e->d_cut_carry.p, e->d_cut_tincl.p};
+    B2_TRY(b2k_cut(st, d_in, n, size_hint, level, win_lo, win_hi, e->d_chunks.p, e->d_scalars.p, max_chunks, &cw));
+    e->launches_other += 4;
     B2_CUDA_CHECK(cudaMemcpyAsync(&n_chunks, e->d_scalars.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
     B2_CUDA_CHECK(cudaStreamSynchronize(st));
     if (n_chunks > max_chunks) B2_FAIL(B2_ERR_INTERNAL, "chunk table overflow");
@@ -484,10 +491,11 @@ void b2_destroy(b2_encoder *e) {
   cudaSetDevice(e->device);
   if (e->st) cudaStreamSynchronize(e->st);
   e->d_ct.release(); e->d_T.release(); e->d_in.release(); e->d_out.release(); e->d_chunks.release();
-  e->d_scalars.release(); e->d_seg.release(); e->d_nseg.release(); e->d_jobs.release(); e->d_text.release();
+  e->d_scalars.release(); e->d_seg.release(); e->d_nseg.release(); e->d_cut_first.release(); e->d_cut_last.release();
+  e->d_cut_tsum.release(); e->d_cut_carry.release(); e->d_cut_tincl.release(); e->d_jobs.release(); e->d_text.release();
   e->d_bwt.release(); e->d_idx.release(); e->d_segmask.release(); e->d_tilemask.release(); e->d_keysA.release(); e->d_keysB.release(); e->d_valsA.release();
   e->d_valsB.release(); e->d_rank.release(); e->d_grp.release(); e->d_tiles.release(); e->d_mtiles.release();
-  e->d_sj.release(); e->d_hist.release(); e->d_tile_head.release(); e->d_carry.release(); e->d_unsorted.release();
+  e->d_sj.release(); e->d_hist.release(); e->d_digit_base.release(); e->d_tile_head.release(); e->d_carry.release(); e->d_unsorted.release();
   e->d_mtf.release(); e->d_rank3.release(); e->d_rank4.release(); e->d_sel.release(); e->d_selpos.release();
   e->d_lens.release(); e->d_gcost.release(); e->d_cost.release(); e->d_low.release(); e->d_bits.release();
   e->d_items.release();

@@ -74,19 +74,23 @@ k_hist(const B2SortTile *__restrict__ tiles, const B2Job *__restrict__ jobs, con
 
 // ---- per-block exclusive scan over (digit major, tile minor) ------------------------------------
 __global__ void __launch_bounds__(256)
-k_scan(const B2SortJob *__restrict__ sj, u32 *__restrict__ hist) {
+k_scan(const B2SortJob *__restrict__ sj, u32 *__restrict__ hist, u32 *__restrict__ digit_base) {
   __shared__ u32 sm[40];
   const B2SortJob s = sj[blockIdx.x];
   const u32 d = threadIdx.x;
+  u32 *h = hist + (size_t)s.tile0 * 256 + d;
   u32 total = 0;
-  for (u32 t = 0; t < s.ntiles; t++) {
-    size_t idx = (size_t)(s.tile0 + t) * 256 + d;
-    u32 c = hist[idx];
-    hist[idx] = total;
-    total += c;
+  u32 t = 0;
+  for (; t + 8 <= s.ntiles; t += 8) {             // 8 independent loads in flight per thread
+    u32 c[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) c[k] = h[(size_t)(t + k) * 256];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { h[(size_t)(t + k) * 256] = total; total += c[k]; }
   }
+  for (; t < s.ntiles; t++) { u32 c = h[(size_t)t * 256]; h[(size_t)t * 256] = total; total += c; }
   u32 base = block_excl_add(total, sm, nullptr);
-  for (u32 t = 0; t < s.ntiles; t++) hist[(size_t)(s.tile0 + t) * 256 + d] += base;
+  digit_base[(size_t)s.job * 256 + d] = base;     // added by the scatter kernel
 }
 
 // ---- stable scatter of one digit ---------------------------------------------------------------
@@ -104,7 +108,8 @@ struct ScatterSmem {
 __global__ void __launch_bounds__(ST_THREADS, 2)
 k_scatter(const B2SortTile *__restrict__ tiles, const B2Job *__restrict__ jobs,
           const u64 *__restrict__ keys_in, const u32 *__restrict__ vals_in,
-          u64 *__restrict__ keys_out, u32 *__restrict__ vals_out, int shift, const u32 *__restrict__ hist) {
+          u64 *__restrict__ keys_out, u32 *__restrict__ vals_out, int shift, const u32 *__restrict__ hist,
+          const u32 *__restrict__ digit_base) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ScatterSmem &S = *reinterpret_cast<ScatterSmem *>(smem_raw);
   const B2SortTile tl = tiles[blockIdx.x];
@@ -113,7 +118,7 @@ k_scatter(const B2SortTile *__restrict__ tiles, const B2Job *__restrict__ jobs,
   const u32 tid = threadIdx.x, w = warp_id(), l = lane_id();
   const u32 lt_mask = (1u << l) - 1u;
   for (int i = tid; i < ST_WARPS * 256; i += ST_THREADS) (&S.warp_cnt[0][0])[i] = 0;
-  S.g_off[tid] = hist[(size_t)blockIdx.x * 256 + tid];
+  S.g_off[tid] = hist[(size_t)blockIdx.x * 256 + tid] + digit_base[(size_t)tl.job * 256 + tid];
   __syncthreads();
   u64 key[ST_ITEMS];
   u32 val[ST_ITEMS];
@@ -347,10 +352,10 @@ int b2k_bwt_batch(B2SortCtx *cx, cudaStream_t st, B2Job *d_jobs, const std::vect
   auto radix_pass = [&](int shift) -> int {
     u32 nt = (u32)tiles.size();
     k_hist<<<nt, ST_THREADS, 0, st>>>(cx->d_tiles, d_jobs, kA, shift, cx->d_hist);
-    k_scan<<<(u32)sj.size(), 256, 0, st>>>(cx->d_sj, cx->d_hist);
+    k_scan<<<(u32)sj.size(), 256, 0, st>>>(cx->d_sj, cx->d_hist, cx->d_digit_base);
     EvPair ev{nullptr, nullptr};
     if (cx->timing) { cudaEventCreate(&ev.a); cudaEventCreate(&ev.b); cudaEventRecord(ev.a, st); }
-    k_scatter<<<nt, ST_THREADS, sizeof(ScatterSmem), st>>>(cx->d_tiles, d_jobs, kA, vA, kB, vB, shift, cx->d_hist);
+    k_scatter<<<nt, ST_THREADS, sizeof(ScatterSmem), st>>>(cx->d_tiles, d_jobs, kA, vA, kB, vB, shift, cx->d_hist, cx->d_digit_base);
     if (cx->timing) { cudaEventRecord(ev.b, st); evs.push_back(ev); }
     B2_CUDA_CHECK(cudaGetLastError());
     std::swap(kA, kB); std::swap(vA, vB);

@@ -1,0 +1,312 @@
+// Stage A1: chunk cutting (Data_Acquisition) as device scans plus a short serial chain.
+//
+// Reference: zip_lib/bzip2-encoding.adb:1160-1208 (Data_Acquisition) and :1413-1429 (chunk loop with
+// the last-two-blocks balancing).  The reference reads bytes while `rle_1_block_size + 5 <
+// capacity` (and < 10 x capacity raw bytes), where rle_1_block_size counts the RLE1 size of the
+// *completed* runs, a run being cut every 259 bytes (:1171-1179, :1195-1204).
+//
+// A "piece" is a maximal equal-byte run counted from the chunk start, split every 259; when the
+// first byte of a new piece is read the previous piece's size min(len,4)+[len>=4] is committed; the
+// chunk ends with the first byte whose commit makes committed + 5 >= capacity.
+// Only the FIRST run of a chunk depends on where the chunk starts (a chunk may start in the middle
+// of a run of the stream); all later runs are runs of the stream itself.  Hence:
+//   k_cut_a   per 2048-byte tile: first / last position where the byte changes       (all SMs)
+//   k_cut_s1  exclusive max-scan over tiles -> start of the run that enters each tile
+//   k_cut_b   per tile: sum of the commits g(p) defined with the runs of the STREAM      (all SMs)
+//   k_cut_s2  inclusive add-scan over tiles -> G
+//   k_cut_chain  one warp walks the chunks: first run analytically, then a binary search on G and
+//                one in-tile scan locate the end of the chunk.
+#include "b2_common.cuh"
+#include "b2_kernels.h"
+
+#define CT_TILE 2048
+#define CT_THREADS 128          // 16 bytes per thread
+#define NONE32 0xFFFFFFFFu
+
+__device__ __forceinline__ u32 enc_size(u32 len) { return (len < 4 ? len : 4) + (len >= 4 ? 1 : 0); }
+
+__device__ __forceinline__ void load16(const u8 *__restrict__ in, u64 base, u64 n_alloc, u8 *b) {
+  // 16-byte aligned vector load when the whole vector is inside the allocation
+  if (base + 16 <= n_alloc) {
+    const uint4 v = *reinterpret_cast<const uint4 *>(in + base);
+    const u32 w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 16; k++) b[k] = (u8)(w[k >> 2] >> (8 * (k & 3)));
+  } else {
+#pragma unroll
+    for (int k = 0; k < 16; k++) b[k] = (base + k < n_alloc) ? in[base + k] : 0;
+  }
+}
+
+__global__ void __launch_bounds__(CT_THREADS)
+k_cut_a(const u8 *__restrict__ in, u64 n, u32 *__restrict__ firstchg, u32 *__restrict__ lastchg) {
+  __shared__ u32 s_first, s_last;
+  const u64 t0 = (u64)blockIdx.x * CT_TILE;
+  const u32 tid = threadIdx.x;
+  if (tid == 0) { s_first = NONE32; s_last = 0; }
+  __syncthreads();
+  const u64 base = t0 + tid * 16;
+  u8 b[16];
+  load16(in, base, n, b);
+  u8 pv = (base > 0 && base < n) ? in[base - 1] : 0;
+  u32 f = NONE32, l = 0;     // l holds offset + 1, 0 = none
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    const u64 p = base + k;
+    if (p < n && (p == 0 || b[k] != pv)) { const u32 o = tid * 16 + k; if (f == NONE32) f = o; l = o + 1; }
+    pv = b[k];
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    f = min(f, __shfl_xor_sync(0xffffffffu, f, o));
+    l = max(l, __shfl_xor_sync(0xffffffffu, l, o));
+  }
+  if (lane_id() == 0) { if (f != NONE32) atomicMin(&s_first, f); if (l) atomicMax(&s_last, l); }
+  __syncthreads();
+  if (tid == 0) { firstchg[blockIdx.x] = s_first; lastchg[blockIdx.x] = s_last; }
+}
+
+// carry_r[t] = (global position of the last change before tile t) + 1, 0 if none.  One CTA.
+__global__ void __launch_bounds__(1024)
+k_cut_s1(const u32 *__restrict__ lastchg, u64 ntiles, u64 *__restrict__ carry_r) {
+  __shared__ u64 sm[1024];
+  const u32 tid = threadIdx.x;
+  const u64 per = (ntiles + 1023) / 1024;
+  const u64 a = tid * per, e = min(ntiles, a + per);
+  u64 loc = 0;
+  for (u64 t = a; t < e; t++) { u32 l = lastchg[t]; if (l) loc = t * CT_TILE + l; }   // (+1 kept: l = offset + 1)
+  sm[tid] = loc;
+  __syncthreads();
+  if (tid == 0) { u64 run = 0; for (int i = 0; i < 1024; i++) { u64 v = sm[i]; sm[i] = run; if (v) run = v; } }
+  __syncthreads();
+  u64 run = sm[tid];
+  for (u64 t = a; t < e; t++) { carry_r[t] = run; u32 l = lastchg[t]; if (l) run = t * CT_TILE + l; }
+}
+
+// commits with the runs of the stream: g(p) = size of the piece that ends at p-1 if a piece starts at p
+__device__ __forceinline__ u32 gcommit(u64 p, bool chg, u64 r_prev, u64 r_cur) {
+  if (p == 0) return 0;
+  if (chg) { const u64 Lr = p - r_prev; return enc_size((u32)((Lr - 1) % 259) + 1); }
+  return ((p - r_cur) % 259 == 0) ? 5u : 0u;
+}
+
+__global__ void __launch_bounds__(CT_THREADS)
+k_cut_b(const u8 *__restrict__ in, u64 n, const u64 *__restrict__ carry_r, u32 *__restrict__ tsum) {
+  __shared__ i32 sm_i[40];
+  __shared__ u32 sm_u[40];
+  const u64 t0 = (u64)blockIdx.x * CT_TILE;
+  const u32 tid = threadIdx.x;
+  const u64 base = t0 + tid * 16;
+  u8 b[16];
+  load16(in, base, n, b);
+  const u8 prev = (base > 0 && base < n) ? in[base - 1] : 0;
+  i32 lc = -1;
+  {
+    u8 pv = prev;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      const u64 p = base + k;
+      if (p < n && (p == 0 || b[k] != pv)) lc = (i32)(tid * 16 + k);
+      pv = b[k];
+    }
+  }
+  i32 tot;
+  const i32 rin = block_excl_max(lc, -1, sm_i, &tot);
+  const u64 cr = carry_r[blockIdx.x];
+  u64 r = rin >= 0 ? t0 + (u64)rin : (cr ? cr - 1 : 0);     // run start of byte base-1 (unused when base == 0)
+  u32 local = 0;
+  {
+    u8 pv = prev;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      const u64 p = base + k;
+      if (p < n) {
+        const bool chg = (p == 0 || b[k] != pv);
+        const u64 rp = r;
+        if (chg) r = p;
+        local += gcommit(p, chg, rp, r);
+      }
+      pv = b[k];
+    }
+  }
+  u32 total;
+  block_excl_add(local, sm_u, &total);
+  if (tid == 0) tsum[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024)
+k_cut_s2(const u32 *__restrict__ tsum, u64 ntiles, u64 *__restrict__ tincl) {
+  __shared__ u64 sm[1024];
+  const u32 tid = threadIdx.x;
+  const u64 per = (ntiles + 1023) / 1024;
+  const u64 a = tid * per, e = min(ntiles, a + per);
+  u64 loc = 0;
+  for (u64 t = a; t < e; t++) loc += tsum[t];
+  sm[tid] = loc;
+  __syncthreads();
+  if (tid == 0) { u64 run = 0; for (int i = 0; i < 1024; i++) { u64 v = sm[i]; sm[i] = run; run += v; } }
+  __syncthreads();
+  u64 run = sm[tid];
+  for (u64 t = a; t < e; t++) { run += tsum[t]; tincl[t] = run; }
+}
+
+// One warp scans one tile.  Each lane owns 64 consecutive bytes.
+//  mode 0: inclusive in-tile prefix of g at global position q          -> returns the prefix
+//  mode 1: first global position p in the tile with excl + prefix(p) >= target   -> position or ~0
+//  mode 2: first global position p > q in the tile where the byte changes        -> position or ~0
+__device__ u64 warp_tile(const u8 *__restrict__ in, u64 n, const u64 *__restrict__ carry_r, u64 t, int mode,
+                         u64 q, u64 excl, u64 target) {
+  const u32 l = lane_id();
+  const u64 t0 = t * CT_TILE;
+  const u64 base = t0 + l * 64;
+  u64 res = ~0ull;
+  if (mode == 2) {
+    u8 pv = (base > 0 && base < n) ? in[base - 1] : 0;
+    for (int k = 0; k < 64; k++) {
+      const u64 p = base + k;
+      u8 c = p < n ? in[p] : 0;
+      if (p < n && p > q && (p == 0 || c != pv) && res == ~0ull) res = p;
+      pv = c;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { u64 x = __shfl_xor_sync(0xffffffffu, res, o); res = min(res, x); }
+    return res;
+  }
+  // run start entering my 64 bytes
+  i32 lc = -1;
+  {
+    u8 pv = (base > 0 && base < n) ? in[base - 1] : 0;
+    for (int k = 0; k < 64; k++) {
+      const u64 p = base + k;
+      u8 c = p < n ? in[p] : 0;
+      if (p < n && (p == 0 || c != pv)) lc = (i32)(l * 64 + k);
+      pv = c;
+    }
+  }
+  i32 inc = warp_incl_max(lc);
+  i32 rin = __shfl_up_sync(0xffffffffu, inc, 1);
+  if (l == 0) rin = -1;
+  const u64 cr = carry_r[t];
+  u64 r = rin >= 0 ? t0 + (u64)rin : (cr ? cr - 1 : 0);
+  // my sum
+  u32 local = 0;
+  {
+    u64 rr = r;
+    u8 pv = (base > 0 && base < n) ? in[base - 1] : 0;
+    for (int k = 0; k < 64; k++) {
+      const u64 p = base + k;
+      u8 c = p < n ? in[p] : 0;
+      if (p < n) { const bool chg = (p == 0 || c != pv); const u64 rp = rr; if (chg) rr = p; local += gcommit(p, chg, rp, rr); }
+      pv = c;
+    }
+  }
+  const u32 incl = warp_incl_add(local);
+  u64 run = excl + (incl - local);
+  {
+    u8 pv = (base > 0 && base < n) ? in[base - 1] : 0;
+    for (int k = 0; k < 64; k++) {
+      const u64 p = base + k;
+      u8 c = p < n ? in[p] : 0;
+      if (p < n) {
+        const bool chg = (p == 0 || c != pv);
+        const u64 rp = r;
+        if (chg) r = p;
+        run += gcommit(p, chg, rp, r);
+        if (mode == 0 && p == q) res = run - excl;
+        if (mode == 1 && res == ~0ull && run >= target) res = p;
+      }
+      pv = c;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) { u64 x = __shfl_xor_sync(0xffffffffu, res, o); res = min(res, x); }
+  return res;
+}
+
+__global__ void __launch_bounds__(32)
+k_cut_chain(const u8 *__restrict__ in, u64 n, i64 size_hint, int level, i64 win_lo, i64 win_hi,
+            const u32 *__restrict__ firstchg, const u64 *__restrict__ carry_r, const u64 *__restrict__ tincl, u64 ntiles,
+            B2Chunk *chunks, u32 *n_chunks, u32 max_chunks) {
+  const u32 l = lane_id();
+  u64 pos = 0;
+  u32 nc = 0;
+  for (;;) {
+    // stream_rest: size_hint - bytes read, sticking at -1 (= unknown_size) once it gets there
+    // (bzip2-encoding.adb:1192-1194); the balancing test :1416-1424 was done in float32 on the host
+    // and arrives as the integer window [win_lo, win_hi].
+    const i64 rest = size_hint < 0 ? -1 : ((i64)pos <= size_hint ? size_hint - (i64)pos : -1);
+    i64 cap = (i64)level * 100000;
+    if (rest >= win_lo && rest <= win_hi) cap = rest / 2;
+    const u64 avail = n - pos;
+    const u64 rawmax = (u64)(10 * cap);                      // multiplier = 10 (:1156)
+    const u64 limit = avail < rawmax ? avail : rawmax;       // raw bytes this chunk may take
+    const u64 need = cap > 5 ? (u64)(cap - 5) : 0;           // stop once committed >= cap - 5
+    u64 len = limit;
+    if (need == 0) len = 0;
+    else if (limit > 0) {
+      const u64 s = pos, end_max = pos + limit;
+      // e1: first position after s where the byte changes (end of the chunk's first run)
+      u64 e1 = ~0ull;
+      {
+        u64 t = s / CT_TILE;
+        e1 = warp_tile(in, n, carry_r, t, 2, s, 0, 0);
+        if (e1 == ~0ull) {
+          // skip tiles without any change, 32 at a time
+          for (u64 tb = t + 1; tb < ntiles && e1 == ~0ull; tb += 32) {
+            const u64 tt = tb + l;
+            const u32 f = tt < ntiles ? firstchg[tt] : NONE32;
+            const u32 m = __ballot_sync(0xffffffffu, f != NONE32);
+            if (m) { const int k = __ffs(m) - 1; const u32 fk = __shfl_sync(0xffffffffu, f, k); e1 = (tb + k) * CT_TILE + fk; }
+            if (tb * CT_TILE >= end_max) break;
+          }
+        }
+        if (e1 == ~0ull) e1 = n;
+      }
+      const u64 run_end = e1 < end_max ? e1 : end_max;       // first run inside the window: [s, run_end)
+      const u64 jstar = (need + 4) / 5;                      // forced breaks needed to reach `need` (5 each, :1199)
+      const u64 pstar = s + 259 * jstar;
+      if (pstar < run_end) len = pstar - s + 1;              // (i) ends inside the first run
+      else if (e1 >= end_max) len = limit;                   // (ii) window exhausted inside the first run
+      else {
+        const u64 L1 = e1 - s;
+        const u64 A = 5 * ((L1 - 1) / 259) + enc_size((u32)((L1 - 1) % 259) + 1);
+        if (A >= need) len = e1 - s + 1;                     // (iii) ends with the first byte of the second run
+        else {
+          const u64 te = e1 / CT_TILE;
+          const u64 excl_e = te ? tincl[te - 1] : 0;
+          const u64 Ge1 = excl_e + warp_tile(in, n, carry_r, te, 0, e1, excl_e, 0);
+          const u64 Gt = Ge1 + (need - A);
+          // first tile whose inclusive prefix reaches Gt
+          u64 lo = te, hi = ntiles;                          // answer in [lo, hi]; hi = ntiles means none
+          while (lo < hi) { const u64 mid = (lo + hi) >> 1; if (tincl[mid] >= Gt) hi = mid; else lo = mid + 1; }
+          if (lo < ntiles && lo * CT_TILE < end_max) {
+            const u64 excl = lo ? tincl[lo - 1] : 0;
+            const u64 p = warp_tile(in, n, carry_r, lo, 1, 0, excl, Gt);
+            if (p != ~0ull && p < end_max) len = p - s + 1;  // (iv)
+          }
+        }
+      }
+    }
+    if (l == 0 && nc < max_chunks) { chunks[nc].start = pos; chunks[nc].len = (u32)len; chunks[nc].cap = (u32)cap; chunks[nc].pad = 0; chunks[nc].pad2 = 0; }
+    nc++;
+    pos += len;
+    if (pos >= n) break;                                     // exit when not More_Bytes (:1428)
+    if (len == 0) break;
+  }
+  if (l == 0) *n_chunks = nc;
+}
+
+int b2k_cut(cudaStream_t st, const u8 *d_in, u64 n, i64 size_hint, int level, i64 win_lo, i64 win_hi,
+            B2Chunk *d_chunks, u32 *d_n_chunks, u32 max_chunks, B2CutWork *w) {
+  const u64 ntiles = (n + CT_TILE - 1) / CT_TILE;
+  if (ntiles) {
+    k_cut_a<<<(u32)ntiles, CT_THREADS, 0, st>>>(d_in, n, w->firstchg, w->lastchg);
+    k_cut_s1<<<1, 1024, 0, st>>>(w->lastchg, ntiles, w->carry_r);
+    k_cut_b<<<(u32)ntiles, CT_THREADS, 0, st>>>(d_in, n, w->carry_r, w->tsum);
+    k_cut_s2<<<1, 1024, 0, st>>>(w->tsum, ntiles, w->tincl);
+  }
+  k_cut_chain<<<1, 32, 0, st>>>(d_in, n, size_hint, level, win_lo, win_hi, w->firstchg, w->carry_r, w->tincl, ntiles,
+                                d_chunks, d_n_chunks, max_chunks);
+  B2_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}

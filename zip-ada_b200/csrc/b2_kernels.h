@@ -27,9 +27,11 @@ struct B2SortStats {
   u64 launches;                // kernels launched by the sort driver
 };
 
-// b2_cut.cu
+// b2_chunks.cu  (per 2048-byte tile work arrays of the chunk cutter)
+struct B2CutWork { u32 *firstchg, *lastchg, *tsum; u64 *carry_r, *tincl; };
 int b2k_cut(cudaStream_t st, const u8 *d_in, u64 n, i64 size_hint, int level, i64 win_lo, i64 win_hi,
-            B2Chunk *d_chunks, u32 *d_n_chunks, u32 max_chunks);
+            B2Chunk *d_chunks, u32 *d_n_chunks, u32 max_chunks, B2CutWork *w);
+// b2_segment.cu
 int b2k_segment(cudaStream_t st, const u8 *d_in, const B2Chunk *d_chunks, u32 n_chunks, const double *d_T,
                 u32 *d_seg, u32 *d_nseg);
 // b2_rle1.cu
@@ -44,7 +46,7 @@ struct B2SortCtx {
   u32 *valsA, *valsB, *rank, *grp;
   B2SortTile *d_tiles;
   B2SortJob *d_sj;
-  u32 *d_hist;
+  u32 *d_hist, *d_digit_base;
   i32 *d_tile_head, *d_carry;
   u32 *d_unsorted, *h_unsorted;
   size_t max_tiles, max_jobs;
