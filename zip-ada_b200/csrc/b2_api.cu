@@ -84,7 +84,8 @@ struct b2_encoder {
   DevBuf<u32> d_unsorted;
   DevBuf<u16> d_mtf;
   DevBuf<u32> d_rank3, d_rank4;
-  DevBuf<u8> d_sel, d_selpos, d_lens;
+  DevBuf<u8> d_sel, d_selprev, d_selpos, d_lens;
+  DevBuf<u32> d_ehist, d_leaves, d_estat, d_selcost;
   DevBuf<unsigned long long> d_gcost;
   DevBuf<u32> d_cost, d_low;
   DevBuf<u32> d_bits;
@@ -136,7 +137,7 @@ void balance_window(int level, i64 &lo, i64 &hi) {
 int ensure_batch_workspace(b2_encoder *e, size_t T, size_t J) {
   const size_t max_tiles = T / B2_SORT_TILE + J + 8;
   const size_t max_mtiles = T / B2_MTF_TILE + J + 8;
-  const size_t GT = T / B2_GROUP_SIZE + 2 * J + 8;
+  const size_t GT = T / B2_GROUP_SIZE + 8 * J + 8;
   B2_TRY(e->d_jobs.ensure(J));
   B2_TRY(e->d_text.ensure(T + 64)); B2_TRY(e->d_bwt.ensure(T + 64)); B2_TRY(e->d_idx.ensure(T + 64));
   B2_TRY(e->d_keysA.ensure(T)); B2_TRY(e->d_keysB.ensure(T));
@@ -150,8 +151,10 @@ int ensure_batch_workspace(b2_encoder *e, size_t T, size_t J) {
   B2_TRY(e->d_unsorted.ensure(J));
   B2_TRY(e->d_mtf.ensure(T + 16 * J + 64));
   B2_TRY(e->d_rank3.ensure(GT)); B2_TRY(e->d_rank4.ensure(GT));
-  B2_TRY(e->d_sel.ensure(GT * B2_N_TRIPLES)); B2_TRY(e->d_selpos.ensure(GT));
-  B2_TRY(e->d_gcost.ensure(GT * B2_N_TRIPLES));
+  B2_TRY(e->d_sel.ensure(GT * B2_N_TRIPLES + 64)); B2_TRY(e->d_selprev.ensure(GT * B2_N_TRIPLES + 64)); B2_TRY(e->d_selpos.ensure(GT));
+  B2_TRY(e->d_ehist.ensure(J * B2_N_TRIPLES * B2_MAX_CODERS * 260)); B2_TRY(e->d_leaves.ensure((J * B2_N_TRIPLES * B2_MAX_CODERS + 64) * 260));
+  B2_TRY(e->d_estat.ensure(J * B2_N_TRIPLES * 2)); B2_TRY(e->d_selcost.ensure(J * B2_N_TRIPLES));
+  B2_TRY(e->d_gcost.ensure(GT * B2_N_TRIPLES + 64));
   B2_TRY(e->d_lens.ensure(J * B2_N_TRIPLES * B2_MAX_CODERS * B2_MAX_ALPHA));
   B2_TRY(e->d_cost.ensure(J * B2_N_TRIPLES)); B2_TRY(e->d_low.ensure(J * B2_N_TRIPLES));
   B2_TRY(e->d_items.ensure(J));
@@ -203,7 +206,7 @@ int run_batch(b2_encoder *e, const u8 *d_in, std::vector<B2Job> &jobs) {
   for (u32 j = 0; j < J; j++) {
     B2Job &b = e->batch_jobs[j];
     if (b.n > b.cap) B2_FAIL(B2_ERR_INTERNAL, "RLE1 output exceeds its slot");
-    u32 gmax = b.n / B2_GROUP_SIZE + 2;
+    u32 gmax = (b.n / B2_GROUP_SIZE + 2 + 3) & ~3u;       // multiple of 4: vector loads in k_ent_sweep
     b.grp_off = gpos; gpos += gmax;
     max_g = std::max(max_g, gmax);
     ids[j] = j; ns[j] = b.n;
@@ -238,8 +241,8 @@ int run_batch(b2_encoder *e, const u8 *d_in, std::vector<B2Job> &jobs) {
   {
     StageTimer tm(e, 4);
     B2_TRY(b2k_entropy(st, e->d_jobs.p, J, max_g, total_groups, e->d_mtf.p, e->d_rank3.p, e->d_rank4.p, e->d_sel.p,
-                       e->d_gcost.p, e->d_lens.p, e->d_cost.p, e->d_low.p, e->level));
-    e->launches_other += 4;
+                       e->d_selprev.p, e->d_gcost.p, e->d_ehist.p, e->d_leaves.p, e->d_lens.p, e->d_estat.p, e->d_selcost.p,
+                       e->d_cost.p, e->d_low.p, e->level, &e->launches_other));
   }
   {
     StageTimer tm(e, 5);
@@ -497,7 +500,8 @@ void b2_destroy(b2_encoder *e) {
   e->d_valsB.release(); e->d_rank.release(); e->d_grp.release(); e->d_tiles.release(); e->d_mtiles.release();
   e->d_sj.release(); e->d_hist.release(); e->d_digit_base.release(); e->d_tile_head.release(); e->d_carry.release(); e->d_unsorted.release();
   e->d_mtf.release(); e->d_rank3.release(); e->d_rank4.release(); e->d_sel.release(); e->d_selpos.release();
-  e->d_lens.release(); e->d_gcost.release(); e->d_cost.release(); e->d_low.release(); e->d_bits.release();
+  e->d_lens.release(); e->d_gcost.release(); e->d_selprev.release(); e->d_ehist.release(); e->d_leaves.release();
+  e->d_estat.release(); e->d_selcost.release(); e->d_cost.release(); e->d_low.release(); e->d_bits.release();
   e->d_items.release();
   if (e->h_unsorted) cudaFreeHost(e->h_unsorted);
   if (e->ev[0]) cudaEventDestroy(e->ev[0]);
@@ -591,7 +595,7 @@ int b2_dbg_block(b2_encoder *e, const uint8_t *raw, uint32_t len, uint8_t *rle_o
   if (rle_out && b.n) B2_CUDA_CHECK(cudaMemcpyAsync(rle_out, e->d_text.p + b.pos_off, b.n, cudaMemcpyDeviceToHost, st));
   if (bwt_out && b.n) B2_CUDA_CHECK(cudaMemcpyAsync(bwt_out, e->d_bwt.p + b.pos_off, b.n, cudaMemcpyDeviceToHost, st));
   if (mtf_out) B2_CUDA_CHECK(cudaMemcpyAsync(mtf_out, e->d_mtf.p + b.mtf_off, (size_t)b.n_mtf * 2, cudaMemcpyDeviceToHost, st));
-  const u32 total_groups = b.n / B2_GROUP_SIZE + 2;   // single job: grp arena size == its own bound
+  const u32 total_groups = (b.n / B2_GROUP_SIZE + 2 + 3) & ~3u;   // single job: grp arena size == its own bound
   if (sel_out) B2_CUDA_CHECK(cudaMemcpyAsync(sel_out, e->d_sel.p + (size_t)b.best * total_groups + b.grp_off, b.n_groups, cudaMemcpyDeviceToHost, st));
   if (lens_out) B2_CUDA_CHECK(cudaMemcpyAsync(lens_out, e->d_lens.p + (size_t)b.best * (B2_MAX_CODERS * B2_MAX_ALPHA), B2_MAX_CODERS * B2_MAX_ALPHA, cudaMemcpyDeviceToHost, st));
   u64 nbytes = (b.nbits + 7) >> 3;

@@ -10,12 +10,22 @@
 //
 // `Construct (sample_width)` for a given (max_code_len, coders) is a pure function of the block's
 // MTF symbols: it rewrites every selector and every used descriptor.  All 20
-// triples of a block therefore run concurrently, one CTA each (k_construct); k_choose then replays
-// the reference's loop order, its `low_cluster_usage` gate and its strict-< cost selection
-// (:930-952) over the stored results, and the stored result of the winner is what the reference's
-// final `Construct` (:961) would recompute.
+// triples of all blocks of a batch therefore advance together, one reclassification iteration
+// (:793-802) per round of kernels:
+//   k_ent_hist   cluster histograms, updated only for groups that changed cluster (:643-652), Avoid_Zeros
+//   k_ent_qsort  the reference's unstable Quick_sort of the leaves, 32 independent sorts per warp in lockstep
+//   k_ent_pm     package-merge code lengths, one warp per (block, triple, coder)
+//   k_ent_cost   bits of every group under every coder (:731-737)
+//   k_ent_sweep  the serial reclassification through the selector MTF list (:672-718): the sweeps of the
+//                20 triples of a block run in the 20 lanes of one warp
+// A triple whose sweep finds no defector is finished (:801) and skipped by later rounds.  k_choose then
+// replays the reference's loop order, its `low_cluster_usage` gate and its strict-< cost selection
+// (:930-952) over the stored results; the stored result of the winner is what the reference's final
+// `Construct` (:961) would recompute.
 #include "b2_common.cuh"
 #include "b2_kernels.h"
+
+#define HSTRIDE 260                    // padded alphabet stride of hist / leaves rows
 
 // ---------------------------------------------------------------------------------------------
 // Ranking keys (:593-614): key(group) = number of symbols in run_a .. min(EOB-1, sample_width-1)
@@ -82,6 +92,182 @@ k_rank_sort(const B2Job *__restrict__ jobs, u32 *__restrict__ rank3, u32 *__rest
 }
 
 // ---------------------------------------------------------------------------------------------
+// Per-problem bookkeeping.  Problem p = block * B2_N_TRIPLES + triple.
+// ---------------------------------------------------------------------------------------------
+struct EntArgs {
+  const B2Job *jobs;
+  const u16 *mtf;
+  const u32 *rank3, *rank4;
+  u8 *sel, *selprev;                    // [triple][total_groups]
+  unsigned long long *gcost;            // [triple][total_groups]
+  u32 *hist;                            // [p][6][HSTRIDE] raw cluster histograms
+  u32 *leaves;                          // interleaved: [(q / 32)][HSTRIDE][q % 32], q = p * 6 + coder
+  u8 *lens;                             // [p][6][B2_MAX_ALPHA]
+  u32 *stat;                            // [p][2]: defectors of the last sweep, finished flag
+  u32 *selcost;                         // [p]
+  u32 *cost_all, *low_all;              // [p]
+  u32 total_groups;
+  int level, n_triples;
+  u32 n_jobs;
+};
+
+__device__ __forceinline__ size_t leaf_index(u32 q, u32 e) { return ((size_t)(q >> 5) * HSTRIDE + e) * 32 + (q & 31); }
+
+// Initial_Clustering_by_Rank (:572-588, :625-631)
+__global__ void __launch_bounds__(256)
+k_ent_init(EntArgs a) {
+  const int t = blockIdx.x;
+  const u32 jb = blockIdx.y;
+  const B2Job &job = a.jobs[jb];
+  const u32 G = job.n_groups;
+  int max_len, sw, ec;
+  b2_triple(a.level, t, max_len, sw, ec);
+  const u32 p = jb * B2_N_TRIPLES + t;
+  u8 *sel = a.sel + (size_t)t * a.total_groups + job.grp_off;
+  u8 *selprev = a.selprev + (size_t)t * a.total_groups + job.grp_off;
+  const u32 *rk = (sw == 3 ? a.rank3 : a.rank4) + job.grp_off;
+  const int attr_tab[5][6] = {{2, 1, 0, 0, 0, 0}, {3, 1, 2, 0, 0, 0}, {4, 2, 1, 3, 0, 0}, {5, 3, 1, 2, 4, 0}, {6, 4, 2, 1, 3, 5}};
+  for (u32 i = threadIdx.x; i < G; i += 256) {
+    // rank position i+1 belongs to range a (1-based) iff high_(a-1) < i+1 <= high_a, high_a = a*G/ec
+    const u32 pos1 = i + 1;
+    int r = 1;
+    while ((u64)r * G / ec < pos1) r++;
+    sel[(rk[i] & 0xFFFFu) - 1] = (u8)attr_tab[ec - 2][r - 1];
+    selprev[i] = 0;
+  }
+  u32 *h = a.hist + (size_t)p * (B2_MAX_CODERS * HSTRIDE);
+  for (u32 i = threadIdx.x; i < B2_MAX_CODERS * HSTRIDE; i += 256) h[i] = 0;
+  u8 *ln = a.lens + (size_t)p * B2_MAX_CODERS * B2_MAX_ALPHA;
+  for (u32 i = threadIdx.x; i < B2_MAX_CODERS * B2_MAX_ALPHA; i += 256) ln[i] = 0;
+  if (threadIdx.x == 0) { a.stat[2 * p] = 1; a.stat[2 * p + 1] = 0; }
+}
+
+// Define_Descriptors, first half (:643-652) + Avoid_Zeros (:439-462)
+__global__ void __launch_bounds__(256)
+k_ent_hist(EntArgs a) {
+  __shared__ u32 h[B2_MAX_CODERS][HSTRIDE];
+  const int t = blockIdx.x;
+  const u32 jb = blockIdx.y;
+  const u32 p = jb * B2_N_TRIPLES + t;
+  if (a.stat[2 * p + 1]) return;
+  const B2Job &job = a.jobs[jb];
+  const u32 M = job.n_mtf, G = job.n_groups;
+  const int A = (int)job.n_used + 2;
+  const u16 *m = a.mtf + job.mtf_off;
+  int max_len, sw, ec;
+  b2_triple(a.level, t, max_len, sw, ec);
+  const u8 *sel = a.sel + (size_t)t * a.total_groups + job.grp_off;
+  u8 *selprev = a.selprev + (size_t)t * a.total_groups + job.grp_off;
+  u32 *hg = a.hist + (size_t)p * (B2_MAX_CODERS * HSTRIDE);
+  const u32 tid = threadIdx.x;
+  for (u32 i = tid; i < (u32)ec * HSTRIDE; i += 256) (&h[0][0])[i] = hg[i];
+  __syncthreads();
+  for (u32 g = tid; g < G; g += 256) {
+    const u32 c = sel[g], o = selprev[g];
+    if (c == o) continue;
+    const u32 s0 = g * B2_GROUP_SIZE, s1 = min(s0 + B2_GROUP_SIZE, M);
+    u32 n0 = 0, n1 = 0;
+    for (u32 s = s0; s < s1; s++) {
+      const u32 sym = m[s];
+      if (sym == 0) n0++;
+      else if (sym == 1) n1++;
+      else { atomicAdd(&h[c - 1][sym], 1u); if (o) atomicSub(&h[o - 1][sym], 1u); }
+    }
+    if (n0) { atomicAdd(&h[c - 1][0], n0); if (o) atomicSub(&h[o - 1][0], n0); }
+    if (n1) { atomicAdd(&h[c - 1][1], n1); if (o) atomicSub(&h[o - 1][1], n1); }
+    selprev[g] = (u8)c;
+  }
+  __syncthreads();
+  for (u32 i = tid; i < (u32)ec * HSTRIDE; i += 256) hg[i] = (&h[0][0])[i];
+  const u32 w = warp_id(), l = lane_id();
+  if ((int)w < ec) {
+    u32 zeroes = 0;
+    for (int s = l; s < A; s += 32) zeroes += (h[w][s] == 0);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) zeroes += __shfl_xor_sync(0xffffffffu, zeroes, o);
+    const u32 q = p * B2_MAX_CODERS + w;
+    for (int s = l; s < A; s += 32) {
+      u32 v = h[w][s];
+      if (zeroes > 0 && zeroes <= 100) v = max(1u, v);
+      else if (zeroes > 100) v = (v == 0) ? 1u : v * 2u;
+      a.leaves[leaf_index(q, (u32)s)] = (v << 9) | (u32)s;      // alphabet order (:230-235); every count is > 0 here
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The reference's Quick_sort (huffman-encoding-length_limited_coding.adb:191-223), whose tie order
+// decides which of several equal-weight symbols get the longer codes.  32 independent sorts per warp,
+// one per lane, advanced in lockstep as a small state machine; arrays interleaved in shared memory
+// (element e of lane l at e*32+l: conflict free).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32)
+k_ent_qsort(EntArgs a, u32 nq) {
+  __shared__ u32 s[HSTRIDE * 32];
+  __shared__ u32 stk[16 * 32];                 // per-lane stack of (first << 16 | count)
+  const u32 l = threadIdx.x;
+  const u32 q = blockIdx.x * 32 + l;
+  u32 n = 0;
+  if (q < nq) {
+    const u32 p = q / B2_MAX_CODERS, c = q % B2_MAX_CODERS;
+    const u32 jb = p / B2_N_TRIPLES, t = p % B2_N_TRIPLES;
+    int max_len, sw, ec;
+    b2_triple(a.level, (int)t, max_len, sw, ec);
+    if ((int)t < a.n_triples && jb < a.n_jobs && (int)c < ec && !a.stat[2 * p + 1]) n = a.jobs[jb].n_used + 2;
+  }
+  const u32 nmax = __reduce_max_sync(0xffffffffu, n);
+  if (nmax == 0) return;
+  u32 *g = a.leaves + (size_t)blockIdx.x * HSTRIDE * 32;
+  for (u32 e = 0; e < nmax; e++) s[e * 32 + l] = g[e * 32 + l];
+  __syncwarp();
+#define EL(x) s[(x) * 32 + l]
+  enum { POP = 0, SI = 1, SJ = 2, CK = 3 };
+  int sp = 0, st = POP;
+  u32 f = 0, nn = 0, pw = 0;
+  i32 i = 0, j = 0;
+  if (n >= 2) { stk[l] = n; sp = 1; }
+  bool active = n >= 2;
+  while (__any_sync(0xffffffffu, active)) {
+    if (active) {
+      if (st == POP) {
+        if (sp == 0) active = false;
+        else {
+          sp--;
+          const u32 v = stk[sp * 32 + l];
+          f = v >> 16; nn = v & 0xFFFFu;
+          pw = EL(f + nn / 2) >> 9;
+          i = 0; j = (i32)nn - 1;
+          st = SI;
+        }
+      } else if (st == SI) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) { if (st == SI) { if ((EL(f + i) >> 9) < pw) i++; else st = SJ; } }
+      } else if (st == SJ) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) { if (st == SJ) { if (pw < (EL(f + j) >> 9)) j--; else st = CK; } }
+      } else {
+        if (i >= j) {
+          // Quick_sort (a (first .. first+i-1)); Quick_sort (a (first+i .. last)); larger range pushed first
+          const u32 n1 = (u32)i, n2 = nn - (u32)i;
+          const u32 r1 = (f << 16) | n1, r2 = ((f + (u32)i) << 16) | n2;
+          if (n1 > n2) { if (n1 >= 2) stk[(sp++) * 32 + l] = r1; if (n2 >= 2) stk[(sp++) * 32 + l] = r2; }
+          else { if (n2 >= 2) stk[(sp++) * 32 + l] = r2; if (n1 >= 2) stk[(sp++) * 32 + l] = r1; }
+          st = POP;
+        } else {
+          const u32 x = EL(f + i), y = EL(f + j);
+          EL(f + i) = y; EL(f + j) = x;
+          i++; j--;
+          st = SI;
+        }
+      }
+    }
+  }
+#undef EL
+  __syncwarp();
+  for (u32 e = 0; e < nmax; e++) g[e * 32 + l] = s[e * 32 + l];
+}
+
+// ---------------------------------------------------------------------------------------------
 // Length-limited code lengths (huffman-encoding-length_limited_coding.adb:46-280).
 //
 // The reference runs the *boundary* package-merge (lazy, recursive, :131-163).  What it computes is
@@ -91,70 +277,22 @@ k_rank_sort(const B2Job *__restrict__ jobs, u32 *__restrict__ rank3, u32 *__rest
 // gets one bit per list in which it is taken (Extract_Bit_Lengths, :180-189).  The boundary
 // version's tie rule "new leaf iff sum > leaf weight" (:151) means a package goes BEFORE a leaf of
 // equal weight.  Each list is built here by one warp as a parallel merge (binary searches); the
-// equality of both formulations was checked on the CPU against the oracle's literal restatement
-// (tests/test_oracle.py::test_forward_package_merge_equals_boundary).  The leaf order comes from
-// the reference's own unstable Quick_sort (:191-223), replayed literally by lane 0 because its tie
-// order decides which of several equal-weight symbols get the longer codes.
+// equality of both formulations is checked on the CPU against the oracle's literal restatement
+// (tests/test_oracle.py::test_forward_package_merge_equals_boundary).
 // ---------------------------------------------------------------------------------------------
 #define LL_MAXBITS 17
 #define LL_MAXITEMS (2 * B2_MAX_ALPHA)
 #define LL_BITWORDS 17
+#define PM_WARPS 4
 
 struct LLScratch {
-  u32 leaf[B2_MAX_ALPHA + 2];              // (weight << 9) | symbol
+  u32 leaf[B2_MAX_ALPHA + 2];              // (weight << 9) | symbol, sorted
   u32 lvl[2][LL_MAXITEMS];                 // merged weights of two consecutive lists
   u32 pkgbits[LL_MAXBITS][LL_BITWORDS];    // bit p set <=> item p of the list is a package
 };
 
-__device__ void ll_quick_sort(u32 *a0, i32 n0) {   // :191-223, compares weights only
-  // explicit stack of (first, n) ranges; sub-ranges are disjoint so their order is irrelevant
-  i32 stk_f[40], stk_n[40];
-  int sp = 0;
-  stk_f[0] = 0; stk_n[0] = n0; sp = 1;
-  while (sp) {
-    sp--;
-    i32 f = stk_f[sp], nn = stk_n[sp];
-    if (nn < 2) continue;
-    u32 *a = a0 + f;
-    const u32 pw = a[nn / 2] >> 9;
-    i32 i = 0, j = nn - 1;
-    for (;;) {
-      while ((a[i] >> 9) < pw) i++;
-      while (pw < (a[j] >> 9)) j--;
-      if (i >= j) break;
-      u32 t = a[i]; a[i] = a[j]; a[j] = t;
-      i++; j--;
-    }
-    // Quick_sort (a (first .. first+i-1)); Quick_sort (a (first+i .. last)); larger range pushed first
-    i32 n1 = i, n2 = nn - i;
-    if (n1 > n2) {
-      stk_f[sp] = f; stk_n[sp] = n1; sp++;
-      stk_f[sp] = f + i; stk_n[sp] = n2; sp++;
-    } else {
-      stk_f[sp] = f + i; stk_n[sp] = n2; sp++;
-      stk_f[sp] = f; stk_n[sp] = n1; sp++;
-    }
-  }
-}
-
-// One warp.  counts[0..n-1] (already through Avoid_Zeros) -> lens[0..n-1].
-__device__ void ll_length_limited_warp(LLScratch &S, const u32 *counts, int n, int max_bits, u8 *lens) {
+__device__ void ll_package_merge_warp(LLScratch &S, int ns, int max_bits, u8 *lens) {
   const u32 l = lane_id();
-  const u32 lt = (1u << l) - 1u;
-  int ns = 0;
-  for (int base = 0; base < n; base += 32) {                // leaves in alphabet order (:230-235)
-    const int a = base + (int)l;
-    const u32 c = a < n ? counts[a] : 0;
-    const u32 m = __ballot_sync(0xffffffffu, c > 0);
-    if (c > 0) S.leaf[ns + __popc(m & lt)] = (c << 9) | (u32)a;
-    ns += __popc(m);
-    if (a < n) lens[a] = 0;
-  }
-  __syncwarp();
-  if (ns == 0) return;
-  if (ns == 1) { if (l == 0) lens[S.leaf[0] & 511u] = 1; __syncwarp(); return; }
-  if (l == 0) ll_quick_sort(S.leaf, ns);
-  __syncwarp();
   const int need = 2 * ns - 2;
   for (int i = l; i < ns; i += 32) S.lvl[0][i] = S.leaf[i] >> 9;
   if (l < LL_BITWORDS) S.pkgbits[0][l] = 0;
@@ -203,7 +341,23 @@ __device__ void ll_length_limited_warp(LLScratch &S, const u32 *counts, int n, i
     const int i = (int)l + 32 * j;
     if (i < ns) lens[S.leaf[i] & 511u] = (u8)cnt[j];
   }
+}
+
+__global__ void __launch_bounds__(32 * PM_WARPS)
+k_ent_pm(EntArgs a, u32 nq) {
+  __shared__ LLScratch S[PM_WARPS];
+  const u32 w = warp_id(), l = lane_id();
+  const u32 q = blockIdx.x * PM_WARPS + w;
+  if (q >= nq) return;
+  const u32 p = q / B2_MAX_CODERS, c = q % B2_MAX_CODERS;
+  const u32 jb = p / B2_N_TRIPLES, t = p % B2_N_TRIPLES;
+  int max_len, sw, ec;
+  b2_triple(a.level, (int)t, max_len, sw, ec);
+  if ((int)t >= a.n_triples || (int)c >= ec || a.stat[2 * p + 1]) return;
+  const int ns = (int)a.jobs[jb].n_used + 2;
+  for (int e = l; e < ns; e += 32) S[w].leaf[e] = a.leaves[leaf_index(q, (u32)e)];
   __syncwarp();
+  ll_package_merge_warp(S[w], ns, max_len, a.lens + ((size_t)p * B2_MAX_CODERS + c) * B2_MAX_ALPHA);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -228,205 +382,156 @@ struct SelList {
   }
 };
 
-#define CT_THREADS 256
-
-struct ConstructSmem {
-  u32 hist[B2_MAX_CODERS][B2_MAX_ALPHA + 2];
-  unsigned long long lenpack[B2_MAX_ALPHA + 2];
-  u8 lens[B2_MAX_CODERS][B2_MAX_ALPHA + 2];
-  LLScratch ll[B2_MAX_CODERS];
-  u32 stat[8];
-  u32 red[40];
-  u32 defectors;
-  u32 selcost;
-};
-
-// Define_Descriptors (:635-657) given selectors: histograms -> Avoid_Zeros -> lengths -> lenpack
-__device__ void ct_define_descriptors(ConstructSmem &S, const u16 *__restrict__ m, const u8 *__restrict__ sel,
-                                      u32 M, u32 G, int A, int ec, int max_len) {
-  const u32 tid = threadIdx.x;
-  for (u32 i = tid; i < B2_MAX_CODERS * (B2_MAX_ALPHA + 2); i += CT_THREADS) (&S.hist[0][0])[i] = 0;
-  __syncthreads();
-  for (u32 g = tid; g < G; g += CT_THREADS) {
-    const u32 c = sel[g] - 1;
-    const u32 s0 = g * B2_GROUP_SIZE, s1 = min(s0 + B2_GROUP_SIZE, M);
-    u32 n0 = 0, n1 = 0;
-    for (u32 s = s0; s < s1; s++) {
-      u32 sym = m[s];
-      if (sym == 0) n0++;
-      else if (sym == 1) n1++;
-      else atomicAdd(&S.hist[c][sym], 1u);
-    }
-    if (n0) atomicAdd(&S.hist[c][0], n0);
-    if (n1) atomicAdd(&S.hist[c][1], n1);
-  }
-  __syncthreads();
-  // one warp per coder: Avoid_Zeros (:439-462) in parallel, then the serial length limiter on lane 0
-  const u32 w = warp_id(), l = lane_id();
-  if ((int)w < ec) {
-    u32 zeroes = 0;
-    for (int s = l; s < A; s += 32) zeroes += (S.hist[w][s] == 0);
-#pragma unroll
-    for (int o = 16; o; o >>= 1) zeroes += __shfl_xor_sync(0xffffffffu, zeroes, o);
-    if (zeroes > 0 && zeroes <= 100) { for (int s = l; s < A; s += 32) S.hist[w][s] = max(1u, S.hist[w][s]); }
-    else if (zeroes > 100) { for (int s = l; s < A; s += 32) { u32 v = S.hist[w][s]; S.hist[w][s] = v == 0 ? 1u : v * 2u; } }
-    __syncwarp();
-    ll_length_limited_warp(S.ll[w], S.hist[w], A, max_len, S.lens[w]);
-  }
-  __syncthreads();
-  for (int s = tid; s < A; s += CT_THREADS) {
-    unsigned long long p = 0;
-    for (int c = 0; c < ec; c++) p |= (unsigned long long)S.lens[c][s] << (10 * c);
-    S.lenpack[s] = p;
-  }
-  __syncthreads();
-}
-
-__device__ void ct_group_costs(ConstructSmem &S, const u16 *__restrict__ m, u32 M, u32 G,
-                               unsigned long long *__restrict__ gcost) {
-  for (u32 g = threadIdx.x; g < G; g += CT_THREADS) {
-    const u32 s0 = g * B2_GROUP_SIZE, s1 = min(s0 + B2_GROUP_SIZE, M);
-    unsigned long long acc = 0;
-    for (u32 s = s0; s < s1; s++) acc += S.lenpack[m[s]];
-    gcost[g] = acc;
-  }
-  __syncthreads();
-}
-
-// grid: (n_triples, n_jobs)
-__global__ void __launch_bounds__(CT_THREADS)
-k_construct(const B2Job *__restrict__ jobs, const u16 *__restrict__ mtf, const u32 *__restrict__ rank3,
-            const u32 *__restrict__ rank4, u8 *__restrict__ sel_all, unsigned long long *__restrict__ gcost_all,
-            u8 *__restrict__ lens_all, u32 *__restrict__ cost_all, u32 *__restrict__ low_all,
-            int level, int n_triples, u32 total_groups) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  ConstructSmem &S = *reinterpret_cast<ConstructSmem *>(smem_raw);
+// bits of every group under every coder (:731-737), six 10-bit fields per group
+__global__ void __launch_bounds__(256)
+k_ent_cost(EntArgs a) {
+  __shared__ unsigned long long lenpack[HSTRIDE];
   const int t = blockIdx.x;
   const u32 jb = blockIdx.y;
-  const B2Job &job = jobs[jb];
+  const u32 p = jb * B2_N_TRIPLES + t;
+  if (a.stat[2 * p + 1]) return;
+  const B2Job &job = a.jobs[jb];
   const u32 M = job.n_mtf, G = job.n_groups;
-  const int A = (int)job.n_used + 2;                 // symbols 0 .. EOB
-  const u16 *m = mtf + job.mtf_off;
+  const int A = (int)job.n_used + 2;
+  const u16 *m = a.mtf + job.mtf_off;
   int max_len, sw, ec;
-  b2_triple(level, t, max_len, sw, ec);
-  u8 *sel = sel_all + (size_t)t * total_groups + job.grp_off;
-  unsigned long long *gcost = gcost_all + (size_t)t * total_groups + job.grp_off;
-  const u32 tid = threadIdx.x;
-
-  // Initial_Clustering_by_Rank (:572-588, :625-631)
-  {
-    const u32 *rk = (sw == 3 ? rank3 : rank4) + job.grp_off;
-    const int attr_tab[5][6] = {{2, 1, 0, 0, 0, 0}, {3, 1, 2, 0, 0, 0}, {4, 2, 1, 3, 0, 0}, {5, 3, 1, 2, 4, 0}, {6, 4, 2, 1, 3, 5}};
-    for (u32 i = tid; i < G; i += CT_THREADS) {
-      // rank position i+1 belongs to range a (1-based) iff low_a <= i+1 <= high_a, high_a = a*G/ec
-      u32 pos1 = i + 1;
-      int a = 1;
-      while ((u64)a * G / ec < pos1) a++;
-      sel[(rk[i] & 0xFFFFu) - 1] = (u8)attr_tab[ec - 2][a - 1];
-    }
+  b2_triple(a.level, t, max_len, sw, ec);
+  const u8 *lens = a.lens + (size_t)p * B2_MAX_CODERS * B2_MAX_ALPHA;
+  for (int s = threadIdx.x; s < A; s += 256) {
+    unsigned long long v = 0;
+    for (int c = 0; c < ec; c++) v |= (unsigned long long)lens[c * B2_MAX_ALPHA + s] << (10 * c);
+    lenpack[s] = v;
   }
   __syncthreads();
+  unsigned long long *gcost = a.gcost + (size_t)t * a.total_groups + job.grp_off;
+  for (u32 g = threadIdx.x; g < G; g += 256) {
+    const u32 s0 = g * B2_GROUP_SIZE, s1 = min(s0 + B2_GROUP_SIZE, M);
+    unsigned long long acc = 0;
+    for (u32 s = s0; s < s1; s++) acc += lenpack[m[s]];
+    gcost[g] = acc;
+  }
+}
 
-  u32 defectors = 0;
-  for (int iteration = 1; iteration <= 10; iteration++) {                 // :793-802
-    ct_define_descriptors(S, m, sel, M, G, A, ec, max_len);
-    ct_group_costs(S, m, M, G, gcost);
-    // Simulate_Entropy_Coding_Variants_and_Reclassify (:661-753): serial through the selector MTF list
-    if (warp_id() == 0) {
-      const u32 l = lane_id();
-      SelList L; L.init();
-      u32 def = 0;
-      for (u32 g0 = 0; g0 < G; g0 += 32) {
-        const u32 g = g0 + l;
-        unsigned long long c = g < G ? gcost[g] : 0;
-        u32 cur = g < G ? sel[g] : 0;
-        u32 mine = cur;
-        const u32 cntk = min(32u, G - g0);
-        for (u32 k = 0; k < cntk; k++) {
-          const unsigned long long ck = __shfl_sync(0xffffffffu, c, k);
-          const u32 clk = __shfl_sync(0xffffffffu, cur, k);
-          // key = (cost << 6) | (coder0 << 3) | place: the minimum is the cheapest coder, lowest
-          // coder on ties (strict "<" scanning cl upward, :691-695), and carries its place along
-          u32 key = 0xFFFFFFFFu;
+// Simulate_Entropy_Coding_Variants_and_Reclassify (:661-753): serial through the selector MTF list.
+// One warp per block; lane t runs the sweep of triple t.
+__global__ void __launch_bounds__(32)
+k_ent_sweep(EntArgs a) {
+  const u32 jb = blockIdx.x;
+  const u32 t = threadIdx.x;
+  const B2Job &job = a.jobs[jb];
+  const u32 G = job.n_groups;
+  const u32 p = jb * B2_N_TRIPLES + t;
+  const bool active = (int)t < a.n_triples && !a.stat[2 * p + 1];
+  int max_len, sw, ec;
+  b2_triple(a.level, (int)(t < (u32)a.n_triples ? t : 0), max_len, sw, ec);
+  const size_t base = (size_t)(active ? t : 0) * a.total_groups + job.grp_off;
+  const unsigned long long *gc = a.gcost + base;
+  u8 *sel = a.sel + base;
+  SelList L; L.init();
+  u32 def = 0;
+  for (u32 g0 = 0; g0 < G; g0 += 4) {
+    unsigned long long c4[4] = {0, 0, 0, 0};
+    u32 s4 = 0;
+    if (active) {
+      const ulonglong2 x = *reinterpret_cast<const ulonglong2 *>(gc + g0);
+      const ulonglong2 y = *reinterpret_cast<const ulonglong2 *>(gc + g0 + 2);
+      c4[0] = x.x; c4[1] = x.y; c4[2] = y.x; c4[3] = y.y;
+      s4 = *reinterpret_cast<const u32 *>(sel + g0);
+    }
 #pragma unroll
-          for (int cl = 0; cl < 6; cl++) {
-            if (cl < ec) {
-              const u32 cost = (u32)((ck >> (10 * cl)) & 1023u) + L.pos[cl];
-              key = min(key, (cost << 6) | ((u32)cl << 3) | L.pos[cl]);
-            }
+    for (int k = 0; k < 4; k++) {
+      if (g0 + k < G) {
+        const unsigned long long ck = c4[k];
+        const u32 clk = (s4 >> (8 * k)) & 255u;
+        // key = (cost << 6) | (coder0 << 3) | place: the minimum is the cheapest coder, lowest coder
+        // on ties (strict "<" scanning cl upward, :691-695), and carries its place along
+        u32 key = 0xFFFFFFFFu;
+#pragma unroll
+        for (int cl = 0; cl < 6; cl++) {
+          if (cl < ec) {
+            const u32 cost = (u32)((ck >> (10 * cl)) & 1023u) + L.pos[cl];
+            key = min(key, (cost << 6) | ((u32)cl << 3) | L.pos[cl]);
           }
-          const u32 best0 = (key >> 3) & 7u;
-          if (best0 + 1 != clk) { def++; if (l == k) mine = best0 + 1; }
-          L.to_front(best0, key & 7u);
         }
-        if (g < G && mine != cur) sel[g] = (u8)mine;
+        const u32 best0 = (key >> 3) & 7u;
+        if (active && best0 + 1 != clk) { def++; sel[g0 + k] = (u8)(best0 + 1); }
+        L.to_front(best0, key & 7u);
       }
-      if (l == 0) S.defectors = def;
     }
-    __syncthreads();
-    defectors = S.defectors;
-    if (defectors == 0) break;
   }
-  if (defectors > 0) {                                                    // :803-807
-    ct_define_descriptors(S, m, sel, M, G, A, ec, max_len);
-    ct_group_costs(S, m, M, G, gcost);
+  if (active) { a.stat[2 * p] = def; if (def == 0) a.stat[2 * p + 1] = 1; }
+}
+
+// Compute_Selectors_Cost (:815-837), lanes = triples
+__global__ void __launch_bounds__(32)
+k_ent_selcost(EntArgs a) {
+  const u32 jb = blockIdx.x;
+  const u32 t = threadIdx.x;
+  const B2Job &job = a.jobs[jb];
+  const u32 G = job.n_groups;
+  const bool active = (int)t < a.n_triples;
+  const u8 *sel = a.sel + (size_t)(active ? t : 0) * a.total_groups + job.grp_off;
+  SelList L; L.init();
+  u32 bits = 0;
+  for (u32 g0 = 0; g0 < G; g0 += 4) {
+    const u32 s4 = *reinterpret_cast<const u32 *>(sel + g0);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (g0 + k < G) {
+        const u32 cl0 = ((s4 >> (8 * k)) & 255u) - 1;
+        const u32 pl = L.place(cl0);
+        bits += pl;
+        L.to_front(cl0, pl);
+      }
+    }
   }
-  // Cluster_Statistics (:757-778)
-  if (tid < 8) S.stat[tid] = 0;
-  if (tid == 0) S.selcost = 0;
+  if (active) a.selcost[jb * B2_N_TRIPLES + t] = bits;
+}
+
+// Cluster_Statistics (:757-778) + Compute_Total_Entropy_Cost (:811-887)
+__global__ void __launch_bounds__(256)
+k_ent_final(EntArgs a) {
+  __shared__ u32 stat[8];
+  __shared__ u32 red[8];
+  const int t = blockIdx.x;
+  const u32 jb = blockIdx.y;
+  const u32 p = jb * B2_N_TRIPLES + t;
+  const B2Job &job = a.jobs[jb];
+  const u32 G = job.n_groups;
+  const int A = (int)job.n_used + 2;
+  int max_len, sw, ec;
+  b2_triple(a.level, t, max_len, sw, ec);
+  const u8 *lens = a.lens + (size_t)p * B2_MAX_CODERS * B2_MAX_ALPHA;
+  const u8 *sel = a.sel + (size_t)t * a.total_groups + job.grp_off;
+  const unsigned long long *gcost = a.gcost + (size_t)t * a.total_groups + job.grp_off;
+  const u32 tid = threadIdx.x;
+  if (tid < 8) stat[tid] = 0;
   __syncthreads();
-  u32 data_bits = 0;
-  for (u32 g = tid; g < G; g += CT_THREADS) {
-    u32 c = sel[g];
-    atomicAdd(&S.stat[c], 1u);
-    data_bits += (u32)((gcost[g] >> (10 * (c - 1))) & 1023u);
+  u32 part = 0;
+  for (u32 g = tid; g < G; g += 256) {
+    const u32 c = sel[g];
+    atomicAdd(&stat[c], 1u);
+    part += (u32)((gcost[g] >> (10 * (c - 1))) & 1023u);           // data bits (:873-881)
   }
-  // Compute_Selectors_Cost (:815-837), serial on warp 0
-  if (warp_id() == 0) {
-    const u32 l = lane_id();
-    SelList L; L.init();
-    u32 bits = 0;
-    for (u32 g0 = 0; g0 < G; g0 += 32) {
-      const u32 g = g0 + l;
-      u32 cur = g < G ? sel[g] : 1;
-      const u32 cntk = min(32u, G - g0);
-      for (u32 k = 0; k < cntk; k++) {
-        const u32 cl0 = __shfl_sync(0xffffffffu, cur, k) - 1;
-        const u32 p = L.place(cl0);
-        bits += p;
-        L.to_front(cl0, p);
-      }
-    }
-    if (l == 0) S.selcost = bits;
+  for (int i = tid; i < ec * A; i += 256) {                         // code length tables (:839-865)
+    const int c = i / A, s = i % A;
+    const int cur = s == 0 ? lens[c * B2_MAX_ALPHA] : lens[c * B2_MAX_ALPHA + s - 1];
+    const int nw = lens[c * B2_MAX_ALPHA + s];
+    const int dlt = nw > cur ? nw - cur : cur - nw;
+    part += 2 * dlt + 1 + (s == 0 ? 5 : 0);
   }
-  // Compute_Huffman_Bit_Lengths_Cost (:839-865): 5 + sum (2*|delta| + 1)
-  u32 len_bits = 0;
-  for (int i = tid; i < ec * A; i += CT_THREADS) {
-    int c = i / A, s = i % A;
-    int cur = s == 0 ? S.lens[c][0] : S.lens[c][s - 1];
-    int nw = S.lens[c][s];
-    int dlt = nw > cur ? nw - cur : cur - nw;
-    len_bits += 2 * dlt + 1 + (s == 0 ? 5 : 0);
-  }
-  u32 part = data_bits + len_bits;
 #pragma unroll
   for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-  __syncthreads();
-  if (lane_id() == 0) S.red[warp_id()] = part;
+  if (lane_id() == 0) red[warp_id()] = part;
   __syncthreads();
   if (tid == 0) {
-    u32 total = S.selcost;
-    for (int w = 0; w < CT_THREADS / 32; w++) total += S.red[w];
+    u32 total = a.selcost[p];
+    for (int w = 0; w < 8; w++) total += red[w];
     const u32 uniform_usage = G / (u32)ec;
     u32 low = 0;
-    for (int c = 1; c <= ec; c++) if (S.stat[c] < uniform_usage / 2) low = 1;
-    cost_all[(size_t)jb * B2_N_TRIPLES + t] = total;
-    low_all[(size_t)jb * B2_N_TRIPLES + t] = low;
-  }
-  u8 *lo = lens_all + ((size_t)jb * B2_N_TRIPLES + t) * (B2_MAX_CODERS * B2_MAX_ALPHA);
-  for (int i = tid; i < B2_MAX_CODERS * B2_MAX_ALPHA; i += CT_THREADS) {
-    int c = i / B2_MAX_ALPHA, s = i % B2_MAX_ALPHA;
-    lo[i] = (c < ec && s < A) ? S.lens[c][s] : 0;
+    for (int c = 1; c <= ec; c++) if (stat[c] < uniform_usage / 2) low = 1;
+    a.cost_all[p] = total;
+    a.low_all[p] = low;
   }
 }
 
@@ -469,12 +574,12 @@ __global__ void k_choose(B2Job *jobs, u32 n_jobs, const u32 *__restrict__ cost_a
 }
 
 int b2k_entropy(cudaStream_t st, B2Job *d_jobs, u32 n_jobs, u32 max_groups_per_job, u32 total_groups,
-                const u16 *d_mtf, u32 *d_rank3, u32 *d_rank4, u8 *d_sel, unsigned long long *d_gcost,
-                u8 *d_lens, u32 *d_cost, u32 *d_low, int level) {
+                const u16 *d_mtf, u32 *d_rank3, u32 *d_rank4, u8 *d_sel, u8 *d_selprev, unsigned long long *d_gcost,
+                u32 *d_hist, u32 *d_leaves, u8 *d_lens, u32 *d_stat, u32 *d_selcost, u32 *d_cost, u32 *d_low,
+                int level, u64 *launches) {
   static bool attr_set = false;
   if (!attr_set) {
-    B2_CUDA_CHECK(cudaFuncSetAttribute(k_construct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ConstructSmem)));
-    B2_CUDA_CHECK(cudaFuncSetAttribute(k_rank_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, 18004 * 4));
+    B2_CUDA_CHECK(cudaFuncSetAttribute(k_rank_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, 18064 * 4));
     attr_set = true;
   }
   if (n_jobs == 0) return 0;
@@ -482,10 +587,28 @@ int b2k_entropy(cudaStream_t st, B2Job *d_jobs, u32 n_jobs, u32 max_groups_per_j
   k_group_keys<<<n_jobs, 256, 0, st>>>(d_jobs, d_mtf, d_rank3, d_rank4);
   size_t sort_smem = ((size_t)max_groups_per_job + 2) * 4;
   k_rank_sort<<<n_jobs * 2, 32, sort_smem, st>>>(d_jobs, d_rank3, d_rank4);
-  dim3 grid(n_triples, n_jobs);
-  k_construct<<<grid, CT_THREADS, sizeof(ConstructSmem), st>>>(d_jobs, d_mtf, d_rank3, d_rank4, d_sel, d_gcost, d_lens,
-                                                             d_cost, d_low, level, n_triples, total_groups);
+  EntArgs a;
+  a.jobs = d_jobs; a.mtf = d_mtf; a.rank3 = d_rank3; a.rank4 = d_rank4; a.sel = d_sel; a.selprev = d_selprev;
+  a.gcost = d_gcost; a.hist = d_hist; a.leaves = d_leaves; a.lens = d_lens; a.stat = d_stat; a.selcost = d_selcost;
+  a.cost_all = d_cost; a.low_all = d_low; a.total_groups = total_groups; a.level = level; a.n_triples = n_triples;
+  a.n_jobs = n_jobs;
+  const dim3 grid(n_triples, n_jobs);
+  const u32 nq = n_jobs * B2_N_TRIPLES * B2_MAX_CODERS;
+  k_ent_init<<<grid, 256, 0, st>>>(a);
+  *launches += 3;
+  for (int it = 0; it <= 10; it++) {
+    // iterations 1..10 (:793-802); round 10 is the extra Define_Descriptors for triples still moving (:803-807)
+    k_ent_hist<<<grid, 256, 0, st>>>(a);
+    k_ent_qsort<<<(nq + 31) / 32, 32, 0, st>>>(a, nq);
+    k_ent_pm<<<(nq + PM_WARPS - 1) / PM_WARPS, 32 * PM_WARPS, 0, st>>>(a, nq);
+    k_ent_cost<<<grid, 256, 0, st>>>(a);
+    *launches += 4;
+    if (it < 10) { k_ent_sweep<<<n_jobs, 32, 0, st>>>(a); *launches += 1; }
+  }
+  k_ent_selcost<<<n_jobs, 32, 0, st>>>(a);
+  k_ent_final<<<grid, 256, 0, st>>>(a);
   k_choose<<<(n_jobs + 127) / 128, 128, 0, st>>>(d_jobs, n_jobs, d_cost, d_low, level, n_triples);
+  *launches += 3;
   B2_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
