@@ -74,7 +74,7 @@ struct b2_encoder {
   // batch workspace
   DevBuf<B2Job> d_jobs;
   DevBuf<u8> d_text, d_bwt, d_idx;
-  DevBuf<u32> d_segmask, d_tilemask;
+  DevBuf<u32> d_m16, d_m256, d_tilemask;
   DevBuf<u64> d_keysA, d_keysB;
   DevBuf<u32> d_valsA, d_valsB, d_rank, d_grp;
   DevBuf<B2SortTile> d_tiles, d_mtiles;
@@ -137,14 +137,15 @@ void balance_window(int level, i64 &lo, i64 &hi) {
 int ensure_batch_workspace(b2_encoder *e, size_t T, size_t J) {
   const size_t max_tiles = T / B2_SORT_TILE + J + 8;
   const size_t max_mtiles = T / B2_MTF_TILE + J + 8;
-  const size_t GT = T / B2_GROUP_SIZE + 8 * J + 8;
+  const size_t GT = T / B2_GROUP_SIZE + 20 * J + 32;
   B2_TRY(e->d_jobs.ensure(J));
   B2_TRY(e->d_text.ensure(T + 64)); B2_TRY(e->d_bwt.ensure(T + 64)); B2_TRY(e->d_idx.ensure(T + 64));
   B2_TRY(e->d_keysA.ensure(T)); B2_TRY(e->d_keysB.ensure(T));
   B2_TRY(e->d_valsA.ensure(T)); B2_TRY(e->d_valsB.ensure(T));
   B2_TRY(e->d_rank.ensure(T)); B2_TRY(e->d_grp.ensure(T));
   B2_TRY(e->d_tiles.ensure(max_tiles)); B2_TRY(e->d_mtiles.ensure(max_mtiles));
-  B2_TRY(e->d_segmask.ensure((T / 64 + 2 * J + 8) * 8)); B2_TRY(e->d_tilemask.ensure(max_mtiles * 8));
+  B2_TRY(e->d_m16.ensure((T / 16 + 8 * J + 8) * 8)); B2_TRY(e->d_m256.ensure((T / 256 + 2 * J + 8) * 8));
+  B2_TRY(e->d_tilemask.ensure(max_mtiles * 8));
   B2_TRY(e->d_sj.ensure(J));
   B2_TRY(e->d_hist.ensure(max_tiles * 256)); B2_TRY(e->d_digit_base.ensure(J * 256));
   B2_TRY(e->d_tile_head.ensure(max_tiles)); B2_TRY(e->d_carry.ensure(max_tiles));
@@ -173,7 +174,7 @@ BatchLayout layout_jobs(std::vector<B2Job> &jobs, int level) {
   u64 pos = 0, mpos = 0;
   for (auto &j : jobs) {
     u64 cap = std::min<u64>((u64)j.raw_len * 5 / 4 + 8, (u64)level * 100000 + 64);
-    cap = (cap + 63) & ~63ull;
+    cap = (cap + 255) & ~255ull;     // 256-aligned slots: the MTF segment masks are addressed by pos_off >> 4 / >> 8
     j.pos_off = (u32)pos; j.cap = (u32)cap;
     pos += cap;
     j.mtf_off = (u32)mpos;
@@ -206,7 +207,7 @@ int run_batch(b2_encoder *e, const u8 *d_in, std::vector<B2Job> &jobs) {
   for (u32 j = 0; j < J; j++) {
     B2Job &b = e->batch_jobs[j];
     if (b.n > b.cap) B2_FAIL(B2_ERR_INTERNAL, "RLE1 output exceeds its slot");
-    u32 gmax = (b.n / B2_GROUP_SIZE + 2 + 3) & ~3u;       // multiple of 4: vector loads in k_ent_sweep
+    u32 gmax = (b.n / B2_GROUP_SIZE + 2 + 15) & ~15u;     // multiple of 16: vector loads in k_ent_sweep / k_ent_selcost
     b.grp_off = gpos; gpos += gmax;
     max_g = std::max(max_g, gmax);
     ids[j] = j; ns[j] = b.n;
@@ -234,7 +235,7 @@ int run_batch(b2_encoder *e, const u8 *d_in, std::vector<B2Job> &jobs) {
     StageTimer tm(e, 3);
     if (!mtiles.empty())
       B2_CUDA_CHECK(cudaMemcpyAsync(e->d_mtiles.p, mtiles.data(), mtiles.size() * sizeof(B2SortTile), cudaMemcpyHostToDevice, st));
-    B2_TRY(b2k_mtf(st, e->d_jobs.p, J, e->d_mtiles.p, (u32)mtiles.size(), e->d_bwt.p, e->d_segmask.p, e->d_tilemask.p, e->d_idx.p, e->d_mtf.p));
+    B2_TRY(b2k_mtf(st, e->d_jobs.p, J, e->d_mtiles.p, (u32)mtiles.size(), e->d_bwt.p, e->d_m16.p, e->d_m256.p, e->d_tilemask.p, e->d_idx.p, e->d_mtf.p));
     e->launches_other += 3;
   }
   const u32 total_groups = gpos;
@@ -360,7 +361,7 @@ int encode_device(b2_encoder *e, const u8 *d_in, u64 n, i64 size_hint, u64 *out_
             B2Job j; memset(&j, 0, sizeof j);
             j.raw_off = P.start + sl.first; j.raw_len = sl.second;
             add.push_back(j);
-            addpos += std::min<u64>((u64)sl.second * 5 / 4 + 72, (u64)level * 100000 + 128);
+            addpos += std::min<u64>((u64)sl.second * 5 / 4 + 264, (u64)level * 100000 + 320);
           } else id = it->second;
           P.tactic_jobs[t].push_back(id);
         }
@@ -496,7 +497,7 @@ void b2_destroy(b2_encoder *e) {
   e->d_ct.release(); e->d_T.release(); e->d_in.release(); e->d_out.release(); e->d_chunks.release();
   e->d_scalars.release(); e->d_seg.release(); e->d_nseg.release(); e->d_cut_first.release(); e->d_cut_last.release();
   e->d_cut_tsum.release(); e->d_cut_carry.release(); e->d_cut_tincl.release(); e->d_jobs.release(); e->d_text.release();
-  e->d_bwt.release(); e->d_idx.release(); e->d_segmask.release(); e->d_tilemask.release(); e->d_keysA.release(); e->d_keysB.release(); e->d_valsA.release();
+  e->d_bwt.release(); e->d_idx.release(); e->d_m16.release(); e->d_m256.release(); e->d_tilemask.release(); e->d_keysA.release(); e->d_keysB.release(); e->d_valsA.release();
   e->d_valsB.release(); e->d_rank.release(); e->d_grp.release(); e->d_tiles.release(); e->d_mtiles.release();
   e->d_sj.release(); e->d_hist.release(); e->d_digit_base.release(); e->d_tile_head.release(); e->d_carry.release(); e->d_unsorted.release();
   e->d_mtf.release(); e->d_rank3.release(); e->d_rank4.release(); e->d_sel.release(); e->d_selpos.release();
@@ -595,7 +596,7 @@ int b2_dbg_block(b2_encoder *e, const uint8_t *raw, uint32_t len, uint8_t *rle_o
   if (rle_out && b.n) B2_CUDA_CHECK(cudaMemcpyAsync(rle_out, e->d_text.p + b.pos_off, b.n, cudaMemcpyDeviceToHost, st));
   if (bwt_out && b.n) B2_CUDA_CHECK(cudaMemcpyAsync(bwt_out, e->d_bwt.p + b.pos_off, b.n, cudaMemcpyDeviceToHost, st));
   if (mtf_out) B2_CUDA_CHECK(cudaMemcpyAsync(mtf_out, e->d_mtf.p + b.mtf_off, (size_t)b.n_mtf * 2, cudaMemcpyDeviceToHost, st));
-  const u32 total_groups = (b.n / B2_GROUP_SIZE + 2 + 3) & ~3u;   // single job: grp arena size == its own bound
+  const u32 total_groups = (b.n / B2_GROUP_SIZE + 2 + 15) & ~15u;   // single job: grp arena size == its own bound
   if (sel_out) B2_CUDA_CHECK(cudaMemcpyAsync(sel_out, e->d_sel.p + (size_t)b.best * total_groups + b.grp_off, b.n_groups, cudaMemcpyDeviceToHost, st));
   if (lens_out) B2_CUDA_CHECK(cudaMemcpyAsync(lens_out, e->d_lens.p + (size_t)b.best * (B2_MAX_CODERS * B2_MAX_ALPHA), B2_MAX_CODERS * B2_MAX_ALPHA, cudaMemcpyDeviceToHost, st));
   u64 nbytes = (b.nbits + 7) >> 3;

@@ -429,20 +429,36 @@ k_ent_sweep(EntArgs a) {
   u8 *sel = a.sel + base;
   SelList L; L.init();
   u32 def = 0;
-  for (u32 g0 = 0; g0 < G; g0 += 4) {
-    unsigned long long c4[4] = {0, 0, 0, 0};
-    u32 s4 = 0;
-    if (active) {
-      const ulonglong2 x = *reinterpret_cast<const ulonglong2 *>(gc + g0);
-      const ulonglong2 y = *reinterpret_cast<const ulonglong2 *>(gc + g0 + 2);
-      c4[0] = x.x; c4[1] = x.y; c4[2] = y.x; c4[3] = y.y;
-      s4 = *reinterpret_cast<const u32 *>(sel + g0);
-    }
+  // 8 groups per step, loaded one step ahead (register double buffer) and prefetched into L2 further ahead
+  unsigned long long nx[8];
+  u32 ns0 = 0, ns1 = 0;
+  auto load8 = [&](u32 g0) {
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
+    for (int k = 0; k < 8; k++) nx[k] = 0;
+    ns0 = ns1 = 0;
+    if (active && g0 < G) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const ulonglong2 x = *reinterpret_cast<const ulonglong2 *>(gc + g0 + 2 * k);
+        nx[2 * k] = x.x; nx[2 * k + 1] = x.y;
+      }
+      const uint2 sv = *reinterpret_cast<const uint2 *>(sel + g0);
+      ns0 = sv.x; ns1 = sv.y;
+      if (g0 + 64 < G) asm volatile("prefetch.global.L2 [%0];" ::"l"(gc + g0 + 64));
+    }
+  };
+  load8(0);
+  for (u32 g0 = 0; g0 < G; g0 += 8) {
+    unsigned long long c8[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) c8[k] = nx[k];
+    const u32 s0 = ns0, s1 = ns1;
+    load8(g0 + 8);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
       if (g0 + k < G) {
-        const unsigned long long ck = c4[k];
-        const u32 clk = (s4 >> (8 * k)) & 255u;
+        const unsigned long long ck = c8[k];
+        const u32 clk = ((k < 4 ? s0 : s1) >> (8 * (k & 3))) & 255u;
         // key = (cost << 6) | (coder0 << 3) | place: the minimum is the cheapest coder, lowest coder
         // on ties (strict "<" scanning cl upward, :691-695), and carries its place along
         u32 key = 0xFFFFFFFFu;
@@ -473,12 +489,15 @@ k_ent_selcost(EntArgs a) {
   const u8 *sel = a.sel + (size_t)(active ? t : 0) * a.total_groups + job.grp_off;
   SelList L; L.init();
   u32 bits = 0;
-  for (u32 g0 = 0; g0 < G; g0 += 4) {
-    const u32 s4 = *reinterpret_cast<const u32 *>(sel + g0);
+  uint4 nx = *reinterpret_cast<const uint4 *>(sel);
+  for (u32 g0 = 0; g0 < G; g0 += 16) {
+    const uint4 cur = nx;
+    if (g0 + 16 < G) nx = *reinterpret_cast<const uint4 *>(sel + g0 + 16);
+    const u32 w4[4] = {cur.x, cur.y, cur.z, cur.w};
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
+    for (int k = 0; k < 16; k++) {
       if (g0 + k < G) {
-        const u32 cl0 = ((s4 >> (8 * k)) & 255u) - 1;
+        const u32 cl0 = ((w4[k >> 2] >> (8 * (k & 3))) & 255u) - 1;
         const u32 pl = L.place(cl0);
         bits += pl;
         L.to_front(cl0, pl);

@@ -8,10 +8,10 @@
 // function of the data before i, so every position is computed independently (k_mtf_index).
 //
 // To keep the backward search short, k_mtf_masks first records which byte values occur in every
-// 64-position segment (256-bit mask) and in every 4096-position tile; a search that leaves its own
-// segment skips whole segments / tiles by OR-ing their masks until it meets one that contains the
-// symbol, and only then walks bytes again.  Worst case per position: 2*64 byte steps + 2*63
-// segment masks + (tiles of the block) tile masks.
+// 16-position segment (256-bit mask), every 256-position segment and every 4096-position tile; a
+// search that leaves its own 16-segment skips whole segments / tiles by OR-ing their masks until it
+// meets one that contains the symbol, descends, and only then walks bytes again.  Worst case per
+// position: 2*15 byte steps + 4*15 segment masks + (tiles of the block) tile masks.
 //
 // The zero-run coding (:348-363, :400-410) is a max-scan (last non-zero position) plus an add-scan
 // (output offsets) per block (k_rle2).
@@ -34,51 +34,57 @@ __device__ __forceinline__ void seen_set(u32 *seen, u32 x) {
   for (int w = 0; w < 8; w++) seen[w] |= (w == (int)wsel) ? bit : 0u;
 }
 
-// One CTA per 4096-position tile: 64 segment masks + the tile mask.
+// One CTA per 4096-position tile; thread t owns the 16 positions [16t, 16t+16) of the tile:
+// 256 masks of 16 positions, 16 masks of 256 positions, 1 tile mask.
 __global__ void __launch_bounds__(MI_THREADS)
 k_mtf_masks(const B2SortTile *__restrict__ tiles, const B2Job *__restrict__ jobs, const u8 *__restrict__ bwt,
-            u32 *__restrict__ segmask, u32 *__restrict__ tilemask) {
+            u32 *__restrict__ m16, u32 *__restrict__ m256, u32 *__restrict__ tilemask) {
   __shared__ u32 tm[8];
   const B2SortTile tl = tiles[blockIdx.x];
   const B2Job &job = jobs[tl.job];
   const u32 n = job.n, off = job.pos_off;
   const u8 *d = bwt + off;
-  const u32 w = warp_id(), l = lane_id();
-  if (threadIdx.x < 8) tm[threadIdx.x] = 0;
+  const u32 tid = threadIdx.x, l = lane_id();
+  if (tid < 8) tm[tid] = 0;
   __syncthreads();
-  u32 acc_tile = 0;   // lane q < 8 accumulates word q of the tile mask over this warp's segments
-  for (int sgi = 0; sgi < 8; sgi++) {
-    const u32 s = (tl.start >> 6) + w * 8 + sgi;       // block-relative segment
-    const u32 p0 = s << 6;
-    if (p0 >= n) break;
-    u32 mine = 0;                                      // lane q < 8 holds word q of the segment mask
+  const u32 p0 = tl.start + tid * 16;
+  u32 mk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (p0 < n) {
+    const uint4 v = *reinterpret_cast<const uint4 *>(d + p0);      // pos_off is a multiple of 64
+    const u32 w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-    for (int h = 0; h < 2; h++) {
-      const u32 p = p0 + h * 32 + l;
-      const bool v = p < n;
-      const u32 b = v ? d[p] : 0;
-#pragma unroll
-      for (int q = 0; q < 8; q++) {
-        u32 r = __reduce_or_sync(0xffffffffu, (v && (b >> 5) == (u32)q) ? (1u << (b & 31)) : 0u);
-        if (l == (u32)q) mine |= r;
-      }
+    for (int k = 0; k < 16; k++) {
+      if (p0 + k < n) seen_set(mk, (w[k >> 2] >> (8 * (k & 3))) & 255u);
     }
-    if (l < 8) { segmask[((size_t)(off >> 6) + s) * 8 + l] = mine; acc_tile |= mine; }
+    u32 *o = m16 + ((size_t)(off >> 4) + (p0 >> 4)) * 8;
+    *reinterpret_cast<uint4 *>(o) = make_uint4(mk[0], mk[1], mk[2], mk[3]);
+    *reinterpret_cast<uint4 *>(o + 4) = make_uint4(mk[4], mk[5], mk[6], mk[7]);
   }
-  if (l < 8 && acc_tile) atomicOr(&tm[l], acc_tile);
+  // 256-position masks: OR over the 16 threads of a half warp
+  const u32 hm = (l < 16) ? 0x0000FFFFu : 0xFFFF0000u;
+  u32 r[8];
+#pragma unroll
+  for (int q = 0; q < 8; q++) r[q] = __reduce_or_sync(hm, mk[q]);
+  if ((l & 15) == 0 && p0 < n) {
+    u32 *o = m256 + ((size_t)(off >> 8) + (p0 >> 8)) * 8;
+#pragma unroll
+    for (int q = 0; q < 8; q++) { o[q] = r[q]; if (r[q]) atomicOr(&tm[q], r[q]); }
+  }
   __syncthreads();
-  if (threadIdx.x < 8) tilemask[(size_t)blockIdx.x * 8 + threadIdx.x] = tm[threadIdx.x];
+  if (tid < 8) tilemask[(size_t)blockIdx.x * 8 + tid] = tm[tid];
 }
 
 __global__ void __launch_bounds__(MI_THREADS)
 k_mtf_index(const B2SortTile *__restrict__ tiles, const B2Job *__restrict__ jobs, const u8 *__restrict__ bwt,
-            const u32 *__restrict__ segmask, const u32 *__restrict__ tilemask, u8 *__restrict__ idx_out) {
+            const u32 *__restrict__ m16, const u32 *__restrict__ m256, const u32 *__restrict__ tilemask,
+            u8 *__restrict__ idx_out) {
   const B2SortTile tl = tiles[blockIdx.x];
   const B2Job &job = jobs[tl.job];
   const u32 n = job.n, off = job.pos_off;
   const u8 *d = bwt + off;
-  const u32 *sm = segmask + (size_t)(off >> 6) * 8;          // block-relative segment masks
-  const u32 *tmk = tilemask + (size_t)job.tile0 * 8;         // block-relative tile masks
+  const u32 *s16 = m16 + (size_t)(off >> 4) * 8;             // block-relative masks
+  const u32 *s256 = m256 + (size_t)(off >> 8) * 8;
+  const u32 *tmk = tilemask + (size_t)job.tile0 * 8;
   for (int k = 0; k < MI_ITEMS; k++) {
     const u32 i = tl.start + k * MI_THREADS + threadIdx.x;
     if (i >= n) continue;
@@ -89,40 +95,43 @@ k_mtf_index(const B2SortTile *__restrict__ tiles, const B2Job *__restrict__ jobs
       u32 seen[8] = {0, 0, 0, 0, 0, 0, 0, 0};
       const u32 bw = b >> 5, bbit = 1u << (b & 31);
       bool found = false;
-      // 1. own segment, byte by byte
-      const i32 seg = (i32)(i >> 6);
-      for (i32 j = (i32)i - 1; j >= (seg << 6); j--) {
-        u32 x = d[j];
+      // 1. own 16-segment, byte by byte
+      const i32 g16 = (i32)(i >> 4);
+      for (i32 j = (i32)i - 1; j >= (g16 << 4); j--) {
+        const u32 x = d[j];
         if (x == b) { found = true; break; }
         seen_set(seen, x);
       }
-      i32 hit_seg = -1;
       if (!found) {
-        // 2. earlier segments of the own tile
-        const i32 tile = (i32)(i >> 12);
-        for (i32 s = seg - 1; s >= (tile << 6); s--) {
-          const u32 *m = sm + (size_t)s * 8;
-          if (m[bw] & bbit) { hit_seg = s; break; }
-          mask_or(seen, m);
-        }
-        // 3. earlier tiles
-        if (hit_seg < 0) {
+        i32 hit16 = -1;
+        // descend into a 256-segment known (or not) to contain b: its 16-segments from `from` down
+        auto scan16 = [&](i32 from, i32 lo) {
+          for (i32 s = from; s >= lo; s--) {
+            const u32 *m = s16 + (size_t)s * 8;
+            if (m[bw] & bbit) { hit16 = s; return; }
+            mask_or(seen, m);
+          }
+        };
+        auto scan256 = [&](i32 from, i32 lo) {
+          for (i32 s = from; s >= lo; s--) {
+            const u32 *m = s256 + (size_t)s * 8;
+            if (m[bw] & bbit) { scan16((s << 4) + 15, s << 4); return; }
+            mask_or(seen, m);
+          }
+        };
+        const i32 g256 = (i32)(i >> 8), tile = (i32)(i >> 12);
+        scan16(g16 - 1, g256 << 4);                          // 2. earlier 16-segments of the own 256-segment
+        if (hit16 < 0) scan256(g256 - 1, tile << 4);         // 3. earlier 256-segments of the own tile
+        if (hit16 < 0) {                                     // 4. earlier tiles
           for (i32 t = tile - 1; t >= 0; t--) {
             const u32 *m = tmk + (size_t)t * 8;
-            if (m[bw] & bbit) {
-              for (i32 s = (t << 6) + 63; s >= (t << 6); s--) {
-                const u32 *ms = sm + (size_t)s * 8;
-                if (ms[bw] & bbit) { hit_seg = s; break; }
-                mask_or(seen, ms);
-              }
-              break;
-            }
+            if (m[bw] & bbit) { scan256((t << 4) + 15, t << 4); break; }
             mask_or(seen, m);
           }
         }
-        if (hit_seg >= 0) {
-          for (i32 j = (hit_seg << 6) + 63; j >= (hit_seg << 6); j--) {
-            u32 x = d[j];
+        if (hit16 >= 0) {
+          for (i32 j = (hit16 << 4) + 15; j >= (hit16 << 4); j--) {
+            const u32 x = d[j];
             if (x == b) { found = true; break; }
             seen_set(seen, x);
           }
@@ -223,10 +232,10 @@ k_rle2(B2Job *jobs, const u8 *__restrict__ idx_in, u16 *__restrict__ mtf) {
 }
 
 int b2k_mtf(cudaStream_t st, B2Job *d_jobs, u32 n_jobs, const B2SortTile *d_tiles, u32 n_tiles,
-            const u8 *d_bwt, u32 *d_segmask, u32 *d_tilemask, u8 *d_idx, u16 *d_mtf) {
+            const u8 *d_bwt, u32 *d_m16, u32 *d_m256, u32 *d_tilemask, u8 *d_idx, u16 *d_mtf) {
   if (n_tiles) {
-    k_mtf_masks<<<n_tiles, MI_THREADS, 0, st>>>(d_tiles, d_jobs, d_bwt, d_segmask, d_tilemask);
-    k_mtf_index<<<n_tiles, MI_THREADS, 0, st>>>(d_tiles, d_jobs, d_bwt, d_segmask, d_tilemask, d_idx);
+    k_mtf_masks<<<n_tiles, MI_THREADS, 0, st>>>(d_tiles, d_jobs, d_bwt, d_m16, d_m256, d_tilemask);
+    k_mtf_index<<<n_tiles, MI_THREADS, 0, st>>>(d_tiles, d_jobs, d_bwt, d_m16, d_m256, d_tilemask, d_idx);
   }
   if (n_jobs) k_rle2<<<n_jobs, R2_THREADS, 0, st>>>(d_jobs, d_idx, d_mtf);
   B2_CUDA_CHECK(cudaGetLastError());
