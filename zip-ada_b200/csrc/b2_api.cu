@@ -5,16 +5,24 @@
 // with Block_Split_Parallel's four tactics (:1214-1359) expanded into a de-duplicated list of
 // blocks ("jobs") that are encoded in batches on the device.  The only serial cross-chunk data are
 // scalars — incoming bit offset, winner, combined CRC — replayed here in O(#chunks).
+//
+// Batches are pipelined: each of W workspaces owns a CUDA stream and a host worker thread, so the
+// latency-bound kernels of one batch (ranking heap sorts, selector sweeps, scans) overlap with the
+// bandwidth-bound kernels (radix passes) of another.  Winners are resolved strictly in chunk order.
 #include "b2_common.cuh"
 #include "b2_kernels.h"
 #include "../../include/b2gpu.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <condition_variable>
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 static thread_local std::string g_last_error = "";
@@ -43,35 +51,23 @@ template <class T> struct DevBuf {
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
-struct HostJob {           // host mirror of a block
-  u64 raw_off; u32 raw_len;
-};
-
 struct ChunkPlan {
   u64 start; u32 len; u32 cap;
-  std::vector<u32> tactic_jobs[4];   // global job ids, in stream order
+  std::vector<u32> tactic_jobs[4];   // job ids inside the chunk's batch, in stream order
   u32 n_seg[2];
   int n_tactics;
 };
 
-}  // namespace
+struct Batch {
+  u32 c0, c1;                        // chunk range [c0, c1)
+  std::vector<B2Job> jobs;
+};
 
-struct b2_encoder {
-  int level = 9, device = 0;
+// Everything one in-flight batch needs on the device.
+struct Workspace {
   cudaStream_t st = nullptr;
-  int timing = 0;                     // 0 off, 1 scatter + call events, 2 also per-stage timers (adds syncs)
-  // constants
-  DevBuf<B2CrcTables> d_ct;
-  DevBuf<double> d_T;
-  // stream-level
-  DevBuf<u8> d_in;
-  DevBuf<u32> d_out;
-  DevBuf<B2Chunk> d_chunks;
-  DevBuf<u32> d_scalars;     // [0] n_chunks, [2..3] total_words (u64)
-  DevBuf<u32> d_seg, d_nseg;
-  DevBuf<u32> d_cut_first, d_cut_last, d_cut_tsum;
-  DevBuf<u64> d_cut_carry, d_cut_tincl;
-  // batch workspace
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  DevBuf<u32> d_scalars;
   DevBuf<B2Job> d_jobs;
   DevBuf<u8> d_text, d_bwt, d_idx;
   DevBuf<u32> d_m16, d_m256, d_tilemask;
@@ -91,17 +87,58 @@ struct b2_encoder {
   DevBuf<u32> d_bits;
   DevBuf<B2ConcatItem> d_items;
   u32 *h_unsorted = nullptr; size_t h_unsorted_cap = 0;
+  std::vector<B2Job> batch_jobs;      // jobs of the current batch, as read back
+  u32 total_groups = 0;
+  // accumulated by this workspace during one encode call
+  B2SortStats sort_stats;
+  u64 launches = 0, blocks = 0, block_bytes = 0;
+  double stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
+  void release() {
+    d_scalars.release(); d_jobs.release(); d_text.release(); d_bwt.release(); d_idx.release(); d_m16.release();
+    d_m256.release(); d_tilemask.release(); d_keysA.release(); d_keysB.release(); d_valsA.release(); d_valsB.release();
+    d_rank.release(); d_grp.release(); d_tiles.release(); d_mtiles.release(); d_sj.release(); d_hist.release();
+    d_digit_base.release(); d_tile_head.release(); d_carry.release(); d_unsorted.release(); d_mtf.release();
+    d_rank3.release(); d_rank4.release(); d_sel.release(); d_selprev.release(); d_selpos.release(); d_lens.release();
+    d_ehist.release(); d_leaves.release(); d_estat.release(); d_selcost.release(); d_gcost.release(); d_cost.release();
+    d_low.release(); d_bits.release(); d_items.release();
+    if (h_unsorted) cudaFreeHost(h_unsorted);
+    h_unsorted = nullptr; h_unsorted_cap = 0;
+    if (ev[0]) cudaEventDestroy(ev[0]);
+    if (ev[1]) cudaEventDestroy(ev[1]);
+    if (st) cudaStreamDestroy(st);
+    st = nullptr; ev[0] = ev[1] = nullptr;
+  }
+};
+
+}  // namespace
+
+struct b2_encoder {
+  int level = 9, device = 0;
+  cudaStream_t st = nullptr;            // stream of the stream-level work (cut, segment, copies, footer)
+  int timing = 0;                       // 0 off, 1 scatter + call events, 2 also per-stage timers (adds syncs, no pipelining)
+  // constants
+  DevBuf<B2CrcTables> d_ct;
+  DevBuf<double> d_T;
+  // stream-level
+  DevBuf<u8> d_in;
+  DevBuf<u32> d_out;
+  DevBuf<B2Chunk> d_chunks;
+  DevBuf<u32> d_scalars;
+  DevBuf<u32> d_seg, d_nseg;
+  DevBuf<u32> d_cut_first, d_cut_last, d_cut_tsum;
+  DevBuf<u64> d_cut_carry, d_cut_tincl;
+  std::vector<Workspace *> ws;
   // host state of the last call
   std::vector<B2Chunk> chunks;
   std::vector<u32> nseg, seg;
   std::vector<b2_chunk_trace> trace;
-  std::vector<B2Job> batch_jobs;      // jobs of the last batch, as read back
   b2_stats stats;
   B2SortStats sort_stats;
-  size_t batch_positions = 96u << 20;   // positions per batch (env B2GPU_BATCH_POSITIONS)
-  size_t batch_jobs_max = 4096;
+  size_t batch_positions = 512u << 20;  // positions per batch (env B2GPU_BATCH_POSITIONS); big batches amortise the latency-bound kernels
+  size_t batch_jobs_max = 4096;         // blocks per batch    (env B2GPU_BATCH_JOBS)
+  int n_workspaces = 1;                 // batches in flight   (env B2GPU_PIPELINE)
   u64 launches_other = 0;
-  // timing
   cudaEvent_t ev[2] = {nullptr, nullptr};
   cudaEvent_t ev_call[2] = {nullptr, nullptr};
 };
@@ -109,14 +146,16 @@ struct b2_encoder {
 namespace {
 
 struct StageTimer {
-  b2_encoder *e; int stage; bool on;
-  StageTimer(b2_encoder *e_, int s) : e(e_), stage(s), on(e_->timing >= 2) { if (on) cudaEventRecord(e->ev[0], e->st); }
+  cudaStream_t st; cudaEvent_t *ev; double *acc; bool on;
+  StageTimer(b2_encoder *e, cudaStream_t st_, cudaEvent_t *ev_, double *acc_) : st(st_), ev(ev_), acc(acc_), on(e->timing >= 2) {
+    if (on) cudaEventRecord(ev[0], st);
+  }
   ~StageTimer() {
     if (on) {
-      cudaEventRecord(e->ev[1], e->st);
-      cudaEventSynchronize(e->ev[1]);
-      float ms = 0; cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]);
-      e->stats.stage_ms[stage] += ms;
+      cudaEventRecord(ev[1], st);
+      cudaEventSynchronize(ev[1]);
+      float ms = 0; cudaEventElapsedTime(&ms, ev[0], ev[1]);
+      *acc += ms;
     }
   }
 };
@@ -134,43 +173,44 @@ void balance_window(int level, i64 &lo, i64 &hi) {
   }
 }
 
-int ensure_batch_workspace(b2_encoder *e, size_t T, size_t J) {
+int ensure_batch_workspace(Workspace *w, size_t T, size_t J) {
   const size_t max_tiles = T / B2_SORT_TILE + J + 8;
   const size_t max_mtiles = T / B2_MTF_TILE + J + 8;
   const size_t GT = T / B2_GROUP_SIZE + 20 * J + 32;
-  B2_TRY(e->d_jobs.ensure(J));
-  B2_TRY(e->d_text.ensure(T + 64)); B2_TRY(e->d_bwt.ensure(T + 64)); B2_TRY(e->d_idx.ensure(T + 64));
-  B2_TRY(e->d_keysA.ensure(T)); B2_TRY(e->d_keysB.ensure(T));
-  B2_TRY(e->d_valsA.ensure(T)); B2_TRY(e->d_valsB.ensure(T));
-  B2_TRY(e->d_rank.ensure(T)); B2_TRY(e->d_grp.ensure(T));
-  B2_TRY(e->d_tiles.ensure(max_tiles)); B2_TRY(e->d_mtiles.ensure(max_mtiles));
-  B2_TRY(e->d_m16.ensure((T / 16 + 8 * J + 8) * 8)); B2_TRY(e->d_m256.ensure((T / 256 + 2 * J + 8) * 8));
-  B2_TRY(e->d_tilemask.ensure(max_mtiles * 8));
-  B2_TRY(e->d_sj.ensure(J));
-  B2_TRY(e->d_hist.ensure(max_tiles * 256)); B2_TRY(e->d_digit_base.ensure(J * 256));
-  B2_TRY(e->d_tile_head.ensure(max_tiles)); B2_TRY(e->d_carry.ensure(max_tiles));
-  B2_TRY(e->d_unsorted.ensure(J));
-  B2_TRY(e->d_mtf.ensure(T + 16 * J + 64));
-  B2_TRY(e->d_rank3.ensure(GT)); B2_TRY(e->d_rank4.ensure(GT));
-  B2_TRY(e->d_sel.ensure(GT * B2_N_TRIPLES + 64)); B2_TRY(e->d_selprev.ensure(GT * B2_N_TRIPLES + 64)); B2_TRY(e->d_selpos.ensure(GT));
-  B2_TRY(e->d_ehist.ensure(J * B2_N_TRIPLES * B2_MAX_CODERS * 260)); B2_TRY(e->d_leaves.ensure((J * B2_N_TRIPLES * B2_MAX_CODERS + 64) * 260));
-  B2_TRY(e->d_estat.ensure(J * B2_N_TRIPLES * 2)); B2_TRY(e->d_selcost.ensure(J * B2_N_TRIPLES));
-  B2_TRY(e->d_gcost.ensure(GT * B2_N_TRIPLES + 64));
-  B2_TRY(e->d_lens.ensure(J * B2_N_TRIPLES * B2_MAX_CODERS * B2_MAX_ALPHA));
-  B2_TRY(e->d_cost.ensure(J * B2_N_TRIPLES)); B2_TRY(e->d_low.ensure(J * B2_N_TRIPLES));
-  B2_TRY(e->d_items.ensure(J));
-  if (J > e->h_unsorted_cap) {
-    if (e->h_unsorted) cudaFreeHost(e->h_unsorted);
-    B2_CUDA_CHECK(cudaMallocHost((void **)&e->h_unsorted, (J + 64) * sizeof(u32)));
-    e->h_unsorted_cap = J + 64;
+  B2_TRY(w->d_scalars.ensure(16));
+  B2_TRY(w->d_jobs.ensure(J));
+  B2_TRY(w->d_text.ensure(T + 64)); B2_TRY(w->d_bwt.ensure(T + 64)); B2_TRY(w->d_idx.ensure(T + 64));
+  B2_TRY(w->d_m16.ensure((T / 16 + 8 * J + 8) * 8)); B2_TRY(w->d_m256.ensure((T / 256 + 2 * J + 8) * 8));
+  B2_TRY(w->d_keysA.ensure(T)); B2_TRY(w->d_keysB.ensure(T));
+  B2_TRY(w->d_valsA.ensure(T)); B2_TRY(w->d_valsB.ensure(T));
+  B2_TRY(w->d_rank.ensure(T)); B2_TRY(w->d_grp.ensure(T));
+  B2_TRY(w->d_tiles.ensure(max_tiles)); B2_TRY(w->d_mtiles.ensure(max_mtiles));
+  B2_TRY(w->d_tilemask.ensure(max_mtiles * 8));
+  B2_TRY(w->d_sj.ensure(J));
+  B2_TRY(w->d_hist.ensure(max_tiles * 256)); B2_TRY(w->d_digit_base.ensure(J * 256));
+  B2_TRY(w->d_tile_head.ensure(max_tiles)); B2_TRY(w->d_carry.ensure(max_tiles));
+  B2_TRY(w->d_unsorted.ensure(J));
+  B2_TRY(w->d_mtf.ensure(T + 16 * J + 64));
+  B2_TRY(w->d_rank3.ensure(GT)); B2_TRY(w->d_rank4.ensure(GT));
+  B2_TRY(w->d_sel.ensure(GT * B2_N_TRIPLES + 64)); B2_TRY(w->d_selprev.ensure(GT * B2_N_TRIPLES + 64));
+  B2_TRY(w->d_selpos.ensure(GT));
+  B2_TRY(w->d_gcost.ensure(GT * B2_N_TRIPLES + 64));
+  B2_TRY(w->d_ehist.ensure(J * B2_N_TRIPLES * B2_MAX_CODERS * 260));
+  B2_TRY(w->d_leaves.ensure((J * B2_N_TRIPLES * B2_MAX_CODERS + 64) * 260));
+  B2_TRY(w->d_estat.ensure(J * B2_N_TRIPLES * 2)); B2_TRY(w->d_selcost.ensure(J * B2_N_TRIPLES));
+  B2_TRY(w->d_lens.ensure(J * B2_N_TRIPLES * B2_MAX_CODERS * B2_MAX_ALPHA));
+  B2_TRY(w->d_cost.ensure(J * B2_N_TRIPLES)); B2_TRY(w->d_low.ensure(J * B2_N_TRIPLES));
+  B2_TRY(w->d_items.ensure(J));
+  if (J > w->h_unsorted_cap) {
+    if (w->h_unsorted) cudaFreeHost(w->h_unsorted);
+    B2_CUDA_CHECK(cudaMallocHost((void **)&w->h_unsorted, (J + 64) * sizeof(u32)));
+    w->h_unsorted_cap = J + 64;
   }
   return 0;
 }
 
-struct BatchLayout { u32 T; u32 GT; u32 max_g; };
-
-// Assigns arena offsets to jobs[0..J) (host), returns totals.
-BatchLayout layout_jobs(std::vector<B2Job> &jobs, int level) {
+// Assigns arena offsets to jobs (host); returns the number of positions.
+u64 layout_jobs(std::vector<B2Job> &jobs, int level) {
   u64 pos = 0, mpos = 0;
   for (auto &j : jobs) {
     u64 cap = std::min<u64>((u64)j.raw_len * 5 / 4 + 8, (u64)level * 100000 + 64);
@@ -180,32 +220,32 @@ BatchLayout layout_jobs(std::vector<B2Job> &jobs, int level) {
     j.mtf_off = (u32)mpos;
     mpos += (cap + 2 + 7) & ~7ull;
   }
-  return BatchLayout{(u32)pos, 0, 0};
+  return pos;
 }
 
-// Runs one batch through RLE1 -> BWT -> MTF/RLE2 -> entropy search -> bit packing.
-// On return e->batch_jobs holds the device's view of the jobs (n, crc, origin, nbits, bits_off ...).
-int run_batch(b2_encoder *e, const u8 *d_in, std::vector<B2Job> &jobs) {
+// Runs one batch through RLE1 -> BWT -> MTF/RLE2 -> entropy search -> bit packing on workspace w.
+// On return w->batch_jobs holds the device's view of the jobs (n, crc, origin, nbits, bits_off ...).
+int run_batch(b2_encoder *e, Workspace *w, const u8 *d_in, std::vector<B2Job> &jobs) {
   const u32 J = (u32)jobs.size();
   if (J == 0) return 0;
-  BatchLayout L = layout_jobs(jobs, e->level);
-  B2_TRY(ensure_batch_workspace(e, (size_t)L.T + 64, J));
-  cudaStream_t st = e->st;
-  B2_CUDA_CHECK(cudaMemcpyAsync(e->d_jobs.p, jobs.data(), J * sizeof(B2Job), cudaMemcpyHostToDevice, st));
+  const u64 T = layout_jobs(jobs, e->level);
+  B2_TRY(ensure_batch_workspace(w, (size_t)T + 64, J));
+  cudaStream_t st = w->st;
+  B2_CUDA_CHECK(cudaMemcpyAsync(w->d_jobs.p, jobs.data(), J * sizeof(B2Job), cudaMemcpyHostToDevice, st));
   {
-    StageTimer tm(e, 1);
-    B2_TRY(b2k_rle1(st, d_in, e->d_jobs.p, J, e->d_text.p, e->d_ct.p));
-    e->launches_other += 1;
+    StageTimer tm(e, st, w->ev, &w->stage_ms[1]);
+    B2_TRY(b2k_rle1(st, d_in, w->d_jobs.p, J, w->d_text.p, e->d_ct.p));
+    w->launches += 1;
   }
-  e->batch_jobs.resize(J);
-  B2_CUDA_CHECK(cudaMemcpyAsync(e->batch_jobs.data(), e->d_jobs.p, J * sizeof(B2Job), cudaMemcpyDeviceToHost, st));
+  w->batch_jobs.resize(J);
+  B2_CUDA_CHECK(cudaMemcpyAsync(w->batch_jobs.data(), w->d_jobs.p, J * sizeof(B2Job), cudaMemcpyDeviceToHost, st));
   B2_CUDA_CHECK(cudaStreamSynchronize(st));
   // group arena offsets need n (M <= n + 1)
   u32 gpos = 0, max_g = 1;
   std::vector<u32> ids(J), ns(J);
   std::vector<B2SortTile> mtiles;
   for (u32 j = 0; j < J; j++) {
-    B2Job &b = e->batch_jobs[j];
+    B2Job &b = w->batch_jobs[j];
     if (b.n > b.cap) B2_FAIL(B2_ERR_INTERNAL, "RLE1 output exceeds its slot");
     u32 gmax = (b.n / B2_GROUP_SIZE + 2 + 15) & ~15u;     // multiple of 16: vector loads in k_ent_sweep / k_ent_selcost
     b.grp_off = gpos; gpos += gmax;
@@ -213,56 +253,135 @@ int run_batch(b2_encoder *e, const u8 *d_in, std::vector<B2Job> &jobs) {
     ids[j] = j; ns[j] = b.n;
     b.tile0 = (u32)mtiles.size();
     for (u32 s = 0; s < b.n; s += B2_MTF_TILE) mtiles.push_back(B2SortTile{j, s});
-    e->stats.block_bytes += b.n;
+    w->block_bytes += b.n;
   }
-  e->stats.blocks += J;
-  // write grp_off back (only field changed on the host)
-  B2_CUDA_CHECK(cudaMemcpyAsync(e->d_jobs.p, e->batch_jobs.data(), J * sizeof(B2Job), cudaMemcpyHostToDevice, st));
+  w->blocks += J;
+  w->total_groups = gpos;
+  // write grp_off / tile0 back (the only fields changed on the host)
+  B2_CUDA_CHECK(cudaMemcpyAsync(w->d_jobs.p, w->batch_jobs.data(), J * sizeof(B2Job), cudaMemcpyHostToDevice, st));
   {
-    StageTimer tm(e, 2);
+    StageTimer tm(e, st, w->ev, &w->stage_ms[2]);
     B2SortCtx cx;
-    cx.keysA = e->d_keysA.p; cx.keysB = e->d_keysB.p; cx.valsA = e->d_valsA.p; cx.valsB = e->d_valsB.p;
-    cx.rank = e->d_rank.p; cx.grp = e->d_grp.p; cx.d_tiles = e->d_tiles.p; cx.d_sj = e->d_sj.p;
-    cx.d_hist = e->d_hist.p; cx.d_digit_base = e->d_digit_base.p; cx.d_tile_head = e->d_tile_head.p; cx.d_carry = e->d_carry.p;
-    cx.d_unsorted = e->d_unsorted.p; cx.h_unsorted = e->h_unsorted;
-    cx.max_tiles = e->d_tiles.cap; cx.max_jobs = e->d_sj.cap; cx.timing = e->timing >= 1;
-    cx.stats = e->sort_stats;
-    int rc = b2k_bwt_batch(&cx, st, e->d_jobs.p, ids, ns, e->d_text.p, e->d_bwt.p);
-    e->sort_stats = cx.stats;
+    cx.keysA = w->d_keysA.p; cx.keysB = w->d_keysB.p; cx.valsA = w->d_valsA.p; cx.valsB = w->d_valsB.p;
+    cx.rank = w->d_rank.p; cx.grp = w->d_grp.p; cx.d_tiles = w->d_tiles.p; cx.d_sj = w->d_sj.p;
+    cx.d_hist = w->d_hist.p; cx.d_digit_base = w->d_digit_base.p; cx.d_tile_head = w->d_tile_head.p; cx.d_carry = w->d_carry.p;
+    cx.d_unsorted = w->d_unsorted.p; cx.h_unsorted = w->h_unsorted;
+    cx.max_tiles = w->d_tiles.cap; cx.max_jobs = w->d_sj.cap; cx.timing = e->timing >= 1;
+    cx.stats = w->sort_stats;
+    int rc = b2k_bwt_batch(&cx, st, w->d_jobs.p, ids, ns, w->d_text.p, w->d_bwt.p);
+    w->sort_stats = cx.stats;
     if (rc) return rc;
   }
   {
-    StageTimer tm(e, 3);
+    StageTimer tm(e, st, w->ev, &w->stage_ms[3]);
     if (!mtiles.empty())
-      B2_CUDA_CHECK(cudaMemcpyAsync(e->d_mtiles.p, mtiles.data(), mtiles.size() * sizeof(B2SortTile), cudaMemcpyHostToDevice, st));
-    B2_TRY(b2k_mtf(st, e->d_jobs.p, J, e->d_mtiles.p, (u32)mtiles.size(), e->d_bwt.p, e->d_m16.p, e->d_m256.p, e->d_tilemask.p, e->d_idx.p, e->d_mtf.p));
-    e->launches_other += 3;
-  }
-  const u32 total_groups = gpos;
-  {
-    StageTimer tm(e, 4);
-    B2_TRY(b2k_entropy(st, e->d_jobs.p, J, max_g, total_groups, e->d_mtf.p, e->d_rank3.p, e->d_rank4.p, e->d_sel.p,
-                       e->d_selprev.p, e->d_gcost.p, e->d_ehist.p, e->d_leaves.p, e->d_lens.p, e->d_estat.p, e->d_selcost.p,
-                       e->d_cost.p, e->d_low.p, e->level, &e->launches_other));
+      B2_CUDA_CHECK(cudaMemcpyAsync(w->d_mtiles.p, mtiles.data(), mtiles.size() * sizeof(B2SortTile), cudaMemcpyHostToDevice, st));
+    B2_TRY(b2k_mtf(st, w->d_jobs.p, J, w->d_mtiles.p, (u32)mtiles.size(), w->d_bwt.p, w->d_m16.p, w->d_m256.p, w->d_tilemask.p,
+                   w->d_idx.p, w->d_mtf.p));
+    w->launches += 3;
   }
   {
-    StageTimer tm(e, 5);
-    u64 *d_total = (u64 *)(e->d_scalars.p + 2);
-    B2_TRY(b2k_bits_layout(st, e->d_jobs.p, J, d_total));
+    StageTimer tm(e, st, w->ev, &w->stage_ms[4]);
+    B2_TRY(b2k_entropy(st, w->d_jobs.p, J, max_g, gpos, w->d_mtf.p, w->d_rank3.p, w->d_rank4.p, w->d_sel.p,
+                       w->d_selprev.p, w->d_gcost.p, w->d_ehist.p, w->d_leaves.p, w->d_lens.p, w->d_estat.p, w->d_selcost.p,
+                       w->d_cost.p, w->d_low.p, e->level, &w->launches));
+  }
+  {
+    StageTimer tm(e, st, w->ev, &w->stage_ms[5]);
+    u64 *d_total = (u64 *)(w->d_scalars.p + 2);
+    B2_TRY(b2k_bits_layout(st, w->d_jobs.p, J, d_total));
     u64 total_words = 0;
     B2_CUDA_CHECK(cudaMemcpyAsync(&total_words, d_total, sizeof(u64), cudaMemcpyDeviceToHost, st));
     B2_CUDA_CHECK(cudaStreamSynchronize(st));
-    B2_TRY(e->d_bits.ensure(total_words + 64));
-    B2_CUDA_CHECK(cudaMemsetAsync(e->d_bits.p, 0, (total_words + 8) * sizeof(u32), st));
-    B2_TRY(b2k_pack(st, e->d_jobs.p, J, e->d_mtf.p, e->d_sel.p, e->d_lens.p, e->d_selpos.p, e->d_bits.p, e->level, total_groups));
-    e->launches_other += 2;
+    B2_TRY(w->d_bits.ensure(total_words + 64));
+    B2_CUDA_CHECK(cudaMemsetAsync(w->d_bits.p, 0, (total_words + 8) * sizeof(u32), st));
+    B2_TRY(b2k_pack(st, w->d_jobs.p, J, w->d_mtf.p, w->d_sel.p, w->d_lens.p, w->d_selpos.p, w->d_bits.p, e->level, gpos));
+    w->launches += 2;
   }
-  B2_CUDA_CHECK(cudaMemcpyAsync(e->batch_jobs.data(), e->d_jobs.p, J * sizeof(B2Job), cudaMemcpyDeviceToHost, st));
+  B2_CUDA_CHECK(cudaMemcpyAsync(w->batch_jobs.data(), w->d_jobs.p, J * sizeof(B2Job), cudaMemcpyDeviceToHost, st));
   B2_CUDA_CHECK(cudaStreamSynchronize(st));
   return 0;
 }
 
 inline u32 rotl1(u32 x) { return (x << 1) | (x >> 31); }
+
+// Slices of one chunk per tactic -> de-duplicated jobs; ids start at first_id.
+int plan_chunk(b2_encoder *e, u32 c, ChunkPlan &P, std::vector<B2Job> &add, size_t first_id, u64 &addpos) {
+  const int level = e->level;
+  std::vector<std::pair<u32, u32>> slices[4];       // (start, len) relative to the chunk
+  int nt = 1;
+  slices[0].push_back({0, P.len});                                   // single (:1236, slices = 1)
+  if (level == 9) {
+    nt = 4;
+    u32 size = P.len / 4, stop = 0;                                  // parts_4 (:1238-1254)
+    for (u32 count = 1; count <= 4; count++) {
+      u32 start = stop;
+      stop = (count == 4) ? P.len : count * size;
+      slices[1].push_back({start, stop - start});
+    }
+    for (int k = 0; k < 2; k++) {                                    // segmented_1/2 (:1266-1291)
+      u32 ns = e->nseg[2 * c + k];
+      if (ns > B2_MAX_SEG) B2_FAIL(B2_ERR_INTERNAL, "segment table overflow");
+      P.n_seg[k] = ns;
+      const u32 *cuts = &e->seg[(size_t)(2 * c + k) * B2_MAX_SEG];
+      if (ns == 0) slices[2 + k].push_back({0, 0});                  // seg.Is_Empty -> one empty block (:1283-1284)
+      u32 index_start = 0;
+      for (u32 s = 0; s < ns; s++) { slices[2 + k].push_back({index_start, cuts[s] - index_start}); index_start = cuts[s]; }
+    }
+  }
+  std::map<std::pair<u32, u32>, u32> seen;
+  add.clear(); addpos = 0;
+  for (int t = 0; t < nt; t++) {
+    P.tactic_jobs[t].clear();
+    for (auto &sl : slices[t]) {
+      auto it = seen.find(sl);
+      u32 id;
+      if (it == seen.end()) {
+        id = (u32)(first_id + add.size());
+        seen[sl] = id;
+        B2Job j; memset(&j, 0, sizeof j);
+        j.raw_off = P.start + sl.first; j.raw_len = sl.second;
+        add.push_back(j);
+        addpos += std::min<u64>((u64)sl.second * 5 / 4 + 264, (u64)level * 100000 + 320);
+      } else id = it->second;
+      P.tactic_jobs[t].push_back(id);
+    }
+  }
+  P.n_tactics = nt;
+  return 0;
+}
+
+struct Resolver {                 // serial state carried from chunk to chunk (:1305-1345)
+  u64 cur_bit = 32;               // after "BZh<level>"
+  u32 combined_crc = 0;
+};
+
+// Winners of the chunks of one finished batch, in order; appends concat items.
+void resolve_batch(b2_encoder *e, Workspace *w, const Batch &B, std::vector<ChunkPlan> &plans, Resolver &R,
+                   std::vector<B2ConcatItem> &items) {
+  for (u32 c = B.c0; c < B.c1; c++) {
+    ChunkPlan &P = plans[c];
+    b2_chunk_trace tr; memset(&tr, 0, sizeof tr);
+    tr.start = P.start; tr.len = P.len; tr.dyn_capacity = P.cap; tr.n_seg1 = P.n_seg[0]; tr.n_seg2 = P.n_seg[1];
+    int best = 0;
+    const u32 in_bits = (u32)(R.cur_bit & 7);
+    for (int t = 0; t < P.n_tactics; t++) {
+      u64 bits = 0;
+      for (u32 id : P.tactic_jobs[t]) bits += w->batch_jobs[id].nbits;
+      tr.bits[t] = bits;
+      tr.bytes[t] = (in_bits + bits) >> 3;      // destination_index: whole bytes flushed
+    }
+    for (int t = 0; t < P.n_tactics; t++) if (tr.bytes[t] < tr.bytes[best]) best = t;
+    tr.winner = best;
+    for (u32 id : P.tactic_jobs[best]) {
+      const B2Job &b = w->batch_jobs[id];
+      items.push_back(B2ConcatItem{b.bits_off, b.nbits, R.cur_bit});
+      R.cur_bit += b.nbits;
+      R.combined_crc = rotl1(R.combined_crc) ^ b.crc;     // (:990)
+    }
+    e->trace[c] = tr;
+  }
+}
 
 // The whole stream, input resident on the device.  Output words land in e->d_out.
 int encode_device(b2_encoder *e, const u8 *d_in, u64 n, i64 size_hint, u64 *out_len) {
@@ -276,14 +395,14 @@ int encode_device(b2_encoder *e, const u8 *d_in, u64 n, i64 size_hint, u64 *out_
   const u32 max_chunks = (u32)(n / (40000ull * level) + 16);
   u32 n_chunks = 0;
   {
-    StageTimer tm(e, 0);
+    StageTimer tm(e, st, e->ev, &e->stats.stage_ms[0]);
     B2_TRY(e->d_chunks.ensure(max_chunks));
     const size_t ct = (size_t)(n / 2048 + 2);
     B2_TRY(e->d_cut_first.ensure(ct)); B2_TRY(e->d_cut_last.ensure(ct)); B2_TRY(e->d_cut_tsum.ensure(ct));
     B2_TRY(e->d_cut_carry.ensure(ct)); B2_TRY(e->d_cut_tincl.ensure(ct));
     B2CutWork cw{e->d_cut_first.p, e->d_cut_last.p, e->d_cut_tsum.p, e->d_cut_carry.p, e->d_cut_tincl.p};
     B2_TRY(b2k_cut(st, d_in, n, size_hint, level, win_lo, win_hi, e->d_chunks.p, e->d_scalars.p, max_chunks, &cw));
-    e->launches_other += 4;
+    e->launches_other += 5;
     B2_CUDA_CHECK(cudaMemcpyAsync(&n_chunks, e->d_scalars.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
     B2_CUDA_CHECK(cudaStreamSynchronize(st));
     if (n_chunks > max_chunks) B2_FAIL(B2_ERR_INTERNAL, "chunk table overflow");
@@ -300,116 +419,97 @@ int encode_device(b2_encoder *e, const u8 *d_in, u64 n, i64 size_hint, u64 *out_
       e->launches_other += 1;
     }
     B2_CUDA_CHECK(cudaStreamSynchronize(st));
-    e->launches_other += 1;
   }
   e->stats.chunks += n_chunks;
+  e->trace.resize(n_chunks);
   // ---- output buffer -------------------------------------------------------------------------
   const u64 out_bound = b2_bound(n) + 1024ull * n_chunks;
   B2_TRY(e->d_out.ensure(out_bound / 4 + 16));
   B2_CUDA_CHECK(cudaMemsetAsync(e->d_out.p, 0, (out_bound / 4 + 8) * sizeof(u32), st));
-  // ---- plan: tactics -> de-duplicated jobs ------------------------------------
+  // ---- plan: batches of whole chunks ---------------------------------------------------------
   std::vector<ChunkPlan> plans(n_chunks);
-  for (u32 c = 0; c < n_chunks; c++) {
-    ChunkPlan &P = plans[c];
-    P.start = e->chunks[c].start; P.len = e->chunks[c].len; P.cap = e->chunks[c].cap;
-    P.n_seg[0] = P.n_seg[1] = 0;
-  }
-  // ---- batches of whole chunks ---------------------------------------------------------------
-  u64 cur_bit = 32;               // after "BZh<level>"
-  u32 combined_crc = 0;
-  u32 c0 = 0;
-  while (c0 < n_chunks) {
-    std::vector<B2Job> jobs;
+  std::vector<Batch> batches;
+  {
+    Batch cur; cur.c0 = 0;
     u64 positions = 0;
-    u32 c1 = c0;
-    while (c1 < n_chunks) {
-      ChunkPlan &P = plans[c1];
-      // slices of this chunk per tactic: (start, len) relative to the chunk
-      std::vector<std::pair<u32, u32>> slices[4];
-      int nt = 1;
-      slices[0].push_back({0, P.len});                                   // single (:1236, slices = 1)
-      if (level == 9) {
-        nt = 4;
-        u32 size = P.len / 4, stop = 0;                                  // parts_4 (:1238-1254)
-        for (u32 count = 1; count <= 4; count++) {
-          u32 start = stop;
-          stop = (count == 4) ? P.len : count * size;
-          slices[1].push_back({start, stop - start});
-        }
-        for (int k = 0; k < 2; k++) {                                    // segmented_1/2 (:1266-1291)
-          u32 ns = e->nseg[2 * c1 + k];
-          if (ns > B2_MAX_SEG) B2_FAIL(B2_ERR_INTERNAL, "segment table overflow");
-          P.n_seg[k] = ns;
-          const u32 *cuts = &e->seg[(size_t)(2 * c1 + k) * B2_MAX_SEG];
-          if (ns == 0) slices[2 + k].push_back({0, 0});                  // seg.Is_Empty -> one empty block (:1283-1284)
-          u32 index_start = 0;
-          for (u32 s = 0; s < ns; s++) { slices[2 + k].push_back({index_start, cuts[s] - index_start}); index_start = cuts[s]; }
-        }
-      }
-      // would this chunk overflow the batch?
-      std::map<std::pair<u32, u32>, u32> seen;
-      std::vector<B2Job> add;
-      u64 addpos = 0;
-      for (int t = 0; t < nt; t++) {
-        P.tactic_jobs[t].clear();
-        for (auto &sl : slices[t]) {
-          auto it = seen.find(sl);
-          u32 id;
-          if (it == seen.end()) {
-            id = (u32)(jobs.size() + add.size());
-            seen[sl] = id;
-            B2Job j; memset(&j, 0, sizeof j);
-            j.raw_off = P.start + sl.first; j.raw_len = sl.second;
-            add.push_back(j);
-            addpos += std::min<u64>((u64)sl.second * 5 / 4 + 264, (u64)level * 100000 + 320);
-          } else id = it->second;
-          P.tactic_jobs[t].push_back(id);
-        }
-      }
-      P.n_tactics = nt;
-      if (!jobs.empty() && (positions + addpos > e->batch_positions || jobs.size() + add.size() > e->batch_jobs_max)) break;
-      jobs.insert(jobs.end(), add.begin(), add.end());
-      positions += addpos;
-      c1++;
-    }
-    B2_TRY(run_batch(e, d_in, jobs));
-    // ---- serial resolve of winners over the chunks of this batch (:1305-1345) -----------------
-    std::vector<B2ConcatItem> items;
-    for (u32 c = c0; c < c1; c++) {
+    std::vector<B2Job> add;
+    for (u32 c = 0; c < n_chunks; c++) {
       ChunkPlan &P = plans[c];
-      b2_chunk_trace tr; memset(&tr, 0, sizeof tr);
-      tr.start = P.start; tr.len = P.len; tr.dyn_capacity = P.cap; tr.n_seg1 = P.n_seg[0]; tr.n_seg2 = P.n_seg[1];
-      int best = 0;
-      const u32 in_bits = (u32)(cur_bit & 7);
-      for (int t = 0; t < P.n_tactics; t++) {
-        u64 bits = 0;
-        for (u32 id : P.tactic_jobs[t]) bits += e->batch_jobs[id].nbits;
-        tr.bits[t] = bits;
-        tr.bytes[t] = (in_bits + bits) >> 3;      // destination_index: whole bytes flushed
+      P.start = e->chunks[c].start; P.len = e->chunks[c].len; P.cap = e->chunks[c].cap;
+      P.n_seg[0] = P.n_seg[1] = 0;
+      u64 addpos = 0;
+      B2_TRY(plan_chunk(e, c, P, add, cur.jobs.size(), addpos));
+      if (!cur.jobs.empty() && (positions + addpos > e->batch_positions || cur.jobs.size() + add.size() > e->batch_jobs_max)) {
+        cur.c1 = c;
+        batches.push_back(std::move(cur));
+        cur = Batch(); cur.c0 = c; positions = 0;
+        B2_TRY(plan_chunk(e, c, P, add, 0, addpos));      // job ids restart in the new batch
       }
-      for (int t = 0; t < P.n_tactics; t++) if (tr.bytes[t] < tr.bytes[best]) best = t;
-      tr.winner = best;
-      for (u32 id : P.tactic_jobs[best]) {
-        const B2Job &b = e->batch_jobs[id];
-        items.push_back(B2ConcatItem{b.bits_off, b.nbits, cur_bit});
-        cur_bit += b.nbits;
-        combined_crc = rotl1(combined_crc) ^ b.crc;     // (:990)
-      }
-      e->trace.push_back(tr);
+      cur.jobs.insert(cur.jobs.end(), add.begin(), add.end());
+      positions += addpos;
     }
-    if ((cur_bit + 128) / 8 > out_bound) B2_FAIL(B2_ERR_INTERNAL, "output bound exceeded");
-    {
-      StageTimer tm(e, 6);
-      B2_TRY(e->d_items.ensure(items.size()));
-      B2_CUDA_CHECK(cudaMemcpyAsync(e->d_items.p, items.data(), items.size() * sizeof(B2ConcatItem), cudaMemcpyHostToDevice, st));
-      B2_TRY(b2k_concat(st, e->d_items.p, (u32)items.size(), e->d_bits.p, e->d_out.p));
-      B2_CUDA_CHECK(cudaStreamSynchronize(st));
-      e->launches_other += 1;
-    }
-    c0 = c1;
+    cur.c1 = n_chunks;
+    if (n_chunks) batches.push_back(std::move(cur));
   }
+  B2_CUDA_CHECK(cudaStreamSynchronize(st));           // output zeroed before any concat
+  // ---- pipelined batches ---------------------------------------------------------------------
+  Resolver R;
+  const int W = (e->timing >= 2) ? 1 : std::max(1, std::min<int>((int)e->ws.size(), (int)batches.size()));
+  for (auto *w : e->ws) {
+    memset(&w->sort_stats, 0, sizeof w->sort_stats);
+    w->launches = 0; w->blocks = 0; w->block_bytes = 0;
+    for (int i = 0; i < 8; i++) w->stage_ms[i] = 0;
+  }
+  std::atomic<u32> next{0};
+  std::mutex mu;
+  std::condition_variable cv;
+  u32 turn = 0;                 // next batch to resolve (guarded by mu)
+  int err = 0;
+  std::string err_msg;
+  auto worker = [&](int wi) {
+    cudaSetDevice(e->device);
+    Workspace *w = e->ws[wi];
+    for (;;) {
+      const u32 b = next.fetch_add(1);
+      if (b >= batches.size()) break;
+      int rc = 0;
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        if (err) rc = err;
+      }
+      if (!rc) rc = run_batch(e, w, d_in, batches[b].jobs);
+      std::unique_lock<std::mutex> lk(mu);
+      cv.wait(lk, [&] { return turn == b; });
+      if (!rc && !err) {
+        std::vector<B2ConcatItem> items;
+        resolve_batch(e, w, batches[b], plans, R, items);
+        if ((R.cur_bit + 128) / 8 > out_bound) { rc = B2_ERR_INTERNAL; b2_set_error(__FILE__, __LINE__, "output bound exceeded"); }
+        if (!rc) {
+          StageTimer tm(e, w->st, w->ev, &w->stage_ms[6]);
+          rc = w->d_items.ensure(items.size());
+          if (!rc && cudaMemcpyAsync(w->d_items.p, items.data(), items.size() * sizeof(B2ConcatItem), cudaMemcpyHostToDevice, w->st) != cudaSuccess) rc = B2_ERR_CUDA;
+          if (!rc) rc = b2k_concat(w->st, w->d_items.p, (u32)items.size(), w->d_bits.p, e->d_out.p);
+          if (!rc && cudaStreamSynchronize(w->st) != cudaSuccess) { rc = B2_ERR_CUDA; b2_set_error(__FILE__, __LINE__, cudaGetErrorString(cudaGetLastError())); }
+          w->launches += 1;
+        }
+      }
+      if (rc && !err) { err = rc; err_msg = g_last_error; }
+      turn = b + 1;
+      lk.unlock();
+      cv.notify_all();
+    }
+  };
+  if (W == 1) worker(0);
+  else {
+    std::vector<std::thread> th;
+    for (int i = 0; i < W; i++) th.emplace_back(worker, i);
+    for (auto &t : th) t.join();
+  }
+  if (err) { g_last_error = err_msg; return err; }
   // ---- header and footer (:1384-1407): 4 + 10 bytes, written through a tiny host staging ------
   {
+    const u64 cur_bit = R.cur_bit;
+    const u32 combined_crc = R.combined_crc;
     u8 head[4] = {'B', 'Z', 'h', (u8)('0' + level)};
     // footer bits: 48-bit magic 0x177245385090 + 32-bit combined CRC at bit offset cur_bit
     u8 foot[16]; memset(foot, 0, sizeof foot);
@@ -433,6 +533,19 @@ int encode_device(b2_encoder *e, const u8 *d_in, u64 n, i64 size_hint, u64 *out_
     B2_CUDA_CHECK(cudaMemcpyAsync(d_out8, head, 4, cudaMemcpyHostToDevice, st));
     B2_CUDA_CHECK(cudaStreamSynchronize(st));
     *out_len = total_bytes;
+  }
+  // ---- merge per-workspace statistics -------------------------------------------------------
+  for (auto *w : e->ws) {
+    e->sort_stats.scatter_launches += w->sort_stats.scatter_launches;
+    e->sort_stats.scatter_elems += w->sort_stats.scatter_elems;
+    e->sort_stats.scatter_ms += w->sort_stats.scatter_ms;
+    e->sort_stats.rounds += w->sort_stats.rounds;
+    e->sort_stats.sorted_elems_round0 += w->sort_stats.sorted_elems_round0;
+    e->sort_stats.sorted_elems_later += w->sort_stats.sorted_elems_later;
+    e->sort_stats.launches += w->sort_stats.launches;
+    e->launches_other += w->launches;
+    e->stats.blocks += w->blocks; e->stats.block_bytes += w->block_bytes;
+    for (int i = 1; i < 8; i++) e->stats.stage_ms[i] += w->stage_ms[i];
   }
   e->stats.sort_rounds = e->sort_stats.rounds;
   e->stats.sort_elems_round0 = e->sort_stats.sorted_elems_round0;
@@ -468,9 +581,16 @@ int b2_create(int level, int device, b2_encoder **out) {
   memset(&e->sort_stats, 0, sizeof e->sort_stats);
   if (const char *s = getenv("B2GPU_BATCH_POSITIONS")) { long long v = atoll(s); if (v >= (1 << 20)) e->batch_positions = (size_t)v; }
   if (const char *s = getenv("B2GPU_BATCH_JOBS")) { long long v = atoll(s); if (v >= 8) e->batch_jobs_max = (size_t)v; }
+  if (const char *s = getenv("B2GPU_PIPELINE")) { int v = atoi(s); if (v >= 1 && v <= 8) e->n_workspaces = v; }
   B2_CUDA_CHECK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
   B2_CUDA_CHECK(cudaEventCreate(&e->ev[0])); B2_CUDA_CHECK(cudaEventCreate(&e->ev[1]));
   B2_CUDA_CHECK(cudaEventCreate(&e->ev_call[0])); B2_CUDA_CHECK(cudaEventCreate(&e->ev_call[1]));
+  for (int i = 0; i < e->n_workspaces; i++) {
+    Workspace *w = new Workspace();
+    e->ws.push_back(w);
+    B2_CUDA_CHECK(cudaStreamCreateWithFlags(&w->st, cudaStreamNonBlocking));
+    B2_CUDA_CHECK(cudaEventCreate(&w->ev[0])); B2_CUDA_CHECK(cudaEventCreate(&w->ev[1]));
+  }
   // constant tables
   B2CrcTables *ct = new B2CrcTables();
   b2k_make_crc_tables(ct);
@@ -494,17 +614,11 @@ void b2_destroy(b2_encoder *e) {
   if (!e) return;
   cudaSetDevice(e->device);
   if (e->st) cudaStreamSynchronize(e->st);
+  for (auto *w : e->ws) { if (w->st) cudaStreamSynchronize(w->st); w->release(); delete w; }
+  e->ws.clear();
   e->d_ct.release(); e->d_T.release(); e->d_in.release(); e->d_out.release(); e->d_chunks.release();
   e->d_scalars.release(); e->d_seg.release(); e->d_nseg.release(); e->d_cut_first.release(); e->d_cut_last.release();
-  e->d_cut_tsum.release(); e->d_cut_carry.release(); e->d_cut_tincl.release(); e->d_jobs.release(); e->d_text.release();
-  e->d_bwt.release(); e->d_idx.release(); e->d_m16.release(); e->d_m256.release(); e->d_tilemask.release(); e->d_keysA.release(); e->d_keysB.release(); e->d_valsA.release();
-  e->d_valsB.release(); e->d_rank.release(); e->d_grp.release(); e->d_tiles.release(); e->d_mtiles.release();
-  e->d_sj.release(); e->d_hist.release(); e->d_digit_base.release(); e->d_tile_head.release(); e->d_carry.release(); e->d_unsorted.release();
-  e->d_mtf.release(); e->d_rank3.release(); e->d_rank4.release(); e->d_sel.release(); e->d_selpos.release();
-  e->d_lens.release(); e->d_gcost.release(); e->d_selprev.release(); e->d_ehist.release(); e->d_leaves.release();
-  e->d_estat.release(); e->d_selcost.release(); e->d_cost.release(); e->d_low.release(); e->d_bits.release();
-  e->d_items.release();
-  if (e->h_unsorted) cudaFreeHost(e->h_unsorted);
+  e->d_cut_tsum.release(); e->d_cut_carry.release(); e->d_cut_tincl.release();
   if (e->ev[0]) cudaEventDestroy(e->ev[0]);
   if (e->ev[1]) cudaEventDestroy(e->ev[1]);
   if (e->ev_call[0]) cudaEventDestroy(e->ev_call[0]);
@@ -536,7 +650,7 @@ int b2_encode_stream(b2_encoder *e, const uint8_t *in, uint64_t n, int64_t size_
   B2_TRY(e->d_in.ensure(n + 256));
   if (e->timing) cudaEventRecord(e->ev_call[0], e->st);
   {
-    StageTimer tm(e, 7);
+    StageTimer tm(e, e->st, e->ev, &e->stats.stage_ms[7]);
     if (n) B2_CUDA_CHECK(cudaMemcpyAsync(e->d_in.p, in, n, cudaMemcpyHostToDevice, e->st));
     B2_CUDA_CHECK(cudaMemsetAsync(e->d_in.p + n, 0, 128, e->st));
   }
@@ -545,7 +659,7 @@ int b2_encode_stream(b2_encoder *e, const uint8_t *in, uint64_t n, int64_t size_
   *out_len = len;
   if (len > out_cap) B2_FAIL(B2_ERR_OUTPUT_TOO_SMALL, "output buffer too small");
   {
-    StageTimer tm(e, 7);
+    StageTimer tm(e, e->st, e->ev, &e->stats.stage_ms[7]);
     if (out) B2_CUDA_CHECK(cudaMemcpyAsync(out, e->d_out.p, len, cudaMemcpyDeviceToHost, e->st));
     if (e->timing) cudaEventRecord(e->ev_call[1], e->st);
     B2_CUDA_CHECK(cudaStreamSynchronize(e->st));
@@ -584,25 +698,26 @@ int b2_dbg_block(b2_encoder *e, const uint8_t *raw, uint32_t len, uint8_t *rle_o
                  b2_block_info *info) {
   if (!e || (len && !raw)) B2_FAIL(B2_ERR_ARGUMENT, "bad argument");
   B2_CUDA_CHECK(cudaSetDevice(e->device));
+  Workspace *w = e->ws[0];
+  cudaStream_t st = w->st;
   B2_TRY(e->d_in.ensure((size_t)len + 256));
-  if (len) B2_CUDA_CHECK(cudaMemcpyAsync(e->d_in.p, raw, len, cudaMemcpyHostToDevice, e->st));
-  B2_CUDA_CHECK(cudaMemsetAsync(e->d_in.p + len, 0, 128, e->st));
+  if (len) B2_CUDA_CHECK(cudaMemcpyAsync(e->d_in.p, raw, len, cudaMemcpyHostToDevice, st));
+  B2_CUDA_CHECK(cudaMemsetAsync(e->d_in.p + len, 0, 128, st));
   std::vector<B2Job> jobs(1);
   memset(&jobs[0], 0, sizeof(B2Job));
   jobs[0].raw_off = 0; jobs[0].raw_len = len;
-  B2_TRY(run_batch(e, e->d_in.p, jobs));
-  const B2Job &b = e->batch_jobs[0];
-  cudaStream_t st = e->st;
-  if (rle_out && b.n) B2_CUDA_CHECK(cudaMemcpyAsync(rle_out, e->d_text.p + b.pos_off, b.n, cudaMemcpyDeviceToHost, st));
-  if (bwt_out && b.n) B2_CUDA_CHECK(cudaMemcpyAsync(bwt_out, e->d_bwt.p + b.pos_off, b.n, cudaMemcpyDeviceToHost, st));
-  if (mtf_out) B2_CUDA_CHECK(cudaMemcpyAsync(mtf_out, e->d_mtf.p + b.mtf_off, (size_t)b.n_mtf * 2, cudaMemcpyDeviceToHost, st));
-  const u32 total_groups = (b.n / B2_GROUP_SIZE + 2 + 15) & ~15u;   // single job: grp arena size == its own bound
-  if (sel_out) B2_CUDA_CHECK(cudaMemcpyAsync(sel_out, e->d_sel.p + (size_t)b.best * total_groups + b.grp_off, b.n_groups, cudaMemcpyDeviceToHost, st));
-  if (lens_out) B2_CUDA_CHECK(cudaMemcpyAsync(lens_out, e->d_lens.p + (size_t)b.best * (B2_MAX_CODERS * B2_MAX_ALPHA), B2_MAX_CODERS * B2_MAX_ALPHA, cudaMemcpyDeviceToHost, st));
+  B2_TRY(run_batch(e, w, e->d_in.p, jobs));
+  const B2Job &b = w->batch_jobs[0];
+  if (rle_out && b.n) B2_CUDA_CHECK(cudaMemcpyAsync(rle_out, w->d_text.p + b.pos_off, b.n, cudaMemcpyDeviceToHost, st));
+  if (bwt_out && b.n) B2_CUDA_CHECK(cudaMemcpyAsync(bwt_out, w->d_bwt.p + b.pos_off, b.n, cudaMemcpyDeviceToHost, st));
+  if (mtf_out) B2_CUDA_CHECK(cudaMemcpyAsync(mtf_out, w->d_mtf.p + b.mtf_off, (size_t)b.n_mtf * 2, cudaMemcpyDeviceToHost, st));
+  const u32 total_groups = w->total_groups;
+  if (sel_out) B2_CUDA_CHECK(cudaMemcpyAsync(sel_out, w->d_sel.p + (size_t)b.best * total_groups + b.grp_off, b.n_groups, cudaMemcpyDeviceToHost, st));
+  if (lens_out) B2_CUDA_CHECK(cudaMemcpyAsync(lens_out, w->d_lens.p + (size_t)b.best * (B2_MAX_CODERS * B2_MAX_ALPHA), B2_MAX_CODERS * B2_MAX_ALPHA, cudaMemcpyDeviceToHost, st));
   u64 nbytes = (b.nbits + 7) >> 3;
   if (bits_out) {
     if (nbytes > bits_cap) B2_FAIL(B2_ERR_OUTPUT_TOO_SMALL, "bits_out too small");
-    B2_CUDA_CHECK(cudaMemcpyAsync(bits_out, (u8 *)(e->d_bits.p + b.bits_off), nbytes, cudaMemcpyDeviceToHost, st));
+    B2_CUDA_CHECK(cudaMemcpyAsync(bits_out, (u8 *)(w->d_bits.p + b.bits_off), nbytes, cudaMemcpyDeviceToHost, st));
   }
   B2_CUDA_CHECK(cudaStreamSynchronize(st));
   if (info) {

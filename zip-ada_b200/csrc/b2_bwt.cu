@@ -330,11 +330,8 @@ struct EvPair { cudaEvent_t a, b; };
 
 int b2k_bwt_batch(B2SortCtx *cx, cudaStream_t st, B2Job *d_jobs, const std::vector<u32> &job_ids,
                   const std::vector<u32> &job_n, const u8 *d_text, u8 *d_bwt) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    B2_CUDA_CHECK(cudaFuncSetAttribute(k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
-    attr_set = true;
-  }
+  // per device and cheap; set on every call so that handles on several devices / threads all have it
+  B2_CUDA_CHECK(cudaFuncSetAttribute(k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
   std::vector<B2SortTile> tiles;
   std::vector<B2SortJob> sj;
   std::vector<u32> ids = job_ids, ns = job_n;

@@ -596,11 +596,7 @@ int b2k_entropy(cudaStream_t st, B2Job *d_jobs, u32 n_jobs, u32 max_groups_per_j
                 const u16 *d_mtf, u32 *d_rank3, u32 *d_rank4, u8 *d_sel, u8 *d_selprev, unsigned long long *d_gcost,
                 u32 *d_hist, u32 *d_leaves, u8 *d_lens, u32 *d_stat, u32 *d_selcost, u32 *d_cost, u32 *d_low,
                 int level, u64 *launches) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    B2_CUDA_CHECK(cudaFuncSetAttribute(k_rank_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, 18064 * 4));
-    attr_set = true;
-  }
+  B2_CUDA_CHECK(cudaFuncSetAttribute(k_rank_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, 18064 * 4));
   if (n_jobs == 0) return 0;
   const int n_triples = level == 9 ? 20 : 5;
   k_group_keys<<<n_jobs, 256, 0, st>>>(d_jobs, d_mtf, d_rank3, d_rank4);
