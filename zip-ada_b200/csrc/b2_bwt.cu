@@ -19,8 +19,8 @@
 #include "b2_common.cuh"
 #include "b2_kernels.h"
 
-#define ST_THREADS 256
-#define ST_ITEMS 16
+#define ST_THREADS 512
+#define ST_ITEMS 8
 #define ST_TILE (ST_THREADS * ST_ITEMS)
 #define ST_WARPS (ST_THREADS / 32)
 #define ST_WCHUNK (32 * ST_ITEMS)      // elements per warp
@@ -61,7 +61,7 @@ k_hist(const B2SortTile *__restrict__ tiles, const B2Job *__restrict__ jobs, con
   const B2Job &job = jobs[tl.job];
   const u32 n = job.n;
   const u64 *kp = keys + job.pos_off;
-  h[threadIdx.x] = 0;
+  if (threadIdx.x < 256) h[threadIdx.x] = 0;
   __syncthreads();
 #pragma unroll 4
   for (int k = 0; k < ST_ITEMS; k++) {
@@ -69,7 +69,7 @@ k_hist(const B2SortTile *__restrict__ tiles, const B2Job *__restrict__ jobs, con
     if (i < n) atomicAdd(&h[(u32)(kp[i] >> shift) & 255u], 1u);
   }
   __syncthreads();
-  hist[(size_t)blockIdx.x * 256 + threadIdx.x] = h[threadIdx.x];
+  if (threadIdx.x < 256) hist[(size_t)blockIdx.x * 256 + threadIdx.x] = h[threadIdx.x];
 }
 
 // ---- per-block exclusive scan over (digit major, tile minor) ------------------------------------
@@ -118,7 +118,7 @@ k_scatter(const B2SortTile *__restrict__ tiles, const B2Job *__restrict__ jobs,
   const u32 tid = threadIdx.x, w = warp_id(), l = lane_id();
   const u32 lt_mask = (1u << l) - 1u;
   for (int i = tid; i < ST_WARPS * 256; i += ST_THREADS) (&S.warp_cnt[0][0])[i] = 0;
-  S.g_off[tid] = hist[(size_t)blockIdx.x * 256 + tid] + digit_base[(size_t)tl.job * 256 + tid];
+  if (tid < 256) S.g_off[tid] = hist[(size_t)blockIdx.x * 256 + tid] + digit_base[(size_t)tl.job * 256 + tid];
   __syncthreads();
   u64 key[ST_ITEMS];
   u32 val[ST_ITEMS];
@@ -148,10 +148,12 @@ k_scatter(const B2SortTile *__restrict__ tiles, const B2Job *__restrict__ jobs,
   // per digit: exclusive over warps, tile count
   {
     u32 run = 0;
+    if (tid < 256) {
 #pragma unroll
-    for (int ww = 0; ww < ST_WARPS; ww++) { u32 c = S.warp_cnt[ww][tid]; S.warp_cnt[ww][tid] = run; run += c; }
+      for (int ww = 0; ww < ST_WARPS; ww++) { u32 c = S.warp_cnt[ww][tid]; S.warp_cnt[ww][tid] = run; run += c; }
+    }
     u32 ts = block_excl_add(run, S.scan, nullptr);
-    S.tile_start[tid] = ts;
+    if (tid < 256) S.tile_start[tid] = ts;
   }
   __syncthreads();
 #pragma unroll
