@@ -72,7 +72,7 @@ struct Workspace {
   DevBuf<u8> d_text, d_bwt, d_idx;
   DevBuf<u32> d_m16, d_m256, d_tilemask;
   DevBuf<u64> d_keysA, d_keysB;
-  DevBuf<u32> d_valsA, d_valsB, d_rank, d_grp;
+  DevBuf<u32> d_valsA, d_valsB, d_rank, d_grp, d_slotA, d_slotB, d_sa, d_tile_cnt;
   DevBuf<B2SortTile> d_tiles, d_mtiles;
   DevBuf<B2SortJob> d_sj;
   DevBuf<u32> d_hist, d_digit_base;
@@ -97,7 +97,7 @@ struct Workspace {
   void release() {
     d_scalars.release(); d_jobs.release(); d_text.release(); d_bwt.release(); d_idx.release(); d_m16.release();
     d_m256.release(); d_tilemask.release(); d_keysA.release(); d_keysB.release(); d_valsA.release(); d_valsB.release();
-    d_rank.release(); d_grp.release(); d_tiles.release(); d_mtiles.release(); d_sj.release(); d_hist.release();
+    d_rank.release(); d_grp.release(); d_slotA.release(); d_slotB.release(); d_sa.release(); d_tile_cnt.release(); d_tiles.release(); d_mtiles.release(); d_sj.release(); d_hist.release();
     d_digit_base.release(); d_tile_head.release(); d_carry.release(); d_unsorted.release(); d_mtf.release();
     d_rank3.release(); d_rank4.release(); d_sel.release(); d_selprev.release(); d_selpos.release(); d_lens.release();
     d_ehist.release(); d_leaves.release(); d_estat.release(); d_selcost.release(); d_gcost.release(); d_cost.release();
@@ -184,6 +184,7 @@ int ensure_batch_workspace(Workspace *w, size_t T, size_t J) {
   B2_TRY(w->d_keysA.ensure(T)); B2_TRY(w->d_keysB.ensure(T));
   B2_TRY(w->d_valsA.ensure(T)); B2_TRY(w->d_valsB.ensure(T));
   B2_TRY(w->d_rank.ensure(T)); B2_TRY(w->d_grp.ensure(T));
+  B2_TRY(w->d_slotA.ensure(T)); B2_TRY(w->d_slotB.ensure(T)); B2_TRY(w->d_sa.ensure(T)); B2_TRY(w->d_tile_cnt.ensure(max_tiles));
   B2_TRY(w->d_tiles.ensure(max_tiles)); B2_TRY(w->d_mtiles.ensure(max_mtiles));
   B2_TRY(w->d_tilemask.ensure(max_mtiles * 8));
   B2_TRY(w->d_sj.ensure(J));
@@ -251,19 +252,21 @@ int run_batch(b2_encoder *e, Workspace *w, const u8 *d_in, std::vector<B2Job> &j
     b.grp_off = gpos; gpos += gmax;
     max_g = std::max(max_g, gmax);
     ids[j] = j; ns[j] = b.n;
+    b.na = b.n;
     b.tile0 = (u32)mtiles.size();
     for (u32 s = 0; s < b.n; s += B2_MTF_TILE) mtiles.push_back(B2SortTile{j, s});
     w->block_bytes += b.n;
   }
   w->blocks += J;
   w->total_groups = gpos;
-  // write grp_off / tile0 back (the only fields changed on the host)
+  // write grp_off / tile0 / na back (the only fields changed on the host)
   B2_CUDA_CHECK(cudaMemcpyAsync(w->d_jobs.p, w->batch_jobs.data(), J * sizeof(B2Job), cudaMemcpyHostToDevice, st));
   {
     StageTimer tm(e, st, w->ev, &w->stage_ms[2]);
     B2SortCtx cx;
     cx.keysA = w->d_keysA.p; cx.keysB = w->d_keysB.p; cx.valsA = w->d_valsA.p; cx.valsB = w->d_valsB.p;
     cx.rank = w->d_rank.p; cx.grp = w->d_grp.p; cx.d_tiles = w->d_tiles.p; cx.d_sj = w->d_sj.p;
+    cx.slotA = w->d_slotA.p; cx.slotB = w->d_slotB.p; cx.sa_full = w->d_sa.p; cx.d_tile_cnt = w->d_tile_cnt.p;
     cx.d_hist = w->d_hist.p; cx.d_digit_base = w->d_digit_base.p; cx.d_tile_head = w->d_tile_head.p; cx.d_carry = w->d_carry.p;
     cx.d_unsorted = w->d_unsorted.p; cx.h_unsorted = w->h_unsorted;
     cx.max_tiles = w->d_tiles.cap; cx.max_jobs = w->d_sj.cap; cx.timing = e->timing >= 1;

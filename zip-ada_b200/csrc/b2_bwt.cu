@@ -4,15 +4,18 @@
 // an O(N) comparator that is a total order (:229-255), so the sorted matrix, its last column and
 // the origin pointer are unique functions of the block; any sort is admissible.
 //
-// Here: cyclic prefix doubling.  Round 0 sorts every rotation by its first 8 bytes (64-bit key,
-// 8 LSD radix passes of 8 bits); round r >= 1 sorts by the 40-bit key (rank[i] << 20 | rank[(i+h)
-// mod n]) with 5 passes, h = 8, 16, ...  A rank is the row index of the first row of a class, so
-// equal prefixes share a rank and a block is finished when every class is a single row or when the
-// compared prefix covers the whole rotation (periodic blocks: the classes are then sets of EQUAL
-// rotations; their last-column bytes coincide and the origin pointer is the first row of the class
-// of rotation 0, because the reference orders equal rotations by offset and rotation 0 has offset
-// 0, :254, :276-279).  All blocks of a batch are sorted together: every radix pass is segmented by
-// block through a tile table, so no block id is needed in the key.
+// Here: cyclic prefix doubling with filtering.  Round 0 sorts every rotation by its first 8 bytes
+// (64-bit key, 8 LSD radix passes of 8 bits).  A rank is the row index ("slot") of the first row of
+// a class, so equal prefixes share a rank.  After every round the rows that are alone in their class
+// are final; only the others ("active" rows) are compacted and re-sorted in round r >= 1 by the
+// 40-bit key (rank[i] << 20 | rank[(i+h) mod n]) with 5 passes, h = 8, 16, ..., and written back to
+// the slots they came from (a class occupies a contiguous range of slots, and the key's high part
+// keeps classes in place).  A block is finished when no row is active or when the compared prefix
+// covers the whole rotation (periodic blocks: the classes are then sets of EQUAL rotations; their
+// last-column bytes coincide and the origin pointer is the first row of the class of rotation 0,
+// because the reference orders equal rotations by offset and rotation 0 has offset 0, :254,
+// :276-279).  All blocks of a batch are sorted together: every radix pass is segmented by block
+// through a tile table, so no block id is needed in the key.
 //
 // Radix pass = histogram (8 B/elt read) + per-block scan (tiny) + scatter (12 B/elt read, 12 B/elt
 // write, staged through shared memory so the writes leave as runs).
@@ -59,7 +62,7 @@ k_hist(const B2SortTile *__restrict__ tiles, const B2Job *__restrict__ jobs, con
   __shared__ u32 h[256];
   const B2SortTile tl = tiles[blockIdx.x];
   const B2Job &job = jobs[tl.job];
-  const u32 n = job.n;
+  const u32 n = job.na;
   const u64 *kp = keys + job.pos_off;
   if (threadIdx.x < 256) h[threadIdx.x] = 0;
   __syncthreads();
@@ -94,8 +97,6 @@ k_scan(const B2SortJob *__restrict__ sj, u32 *__restrict__ hist, u32 *__restrict
 }
 
 // ---- stable scatter of one digit ---------------------------------------------------------------
-// Dynamic shared memory: keys[ST_TILE] u64, vals[ST_TILE] u32, warp_cnt[ST_WARPS][256] u32,
-// tile_start[256] u32, g_off[256] u32, scan scratch.
 struct ScatterSmem {
   u64 keys[ST_TILE];
   u32 vals[ST_TILE];
@@ -114,7 +115,7 @@ k_scatter(const B2SortTile *__restrict__ tiles, const B2Job *__restrict__ jobs,
   ScatterSmem &S = *reinterpret_cast<ScatterSmem *>(smem_raw);
   const B2SortTile tl = tiles[blockIdx.x];
   const B2Job &job = jobs[tl.job];
-  const u32 n = job.n, off = job.pos_off;
+  const u32 n = job.na, off = job.pos_off;
   const u32 tid = threadIdx.x, w = warp_id(), l = lane_id();
   const u32 lt_mask = (1u << l) - 1u;
   for (int i = tid; i < ST_WARPS * 256; i += ST_THREADS) (&S.warp_cnt[0][0])[i] = 0;
@@ -180,111 +181,140 @@ k_scatter(const B2SortTile *__restrict__ tiles, const B2Job *__restrict__ jobs,
   }
 }
 
-// ---- class heads -> ranks ---------------------------------------------------------------------
+// ---- class heads, singletons -> ranks, compaction of the still active rows --------------------
+// Works on the sorted compact list of a block: c in [0, na).  head(c): key differs from key(c-1);
+// single(c): head(c) and (c+1 == na or head(c+1)).
 __global__ void __launch_bounds__(ST_THREADS)
 k_heads(const B2SortTile *__restrict__ tiles, const B2Job *__restrict__ jobs, const u64 *__restrict__ keys,
-        i32 *__restrict__ tile_head) {
+        i32 *__restrict__ tile_head, u32 *__restrict__ tile_cnt) {
   __shared__ i32 last;
+  __shared__ u32 cnt;
   const B2SortTile tl = tiles[blockIdx.x];
   const B2Job &job = jobs[tl.job];
-  const u32 n = job.n;
+  const u32 n = job.na;
   const u64 *kp = keys + job.pos_off;
-  if (threadIdx.x == 0) last = -1;
+  if (threadIdx.x == 0) { last = -1; cnt = 0; }
   __syncthreads();
   i32 mine = -1;
+  u32 act = 0;
 #pragma unroll 4
   for (int k = 0; k < ST_ITEMS; k++) {
     u32 i = tl.start + threadIdx.x + k * ST_THREADS;
-    if (i < n && (i == 0 || kp[i] != kp[i - 1])) mine = (i32)i;
+    if (i < n) {
+      const u64 kc = kp[i];
+      const bool head = (i == 0) || kc != kp[i - 1];
+      const bool nexthead = (i + 1 == n) || kp[i + 1] != kc;
+      if (head) mine = (i32)i;
+      if (!(head && nexthead)) act++;
+    }
   }
 #pragma unroll
-  for (int o = 16; o; o >>= 1) mine = max(mine, __shfl_xor_sync(0xffffffffu, mine, o));
-  if (lane_id() == 0 && mine >= 0) atomicMax(&last, mine);
+  for (int o = 16; o; o >>= 1) { mine = max(mine, __shfl_xor_sync(0xffffffffu, mine, o)); act += __shfl_xor_sync(0xffffffffu, act, o); }
+  if (lane_id() == 0) { if (mine >= 0) atomicMax(&last, mine); if (act) atomicAdd(&cnt, act); }
   __syncthreads();
-  if (threadIdx.x == 0) tile_head[blockIdx.x] = last;
+  if (threadIdx.x == 0) { tile_head[blockIdx.x] = last; tile_cnt[blockIdx.x] = cnt; }
 }
 
 __global__ void k_scan_heads(const B2SortJob *__restrict__ sj, u32 n_sj, B2Job *jobs,
-                             const i32 *__restrict__ tile_head, i32 *__restrict__ carry_in) {
+                             const i32 *__restrict__ tile_head, i32 *__restrict__ carry_in, u32 *__restrict__ tile_cnt) {
   u32 s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_sj) return;
   const B2SortJob j = sj[s];
   i32 run = -1;
+  u32 pre = 0;
   for (u32 t = 0; t < j.ntiles; t++) {
     carry_in[j.tile0 + t] = run;
     i32 h = tile_head[j.tile0 + t];
     if (h >= 0) run = h;
+    u32 c = tile_cnt[j.tile0 + t];
+    tile_cnt[j.tile0 + t] = pre;                 // exclusive prefix of active rows
+    pre += c;
   }
-  jobs[j.job].unsorted = 0;
+  jobs[j.job].unsorted = pre;                    // active rows of the next round
 }
 
+// slot_in == nullptr: round 0, the compact list is the whole block (slot of c is c).
 __global__ void __launch_bounds__(ST_THREADS)
-k_ranks(const B2SortTile *__restrict__ tiles, B2Job *jobs, const u64 *__restrict__ keys,
-        const u32 *__restrict__ sa, const i32 *__restrict__ carry_in, u32 *__restrict__ rank, u32 *__restrict__ grp) {
+k_ranks(const B2SortTile *__restrict__ tiles, const B2Job *__restrict__ jobs, const u64 *__restrict__ keys,
+        const u32 *__restrict__ vals, const i32 *__restrict__ carry_in, const u32 *__restrict__ tile_cnt,
+        const u32 *__restrict__ slot_in, u32 *__restrict__ rank, u32 *__restrict__ sa_full,
+        u32 *__restrict__ slot_out, u32 *__restrict__ vals_out, u32 *__restrict__ grp_out) {
   __shared__ i32 wl[ST_WARPS];
-  __shared__ u32 nonhead;
+  __shared__ u32 wact[ST_WARPS];
   const B2SortTile tl = tiles[blockIdx.x];
-  B2Job &job = jobs[tl.job];
-  const u32 n = job.n, off = job.pos_off;
+  const B2Job &job = jobs[tl.job];
+  const u32 n = job.na, off = job.pos_off;
   const u64 *kp = keys + off;
   const u32 w = warp_id(), l = lane_id();
   const u32 wbase = tl.start + w * ST_WCHUNK;
-  if (threadIdx.x == 0) nonhead = 0;
-  u32 masks[ST_ITEMS];
+  u32 hmask[ST_ITEMS], amask[ST_ITEMS];
   i32 wlast = -1;
-  u32 nh = 0;
+  u32 na_w = 0;
 #pragma unroll
   for (int k = 0; k < ST_ITEMS; k++) {
-    u32 i = wbase + k * 32 + l;
-    bool valid = i < n;
-    bool flag = valid && (i == 0 || kp[i] != kp[i - 1]);
-    u32 m = __ballot_sync(0xffffffffu, flag);
-    masks[k] = m;
+    const u32 i = wbase + k * 32 + l;
+    bool head = false, act = false;
+    if (i < n) {
+      const u64 kc = kp[i];
+      head = (i == 0) || kc != kp[i - 1];
+      const bool nexthead = (i + 1 == n) || kp[i + 1] != kc;
+      act = !(head && nexthead);
+    }
+    const u32 m = __ballot_sync(0xffffffffu, head);
+    const u32 am = __ballot_sync(0xffffffffu, act);
+    hmask[k] = m; amask[k] = am;
     if (m) wlast = (i32)(wbase + k * 32 + (31 - __clz(m)));
-    if (valid && !flag) nh++;
+    na_w += __popc(am);
   }
-  if (l == 0) wl[w] = wlast;
+  if (l == 0) { wl[w] = wlast; wact[w] = na_w; }
   __syncthreads();
   i32 carry = carry_in[blockIdx.x];
-  for (u32 ww = 0; ww < w; ww++) carry = max(carry, wl[ww]);
+  u32 cbase = tile_cnt[blockIdx.x];
+  for (u32 ww = 0; ww < w; ww++) { carry = max(carry, wl[ww]); cbase += wact[ww]; }
   const u32 le_mask = 0xFFFFFFFFu >> (31 - l);
+  const u32 lt_mask = (1u << l) - 1u;
 #pragma unroll
   for (int k = 0; k < ST_ITEMS; k++) {
-    u32 i = wbase + k * 32 + l;
-    u32 m = masks[k];
-    u32 mm = m & le_mask;
-    i32 head = mm ? (i32)(wbase + k * 32 + (31 - __clz(mm))) : carry;
+    const u32 i = wbase + k * 32 + l;
+    const u32 m = hmask[k], am = amask[k];
+    const u32 mm = m & le_mask;
+    const i32 headc = mm ? (i32)(wbase + k * 32 + (31 - __clz(mm))) : carry;
     if (m) carry = (i32)(wbase + k * 32 + (31 - __clz(m)));
     if (i < n) {
-      rank[off + sa[off + i]] = (u32)head;
-      grp[off + i] = (u32)head;
+      const u32 slot = slot_in ? slot_in[off + i] : i;
+      const u32 headslot = slot_in ? slot_in[off + (u32)headc] : (u32)headc;
+      const u32 v = vals[off + i];
+      sa_full[off + slot] = v;
+      rank[off + v] = headslot;
+      if ((am >> l) & 1u) {
+        const u32 o = off + cbase + __popc(am & lt_mask);
+        slot_out[o] = slot;
+        vals_out[o] = v;
+        grp_out[o] = headslot;
+      }
     }
+    cbase += __popc(am);
   }
-#pragma unroll
-  for (int o = 16; o; o >>= 1) nh += __shfl_xor_sync(0xffffffffu, nh, o);
-  if (l == 0 && nh) atomicAdd(&nonhead, nh);
-  __syncthreads();
-  if (threadIdx.x == 0 && nonhead) atomicAdd(&job.unsorted, nonhead);
 }
 
-__global__ void k_collect_unsorted(const B2SortJob *__restrict__ sj, u32 n_sj, const B2Job *__restrict__ jobs,
-                                   u32 *__restrict__ out) {
+// after a round: report the active count and make it the list length of the next round
+__global__ void k_collect_unsorted(const B2SortJob *__restrict__ sj, u32 n_sj, B2Job *jobs, u32 *__restrict__ out) {
   u32 s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s < n_sj) out[s] = jobs[sj[s].job].unsorted;
+  if (s < n_sj) { B2Job &j = jobs[sj[s].job]; out[s] = j.unsorted; j.na = j.unsorted; }
 }
 
-// ---- doubling keys ---------------------------------------------------------------------------
+// ---- doubling keys over the compact list -------------------------------------------------------
 __global__ void __launch_bounds__(ST_THREADS)
 k_keys(const B2SortTile *__restrict__ tiles, const B2Job *__restrict__ jobs, const u32 *__restrict__ sa,
        const u32 *__restrict__ grp, const u32 *__restrict__ rank, u64 *__restrict__ keys, u32 h) {
   const B2SortTile tl = tiles[blockIdx.x];
   const B2Job &job = jobs[tl.job];
-  const u32 n = job.n, off = job.pos_off;
+  const u32 n = job.n, na = job.na, off = job.pos_off;
   const u32 hh = h % n;
 #pragma unroll 4
   for (int k = 0; k < ST_ITEMS; k++) {
     u32 i = tl.start + threadIdx.x + k * ST_THREADS;
-    if (i < n) {
+    if (i < na) {
       u32 s = sa[off + i] + hh;
       if (s >= n) s -= n;
       keys[off + i] = ((u64)grp[off + i] << 20) | (u64)rank[off + s];
@@ -330,18 +360,22 @@ static int build_tiles(const std::vector<u32> &job_ids, const std::vector<u32> &
 
 struct EvPair { cudaEvent_t a, b; };
 
+// job_n[k] = post-RLE1 size of block job_ids[k]; the device copies have na == n on entry.
 int b2k_bwt_batch(B2SortCtx *cx, cudaStream_t st, B2Job *d_jobs, const std::vector<u32> &job_ids,
                   const std::vector<u32> &job_n, const u8 *d_text, u8 *d_bwt) {
   // per device and cheap; set on every call so that handles on several devices / threads all have it
   B2_CUDA_CHECK(cudaFuncSetAttribute(k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
   std::vector<B2SortTile> tiles;
   std::vector<B2SortJob> sj;
-  std::vector<u32> ids = job_ids, ns = job_n;
-  build_tiles(ids, ns, tiles, sj);
+  std::vector<u32> ids, ns, nas;             // active blocks: id, size, active rows
+  for (size_t k = 0; k < job_ids.size(); k++) if (job_n[k] > 0) { ids.push_back(job_ids[k]); ns.push_back(job_n[k]); }
+  nas = ns;
+  build_tiles(ids, nas, tiles, sj);
   if (tiles.empty()) return 0;
   if (tiles.size() > cx->max_tiles || sj.size() > cx->max_jobs) { b2_set_error(__FILE__, __LINE__, "sort workspace too small"); return 11; }
   u64 *kA = cx->keysA, *kB = cx->keysB;
   u32 *vA = cx->valsA, *vB = cx->valsB;
+  u32 *slotA = cx->slotA, *slotB = cx->slotB;
   std::vector<EvPair> evs;
   auto upload = [&]() -> int {
     B2_CUDA_CHECK(cudaMemcpyAsync(cx->d_tiles, tiles.data(), tiles.size() * sizeof(B2SortTile), cudaMemcpyHostToDevice, st));
@@ -359,31 +393,28 @@ int b2k_bwt_batch(B2SortCtx *cx, cudaStream_t st, B2Job *d_jobs, const std::vect
     B2_CUDA_CHECK(cudaGetLastError());
     std::swap(kA, kB); std::swap(vA, vB);
     u64 el = 0;
-    for (u32 x : ns) el += x;
+    for (u32 x : nas) el += x;
     cx->stats.scatter_launches++;
     cx->stats.scatter_elems += el;
     cx->stats.launches += 3;
     return 0;
   };
-  auto ranks = [&]() -> int {
+  // heads -> ranks -> compaction; afterwards vA holds the compacted rotation indices, slotA their slots
+  auto ranks = [&](bool round0) -> int {
     u32 nt = (u32)tiles.size(), nj = (u32)sj.size();
-    k_heads<<<nt, ST_THREADS, 0, st>>>(cx->d_tiles, d_jobs, kA, cx->d_tile_head);
-    k_scan_heads<<<(nj + 127) / 128, 128, 0, st>>>(cx->d_sj, nj, d_jobs, cx->d_tile_head, cx->d_carry);
-    k_ranks<<<nt, ST_THREADS, 0, st>>>(cx->d_tiles, d_jobs, kA, vA, cx->d_carry, cx->rank, cx->grp);
+    k_heads<<<nt, ST_THREADS, 0, st>>>(cx->d_tiles, d_jobs, kA, cx->d_tile_head, cx->d_tile_cnt);
+    k_scan_heads<<<(nj + 127) / 128, 128, 0, st>>>(cx->d_sj, nj, d_jobs, cx->d_tile_head, cx->d_carry, cx->d_tile_cnt);
+    k_ranks<<<nt, ST_THREADS, 0, st>>>(cx->d_tiles, d_jobs, kA, vA, cx->d_carry, cx->d_tile_cnt, round0 ? nullptr : slotA,
+                                       cx->rank, cx->sa_full, slotB, vB, cx->grp);
     k_collect_unsorted<<<(nj + 127) / 128, 128, 0, st>>>(cx->d_sj, nj, d_jobs, cx->d_unsorted);
     cx->stats.launches += 4;
     B2_CUDA_CHECK(cudaGetLastError());
+    std::swap(vA, vB); std::swap(slotA, slotB);
     B2_CUDA_CHECK(cudaMemcpyAsync(cx->h_unsorted, cx->d_unsorted, nj * sizeof(u32), cudaMemcpyDeviceToHost, st));
     B2_CUDA_CHECK(cudaStreamSynchronize(st));
     return 0;
   };
 
-  // compact per-active-job n (ns) aligned with sj
-  {
-    std::vector<u32> ids2, ns2;
-    for (size_t k = 0; k < ids.size(); k++) if (ns[k] > 0) { ids2.push_back(ids[k]); ns2.push_back(ns[k]); }
-    ids.swap(ids2); ns.swap(ns2);
-  }
   int rc;
   if ((rc = upload())) return rc;
   {
@@ -393,36 +424,36 @@ int b2k_bwt_batch(B2SortCtx *cx, cudaStream_t st, B2Job *d_jobs, const std::vect
   k_keys0<<<(u32)tiles.size(), ST_THREADS, 0, st>>>(cx->d_tiles, d_jobs, d_text, kA, vA);
   cx->stats.launches += 1;
   for (int p = 0; p < 8; p++) if ((rc = radix_pass(8 * p))) return rc;
-  if ((rc = ranks())) return rc;
+  if ((rc = ranks(true))) return rc;
   cx->stats.rounds++;
   u64 reflect = 8;
   for (;;) {
     // split finished / unfinished
-    std::vector<u32> fin_ids, fin_n, go_ids, go_n;
+    std::vector<u32> fin_ids, fin_n, go_ids, go_n, go_na;
     for (size_t k = 0; k < ids.size(); k++) {
       bool done = cx->h_unsorted[k] == 0 || reflect >= ns[k];
       if (done) { fin_ids.push_back(ids[k]); fin_n.push_back(ns[k]); }
-      else { go_ids.push_back(ids[k]); go_n.push_back(ns[k]); }
+      else { go_ids.push_back(ids[k]); go_n.push_back(ns[k]); go_na.push_back(cx->h_unsorted[k]); }
     }
     if (!fin_ids.empty()) {
       build_tiles(fin_ids, fin_n, tiles, sj);
       if ((rc = upload())) return rc;
-      k_bwt_out<<<(u32)tiles.size(), ST_THREADS, 0, st>>>(cx->d_tiles, d_jobs, vA, d_text, cx->rank, d_bwt);
+      k_bwt_out<<<(u32)tiles.size(), ST_THREADS, 0, st>>>(cx->d_tiles, d_jobs, cx->sa_full, d_text, cx->rank, d_bwt);
       B2_CUDA_CHECK(cudaGetLastError());
       cx->stats.launches += 1;
     }
     if (go_ids.empty()) break;
-    ids.swap(go_ids); ns.swap(go_n);
-    build_tiles(ids, ns, tiles, sj);
+    ids.swap(go_ids); ns.swap(go_n); nas.swap(go_na);
+    build_tiles(ids, nas, tiles, sj);
     if ((rc = upload())) return rc;
     {
-      u64 el = 0; for (u32 x : ns) el += x;
+      u64 el = 0; for (u32 x : nas) el += x;
       cx->stats.sorted_elems_later += el;
     }
     k_keys<<<(u32)tiles.size(), ST_THREADS, 0, st>>>(cx->d_tiles, d_jobs, vA, cx->grp, cx->rank, kA, (u32)(reflect));
     cx->stats.launches += 1;
     for (int p = 0; p < 5; p++) if ((rc = radix_pass(8 * p))) return rc;
-    if ((rc = ranks())) return rc;
+    if ((rc = ranks(false))) return rc;
     cx->stats.rounds++;
     reflect *= 2;
   }

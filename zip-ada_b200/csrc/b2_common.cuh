@@ -36,7 +36,9 @@ struct B2Job {
   u32 n_groups;     // G = 1 + (M-1)/50
   u32 best;         // winning triple index           (written by k_choose)
   u32 best_cost;
-  u32 unsorted;     // sort bookkeeping: rows not yet alone in their class
+  u32 unsorted;     // sort bookkeeping: rows not yet alone in their class after the current round
+  u32 na;           // sort bookkeeping: rows in the compact (active) list of the current round
+  u32 pad1;
   u32 tile0;        // index of the block's first 4096-tile in the MTF tile table
   u64 nbits;        // exact size of the block's bitstream (written by k_choose)
   u64 bits_off;     // u32-word offset in the bit arena (written by k_bits_layout)

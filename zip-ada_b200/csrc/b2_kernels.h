@@ -44,6 +44,7 @@ struct B2ConcatItem { u64 src_word; u64 nbits; u64 dst_bit; };
 struct B2SortCtx {
   u64 *keysA, *keysB;
   u32 *valsA, *valsB, *rank, *grp;
+  u32 *slotA, *slotB, *sa_full, *d_tile_cnt;
   B2SortTile *d_tiles;
   B2SortJob *d_sj;
   u32 *d_hist, *d_digit_base;
