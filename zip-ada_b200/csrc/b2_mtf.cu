@@ -74,10 +74,38 @@ k_mtf_masks(const B2SortTile *__restrict__ tiles, const B2Job *__restrict__ jobs
   if (tid < 8) tilemask[(size_t)blockIdx.x * 8 + tid] = tm[tid];
 }
 
+// OR of `mine` (8 words, only meaningful on lanes with `take`) over the warp, added to seen[] on all lanes.
+__device__ __forceinline__ void warp_or_into(u32 *seen, const u32 *mine, bool take) {
+#pragma unroll
+  for (int q = 0; q < 8; q++) seen[q] |= __reduce_or_sync(0xffffffffu, take ? mine[q] : 0u);
+}
+
+// Scans up to 32 masks downwards from index `from` (lane l looks at mask from - l, valid while >= lo).
+// Returns the index of the nearest mask that contains b (or -1) and ORs all nearer masks into seen[].
+__device__ __forceinline__ i32 warp_scan_masks(const u32 *__restrict__ masks, i32 from, i32 lo, u32 bw, u32 bbit, u32 *seen) {
+  const u32 l = lane_id();
+  const i32 s = from - (i32)l;
+  const bool valid = s >= lo;
+  u32 m[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (valid) {
+    const uint4 a = *reinterpret_cast<const uint4 *>(masks + (size_t)s * 8), c = *reinterpret_cast<const uint4 *>(masks + (size_t)s * 8 + 4);
+    m[0] = a.x; m[1] = a.y; m[2] = a.z; m[3] = a.w; m[4] = c.x; m[5] = c.y; m[6] = c.z; m[7] = c.w;
+  }
+  u32 wsel = m[0];
+#pragma unroll
+  for (int q = 1; q < 8; q++) wsel = (bw == (u32)q) ? m[q] : wsel;
+  const u32 hit = __ballot_sync(0xffffffffu, valid && (wsel & bbit));
+  const u32 first = hit ? (u32)(__ffs(hit) - 1) : 32u;     // nearest mask containing b
+  warp_or_into(seen, m, valid && l < first);
+  return hit ? from - (i32)first : -1;
+}
+
 __global__ void __launch_bounds__(MI_THREADS)
 k_mtf_index(const B2SortTile *__restrict__ tiles, const B2Job *__restrict__ jobs, const u8 *__restrict__ bwt,
             const u32 *__restrict__ m16, const u32 *__restrict__ m256, const u32 *__restrict__ tilemask,
             u8 *__restrict__ idx_out) {
+  __shared__ u16 hard[B2_MTF_TILE];
+  __shared__ u32 n_hard;
   const B2SortTile tl = tiles[blockIdx.x];
   const B2Job &job = jobs[tl.job];
   const u32 n = job.n, off = job.pos_off;
@@ -85,75 +113,89 @@ k_mtf_index(const B2SortTile *__restrict__ tiles, const B2Job *__restrict__ jobs
   const u32 *s16 = m16 + (size_t)(off >> 4) * 8;             // block-relative masks
   const u32 *s256 = m256 + (size_t)(off >> 8) * 8;
   const u32 *tmk = tilemask + (size_t)job.tile0 * 8;
+  if (threadIdx.x == 0) n_hard = 0;
+  __syncthreads();
+  // ---- phase A: every thread, own 16-segment only ---------------------------------------------
   for (int k = 0; k < MI_ITEMS; k++) {
     const u32 i = tl.start + k * MI_THREADS + threadIdx.x;
     if (i >= n) continue;
     const u32 b = d[i];
-    u32 idx;
-    if (i > 0 && d[i - 1] == b) idx = 0;
-    else {
-      u32 seen[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      const u32 bw = b >> 5, bbit = 1u << (b & 31);
-      bool found = false;
-      // 1. own 16-segment, byte by byte
-      const i32 g16 = (i32)(i >> 4);
-      for (i32 j = (i32)i - 1; j >= (g16 << 4); j--) {
-        const u32 x = d[j];
-        if (x == b) { found = true; break; }
-        seen_set(seen, x);
-      }
-      if (!found) {
-        i32 hit16 = -1;
-        // descend into a 256-segment known (or not) to contain b: its 16-segments from `from` down
-        auto scan16 = [&](i32 from, i32 lo) {
-          for (i32 s = from; s >= lo; s--) {
-            const u32 *m = s16 + (size_t)s * 8;
-            if (m[bw] & bbit) { hit16 = s; return; }
-            mask_or(seen, m);
-          }
-        };
-        auto scan256 = [&](i32 from, i32 lo) {
-          for (i32 s = from; s >= lo; s--) {
-            const u32 *m = s256 + (size_t)s * 8;
-            if (m[bw] & bbit) { scan16((s << 4) + 15, s << 4); return; }
-            mask_or(seen, m);
-          }
-        };
-        const i32 g256 = (i32)(i >> 8), tile = (i32)(i >> 12);
-        scan16(g16 - 1, g256 << 4);                          // 2. earlier 16-segments of the own 256-segment
-        if (hit16 < 0) scan256(g256 - 1, tile << 4);         // 3. earlier 256-segments of the own tile
-        if (hit16 < 0) {                                     // 4. earlier tiles
-          for (i32 t = tile - 1; t >= 0; t--) {
-            const u32 *m = tmk + (size_t)t * 8;
-            if (m[bw] & bbit) { scan256((t << 4) + 15, t << 4); break; }
-            mask_or(seen, m);
-          }
-        }
-        if (hit16 >= 0) {
-          for (i32 j = (hit16 << 4) + 15; j >= (hit16 << 4); j--) {
-            const u32 x = d[j];
-            if (x == b) { found = true; break; }
-            seen_set(seen, x);
-          }
+    if (i > 0 && d[i - 1] == b) { idx_out[off + i] = 0; continue; }
+    u32 seen[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    bool found = false;
+    for (i32 j = (i32)i - 1; j >= (i32)(i & ~15u); j--) {
+      const u32 x = d[j];
+      if (x == b) { found = true; break; }
+      seen_set(seen, x);
+    }
+    if (found) {
+      u32 idx = 0;
+#pragma unroll
+      for (int w = 0; w < 8; w++) idx += __popc(seen[w]);
+      idx_out[off + i] = (u8)idx;
+    } else {
+      hard[atomicAdd(&n_hard, 1u)] = (u16)(i - tl.start);
+    }
+  }
+  __syncthreads();
+  // ---- phase B: one warp per remaining position, masks examined 32 at a time ------------------
+  const u32 nh = n_hard, l = lane_id();
+  for (u32 hI = warp_id(); hI < nh; hI += MI_THREADS / 32) {
+    const u32 i = tl.start + hard[hI];
+    const u32 b = d[i];
+    const u32 bw = b >> 5, bbit = 1u << (b & 31);
+    u32 seen[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    u32 mine[8];
+    // own 16-segment (b is known not to occur in it before i)
+    {
+      const u32 p = (i & ~15u) + l;
+      const bool take = l < 16 && p < i;
+#pragma unroll
+      for (int q = 0; q < 8; q++) mine[q] = 0;
+      if (take) seen_set(mine, d[p]);
+      warp_or_into(seen, mine, take);
+    }
+    const i32 g16 = (i32)(i >> 4), g256 = (i32)(i >> 8), tile = (i32)(i >> 12);
+    i32 hit16 = warp_scan_masks(s16, g16 - 1, g256 << 4, bw, bbit, seen);              // own 256-segment
+    if (hit16 < 0) {
+      i32 hit256 = warp_scan_masks(s256, g256 - 1, tile << 4, bw, bbit, seen);         // own tile
+      if (hit256 < 0) {
+        for (i32 t = tile - 1; t >= 0 && hit256 < 0; t -= 32) {                        // earlier tiles
+          const i32 ht = warp_scan_masks(tmk, t, 0, bw, bbit, seen);
+          if (ht >= 0) { hit256 = warp_scan_masks(s256, (ht << 4) + 15, ht << 4, bw, bbit, seen); break; }
         }
       }
-      if (found) {
-        idx = 0;
+      if (hit256 >= 0) hit16 = warp_scan_masks(s16, (hit256 << 4) + 15, hit256 << 4, bw, bbit, seen);
+    }
+    bool found = false;
+    if (hit16 >= 0) {
+      // bytes of the hit segment from its end downwards: lane l looks at byte 15 - l
+      const u32 p = ((u32)hit16 << 4) + 15 - l;
+      const u32 x = l < 16 ? d[p] : 256u;
+      const u32 mt = __ballot_sync(0xffffffffu, x == b);
+      const u32 first = (u32)(__ffs(mt) - 1);
+      const bool take = l < first;
 #pragma unroll
-        for (int w = 0; w < 8; w++) idx += __popc(seen[w]);
-      } else {
-        // rank of b among used bytes + seen symbols larger than b
-        idx = 0;
-        const u32 bb = b & 31;
+      for (int q = 0; q < 8; q++) mine[q] = 0;
+      if (take) seen_set(mine, x);
+      warp_or_into(seen, mine, take);
+      found = true;
+    }
+    u32 idx = 0;
+    if (found) {
 #pragma unroll
-        for (int w = 0; w < 8; w++) {
-          u32 below = (w < (int)bw) ? 0xFFFFFFFFu : ((w == (int)bw) ? ((1u << bb) - 1u) : 0u);
-          u32 above = (w > (int)bw) ? 0xFFFFFFFFu : ((w == (int)bw) ? (bb == 31 ? 0u : (0xFFFFFFFFu << (bb + 1))) : 0u);
-          idx += __popc(job.in_use[w] & below) + __popc(seen[w] & above);
-        }
+      for (int w = 0; w < 8; w++) idx += __popc(seen[w]);
+    } else {
+      // rank of b among used bytes + seen symbols larger than b
+      const u32 bb = b & 31;
+#pragma unroll
+      for (int w = 0; w < 8; w++) {
+        u32 below = (w < (int)bw) ? 0xFFFFFFFFu : ((w == (int)bw) ? ((1u << bb) - 1u) : 0u);
+        u32 above = (w > (int)bw) ? 0xFFFFFFFFu : ((w == (int)bw) ? (bb == 31 ? 0u : (0xFFFFFFFFu << (bb + 1))) : 0u);
+        idx += __popc(job.in_use[w] & below) + __popc(seen[w] & above);
       }
     }
-    idx_out[off + i] = (u8)idx;
+    if (l == 0) idx_out[off + i] = (u8)idx;
   }
 }
 
