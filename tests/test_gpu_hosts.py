@@ -1,0 +1,62 @@
+"""The C++ and Python mirrors of the generic Encode, driven through the C ABI.  `-m gpu`."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import datagen
+import oracle_lib as orc
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cpp_host_mirror_b2enc(tmp_path):
+    exe = tmp_path / "b2enc"
+    pkg = os.path.join(ROOT, "zip-ada_b200")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", os.path.join(pkg, "host", "b2enc.cpp"), "-L" + pkg, "-lb2gpu",
+                           "-Wl,-rpath," + pkg, "-o", str(exe)])
+    data = datagen.mixed(700_000, 100_000, 41)
+    fin, fout = tmp_path / "in.bin", tmp_path / "out.bz2"
+    fin.write_bytes(data.tobytes())
+    subprocess.check_call([str(exe), str(fin), str(fout), "-3"])
+    # bzip2_enc passes no size hint (extras/bzip2_enc.adb:51-55)
+    assert fout.read_bytes() == orc.encode_stream(data, 9, -1)
+
+
+def test_python_callbacks_mirror(enc9):
+    data = datagen.text(50_000, 42).tobytes()
+    pos = [0]
+    out = bytearray()
+
+    def read_byte():
+        b = data[pos[0]]
+        pos[0] += 1
+        return b
+
+    enc9.encode_callbacks(read_byte, lambda: pos[0] < len(data), out.append, len(data))
+    assert bytes(out) == orc.encode_stream(data, 9, len(data))
+
+
+def test_two_handles_are_independent(b2mod):
+    d1, d2 = datagen.text(300_000, 43), datagen.random_bytes(200_000, 44)
+    with b2mod.Encoder(9, 0) as a, b2mod.Encoder(4, 0) as b:
+        o1 = a.encode(d1, d1.size).tobytes()
+        o2 = b.encode(d2, d2.size).tobytes()
+        o1b = a.encode(d1, d1.size).tobytes()
+    assert o1 == o1b == orc.encode_stream(d1, 9, d1.size)
+    assert o2 == orc.encode_stream(d2, 4, d2.size)
+
+
+def test_small_batches_and_pipeline_give_identical_bytes(b2mod, monkeypatch):
+    data = datagen.mixed(6_000_000, 700_000, 45)
+    ref = None
+    for pos, pipe in (("4000000", "1"), ("4000000", "2"), ("600000000", "1")):
+        monkeypatch.setenv("B2GPU_BATCH_POSITIONS", pos)
+        monkeypatch.setenv("B2GPU_PIPELINE", pipe)
+        with b2mod.Encoder(9, 0) as e:
+            out = e.encode(data, data.size).tobytes()
+        ref = ref or out
+        assert out == ref
+    assert ref == orc.encode_stream(data, 9, data.size)

@@ -150,7 +150,7 @@ k_cut_s2(const u32 *__restrict__ tsum, u64 ntiles, u64 *__restrict__ tincl) {
   for (u64 t = a; t < e; t++) { run += tsum[t]; tincl[t] = run; }
 }
 
-// One warp scans one tile.  Each lane owns 64 consecutive bytes.
+// One warp scans one tile.  Each lane owns 64 consecutive bytes, loaded once as four 16-byte vectors.
 //  mode 0: inclusive in-tile prefix of g at global position q          -> returns the prefix
 //  mode 1: first global position p in the tile with excl + prefix(p) >= target   -> position or ~0
 //  mode 2: first global position p > q in the tile where the byte changes        -> position or ~0
@@ -159,12 +159,22 @@ __device__ u64 warp_tile(const u8 *__restrict__ in, u64 n, const u64 *__restrict
   const u32 l = lane_id();
   const u64 t0 = t * CT_TILE;
   const u64 base = t0 + l * 64;
+  u32 w[16];
+#pragma unroll
+  for (int v = 0; v < 4; v++) {
+    u8 b16[16];
+    load16(in, base + 16 * v, n, b16);
+#pragma unroll
+    for (int k = 0; k < 4; k++) w[4 * v + k] = (u32)b16[4 * k] | ((u32)b16[4 * k + 1] << 8) | ((u32)b16[4 * k + 2] << 16) | ((u32)b16[4 * k + 3] << 24);
+  }
+  const u8 prev = (base > 0 && base < n) ? in[base - 1] : 0;
   u64 res = ~0ull;
   if (mode == 2) {
-    u8 pv = (base > 0 && base < n) ? in[base - 1] : 0;
+    u8 pv = prev;
+#pragma unroll
     for (int k = 0; k < 64; k++) {
       const u64 p = base + k;
-      u8 c = p < n ? in[p] : 0;
+      const u8 c = (u8)(w[k >> 2] >> (8 * (k & 3)));
       if (p < n && p > q && (p == 0 || c != pv) && res == ~0ull) res = p;
       pv = c;
     }
@@ -175,10 +185,11 @@ __device__ u64 warp_tile(const u8 *__restrict__ in, u64 n, const u64 *__restrict
   // run start entering my 64 bytes
   i32 lc = -1;
   {
-    u8 pv = (base > 0 && base < n) ? in[base - 1] : 0;
+    u8 pv = prev;
+#pragma unroll
     for (int k = 0; k < 64; k++) {
       const u64 p = base + k;
-      u8 c = p < n ? in[p] : 0;
+      const u8 c = (u8)(w[k >> 2] >> (8 * (k & 3)));
       if (p < n && (p == 0 || c != pv)) lc = (i32)(l * 64 + k);
       pv = c;
     }
@@ -187,15 +198,16 @@ __device__ u64 warp_tile(const u8 *__restrict__ in, u64 n, const u64 *__restrict
   i32 rin = __shfl_up_sync(0xffffffffu, inc, 1);
   if (l == 0) rin = -1;
   const u64 cr = carry_r[t];
-  u64 r = rin >= 0 ? t0 + (u64)rin : (cr ? cr - 1 : 0);
+  const u64 r0 = rin >= 0 ? t0 + (u64)rin : (cr ? cr - 1 : 0);
   // my sum
   u32 local = 0;
   {
-    u64 rr = r;
-    u8 pv = (base > 0 && base < n) ? in[base - 1] : 0;
+    u64 rr = r0;
+    u8 pv = prev;
+#pragma unroll 8
     for (int k = 0; k < 64; k++) {
       const u64 p = base + k;
-      u8 c = p < n ? in[p] : 0;
+      const u8 c = (u8)(w[k >> 2] >> (8 * (k & 3)));
       if (p < n) { const bool chg = (p == 0 || c != pv); const u64 rp = rr; if (chg) rr = p; local += gcommit(p, chg, rp, rr); }
       pv = c;
     }
@@ -203,10 +215,12 @@ __device__ u64 warp_tile(const u8 *__restrict__ in, u64 n, const u64 *__restrict
   const u32 incl = warp_incl_add(local);
   u64 run = excl + (incl - local);
   {
-    u8 pv = (base > 0 && base < n) ? in[base - 1] : 0;
+    u64 r = r0;
+    u8 pv = prev;
+#pragma unroll 8
     for (int k = 0; k < 64; k++) {
       const u64 p = base + k;
-      u8 c = p < n ? in[p] : 0;
+      const u8 c = (u8)(w[k >> 2] >> (8 * (k & 3)));
       if (p < n) {
         const bool chg = (p == 0 || c != pv);
         const u64 rp = r;
