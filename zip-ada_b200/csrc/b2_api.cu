@@ -73,7 +73,7 @@ struct Workspace {
   DevBuf<u32> d_m16, d_m256, d_tilemask;
   DevBuf<u64> d_keysA, d_keysB;
   DevBuf<u32> d_valsA, d_valsB, d_rank, d_grp, d_slotA, d_slotB, d_sa, d_tile_cnt;
-  DevBuf<B2SortTile> d_tiles, d_mtiles;
+  DevBuf<B2SortTile> d_tiles, d_mtiles, d_msegs;
   DevBuf<B2SortJob> d_sj;
   DevBuf<u32> d_hist, d_digit_base;
   DevBuf<i32> d_tile_head, d_carry;
@@ -97,7 +97,7 @@ struct Workspace {
   void release() {
     d_scalars.release(); d_jobs.release(); d_text.release(); d_bwt.release(); d_idx.release(); d_m16.release();
     d_m256.release(); d_tilemask.release(); d_keysA.release(); d_keysB.release(); d_valsA.release(); d_valsB.release();
-    d_rank.release(); d_grp.release(); d_slotA.release(); d_slotB.release(); d_sa.release(); d_tile_cnt.release(); d_tiles.release(); d_mtiles.release(); d_sj.release(); d_hist.release();
+    d_rank.release(); d_grp.release(); d_slotA.release(); d_slotB.release(); d_sa.release(); d_tile_cnt.release(); d_tiles.release(); d_mtiles.release(); d_msegs.release(); d_sj.release(); d_hist.release();
     d_digit_base.release(); d_tile_head.release(); d_carry.release(); d_unsorted.release(); d_mtf.release();
     d_rank3.release(); d_rank4.release(); d_sel.release(); d_selprev.release(); d_selpos.release(); d_lens.release();
     d_ehist.release(); d_leaves.release(); d_estat.release(); d_selcost.release(); d_gcost.release(); d_cost.release();
@@ -186,7 +186,7 @@ int ensure_batch_workspace(Workspace *w, size_t T, size_t J) {
   B2_TRY(w->d_rank.ensure(T)); B2_TRY(w->d_grp.ensure(T));
   B2_TRY(w->d_slotA.ensure(T)); B2_TRY(w->d_slotB.ensure(T)); B2_TRY(w->d_sa.ensure(T)); B2_TRY(w->d_tile_cnt.ensure(max_tiles));
   B2_TRY(w->d_tiles.ensure(max_tiles)); B2_TRY(w->d_mtiles.ensure(max_mtiles));
-  B2_TRY(w->d_tilemask.ensure(max_mtiles * 8));
+  B2_TRY(w->d_tilemask.ensure(max_mtiles * 8)); B2_TRY(w->d_msegs.ensure(T / B2_MTF_SEG + J + 8));
   B2_TRY(w->d_sj.ensure(J));
   B2_TRY(w->d_hist.ensure(max_tiles * 256)); B2_TRY(w->d_digit_base.ensure(J * 256));
   B2_TRY(w->d_tile_head.ensure(max_tiles)); B2_TRY(w->d_carry.ensure(max_tiles));
@@ -244,7 +244,7 @@ int run_batch(b2_encoder *e, Workspace *w, const u8 *d_in, std::vector<B2Job> &j
   // group arena offsets need n (M <= n + 1)
   u32 gpos = 0, max_g = 1;
   std::vector<u32> ids(J), ns(J);
-  std::vector<B2SortTile> mtiles;
+  std::vector<B2SortTile> mtiles, msegs;
   for (u32 j = 0; j < J; j++) {
     B2Job &b = w->batch_jobs[j];
     if (b.n > b.cap) B2_FAIL(B2_ERR_INTERNAL, "RLE1 output exceeds its slot");
@@ -255,6 +255,7 @@ int run_batch(b2_encoder *e, Workspace *w, const u8 *d_in, std::vector<B2Job> &j
     b.na = b.n;
     b.tile0 = (u32)mtiles.size();
     for (u32 s = 0; s < b.n; s += B2_MTF_TILE) mtiles.push_back(B2SortTile{j, s});
+    for (u32 s = 0; s < b.n; s += B2_MTF_SEG) msegs.push_back(B2SortTile{j, s});
     w->block_bytes += b.n;
   }
   w->blocks += J;
@@ -279,8 +280,10 @@ int run_batch(b2_encoder *e, Workspace *w, const u8 *d_in, std::vector<B2Job> &j
     StageTimer tm(e, st, w->ev, &w->stage_ms[3]);
     if (!mtiles.empty())
       B2_CUDA_CHECK(cudaMemcpyAsync(w->d_mtiles.p, mtiles.data(), mtiles.size() * sizeof(B2SortTile), cudaMemcpyHostToDevice, st));
-    B2_TRY(b2k_mtf(st, w->d_jobs.p, J, w->d_mtiles.p, (u32)mtiles.size(), w->d_bwt.p, w->d_m16.p, w->d_m256.p, w->d_tilemask.p,
-                   w->d_idx.p, w->d_mtf.p));
+    if (!msegs.empty())
+      B2_CUDA_CHECK(cudaMemcpyAsync(w->d_msegs.p, msegs.data(), msegs.size() * sizeof(B2SortTile), cudaMemcpyHostToDevice, st));
+    B2_TRY(b2k_mtf(st, w->d_jobs.p, J, w->d_mtiles.p, (u32)mtiles.size(), w->d_msegs.p, (u32)msegs.size(), w->d_bwt.p, w->d_m16.p,
+                   w->d_m256.p, w->d_tilemask.p, w->d_idx.p, w->d_mtf.p));
     w->launches += 3;
   }
   {

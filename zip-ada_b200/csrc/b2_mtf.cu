@@ -5,7 +5,8 @@
 // DISTINCT symbols seen since the previous occurrence of the same symbol; if there is none, it is
 // (rank of the symbol among the used bytes) + (number of distinct symbols seen so far that are
 // larger), because the list starts in increasing order (:374-376, :320-328).  That is a pure
-// function of the data before i, so every position is computed independently (k_mtf_index).
+// function of the data before i, so a block can be cut into segments that are processed
+// independently once the list at the segment start is known (k_mtf_seq).
 //
 // To keep the backward search short, k_mtf_masks first records which byte values occur in every
 // 16-position segment (256-bit mask), every 256-position segment and every 4096-position tile; a
@@ -74,128 +75,165 @@ k_mtf_masks(const B2SortTile *__restrict__ tiles, const B2Job *__restrict__ jobs
   if (tid < 8) tilemask[(size_t)blockIdx.x * 8 + tid] = tm[tid];
 }
 
-// OR of `mine` (8 words, only meaningful on lanes with `take`) over the warp, added to seen[] on all lanes.
-__device__ __forceinline__ void warp_or_into(u32 *seen, const u32 *mine, bool take) {
+// ---------------------------------------------------------------------------------------------
+// k_mtf_seq: one warp per segment of B2_MTF_SEG positions.
+//  1. The list at the segment start is rebuilt from the data before it: walking backwards, the
+//     symbols appear in the order of their last occurrence, which IS the list order; whole
+//     16- / 256-position segments that hold no symbol not yet seen are skipped through their masks;
+//     symbols never seen keep the initial increasing order (:374-376) behind the seen ones.
+//  2. The segment is then processed in order with the list spread over the warp (lane l holds
+//     places 8l .. 8l+7): find by byte compare + ballot, move to front by a byte shift with the
+//     carry passed between neighbouring lanes (:384-396).
+// ---------------------------------------------------------------------------------------------
+#define MS_WARPS 4
+
+__device__ __forceinline__ bool mask_has_new(const u32 *m, const u32 *seen) {
+  u32 r = 0;
 #pragma unroll
-  for (int q = 0; q < 8; q++) seen[q] |= __reduce_or_sync(0xffffffffu, take ? mine[q] : 0u);
+  for (int q = 0; q < 8; q++) r |= m[q] & ~seen[q];
+  return r != 0;
+}
+__device__ __forceinline__ void load_mask(const u32 *__restrict__ p, u32 *m) {
+  const uint4 a = *reinterpret_cast<const uint4 *>(p), c = *reinterpret_cast<const uint4 *>(p + 4);
+  m[0] = a.x; m[1] = a.y; m[2] = a.z; m[3] = a.w; m[4] = c.x; m[5] = c.y; m[6] = c.z; m[7] = c.w;
+}
+__device__ __forceinline__ bool seen_has(const u32 *seen, u32 x) {
+  u32 w = seen[0];
+#pragma unroll
+  for (int q = 1; q < 8; q++) w = ((x >> 5) == (u32)q) ? seen[q] : w;
+  return (w >> (x & 31)) & 1u;
 }
 
-// Scans up to 32 masks downwards from index `from` (lane l looks at mask from - l, valid while >= lo).
-// Returns the index of the nearest mask that contains b (or -1) and ORs all nearer masks into seen[].
-__device__ __forceinline__ i32 warp_scan_masks(const u32 *__restrict__ masks, i32 from, i32 lo, u32 bw, u32 bbit, u32 *seen) {
-  const u32 l = lane_id();
-  const i32 s = from - (i32)l;
-  const bool valid = s >= lo;
-  u32 m[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (valid) {
-    const uint4 a = *reinterpret_cast<const uint4 *>(masks + (size_t)s * 8), c = *reinterpret_cast<const uint4 *>(masks + (size_t)s * 8 + 4);
-    m[0] = a.x; m[1] = a.y; m[2] = a.z; m[3] = a.w; m[4] = c.x; m[5] = c.y; m[6] = c.z; m[7] = c.w;
-  }
-  u32 wsel = m[0];
-#pragma unroll
-  for (int q = 1; q < 8; q++) wsel = (bw == (u32)q) ? m[q] : wsel;
-  const u32 hit = __ballot_sync(0xffffffffu, valid && (wsel & bbit));
-  const u32 first = hit ? (u32)(__ffs(hit) - 1) : 32u;     // nearest mask containing b
-  warp_or_into(seen, m, valid && l < first);
-  return hit ? from - (i32)first : -1;
-}
-
-__global__ void __launch_bounds__(MI_THREADS)
-k_mtf_index(const B2SortTile *__restrict__ tiles, const B2Job *__restrict__ jobs, const u8 *__restrict__ bwt,
-            const u32 *__restrict__ m16, const u32 *__restrict__ m256, const u32 *__restrict__ tilemask,
-            u8 *__restrict__ idx_out) {
-  __shared__ u16 hard[B2_MTF_TILE];
-  __shared__ u32 n_hard;
-  const B2SortTile tl = tiles[blockIdx.x];
-  const B2Job &job = jobs[tl.job];
+__global__ void __launch_bounds__(32 * MS_WARPS)
+k_mtf_seq(const B2SortTile *__restrict__ segs, u32 n_segs, const B2Job *__restrict__ jobs, const u8 *__restrict__ bwt,
+          const u32 *__restrict__ m16, const u32 *__restrict__ m256, u8 *__restrict__ idx_out) {
+  __shared__ u8 lists[MS_WARPS][256];
+  const u32 unit = blockIdx.x * MS_WARPS + warp_id();
+  if (unit >= n_segs) return;
+  const u32 l = lane_id(), lt = (1u << l) - 1u;
+  const B2SortTile sg = segs[unit];
+  const B2Job &job = jobs[sg.job];
   const u32 n = job.n, off = job.pos_off;
   const u8 *d = bwt + off;
-  const u32 *s16 = m16 + (size_t)(off >> 4) * 8;             // block-relative masks
+  const u32 *s16 = m16 + (size_t)(off >> 4) * 8;
   const u32 *s256 = m256 + (size_t)(off >> 8) * 8;
-  const u32 *tmk = tilemask + (size_t)job.tile0 * 8;
-  if (threadIdx.x == 0) n_hard = 0;
-  __syncthreads();
-  // ---- phase A: every thread, own 16-segment only ---------------------------------------------
-  for (int k = 0; k < MI_ITEMS; k++) {
-    const u32 i = tl.start + k * MI_THREADS + threadIdx.x;
-    if (i >= n) continue;
-    const u32 b = d[i];
-    if (i > 0 && d[i - 1] == b) { idx_out[off + i] = 0; continue; }
-    u32 seen[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    bool found = false;
-    for (i32 j = (i32)i - 1; j >= (i32)(i & ~15u); j--) {
-      const u32 x = d[j];
-      if (x == b) { found = true; break; }
-      seen_set(seen, x);
-    }
-    if (found) {
-      u32 idx = 0;
+  u8 *lst = lists[warp_id()];
+  const u32 p0 = sg.start, p1 = min(n, sg.start + B2_MTF_SEG);
+  const u32 n_used = job.n_used;
+  // ---- 1. list at p0 ---------------------------------------------------------------------------
+  u32 seen[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  u32 count = 0;
+  u32 q = p0;                                   // everything at positions >= q has been examined
+  while (count < n_used && q > 0) {
+    // a) bytes of the 16-segment that ends at q (those below q), most recent first
+    {
+      const u32 sbeg = (q - 1) & ~15u;
+      const u32 pos = q - 1 - l;
+      const bool valid = l < 16 && q >= 1 + l && pos >= sbeg;
+      const u32 x = valid ? d[pos] : (256u + l);
+      const bool fresh = valid && !seen_has(seen, x);
+      const u32 peers = __match_any_sync(0xffffffffu, x);
+      const bool first = fresh && ((peers & lt) == 0);         // most recent occurrence within these 16
+      const u32 bm = __ballot_sync(0xffffffffu, first);
+      if (first) lst[count + __popc(bm & lt)] = (u8)x;
+      count += __popc(bm);
+      u32 mine[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      if (first) seen_set(mine, x);
 #pragma unroll
-      for (int w = 0; w < 8; w++) idx += __popc(seen[w]);
-      idx_out[off + i] = (u8)idx;
-    } else {
-      hard[atomicAdd(&n_hard, 1u)] = (u16)(i - tl.start);
+      for (int w = 0; w < 8; w++) seen[w] |= __reduce_or_sync(0xffffffffu, mine[w]);
+      q = sbeg;
+    }
+    if (count >= n_used || q == 0) break;
+    // b) remaining 16-segments of the current 256-segment
+    bool located = false;
+    if (q & 255u) {
+      const i32 from = (i32)(q >> 4) - 1, lo = (i32)((q >> 8) << 4);
+      const i32 sidx = from - (i32)l;
+      bool has = false;
+      if (sidx >= lo) { u32 m[8]; load_mask(s16 + (size_t)sidx * 8, m); has = mask_has_new(m, seen); }
+      const u32 hm = __ballot_sync(0xffffffffu, has);
+      if (hm) { q = (u32)(from - (__ffs(hm) - 1) + 1) << 4; located = true; }
+      else q = (q >> 8) << 8;
+    }
+    // c) whole 256-segments, 32 per step
+    while (!located && q > 0) {
+      const i32 from = (i32)(q >> 8) - 1;
+      const i32 sidx = from - (i32)l;
+      bool has = false;
+      if (sidx >= 0) { u32 m[8]; load_mask(s256 + (size_t)sidx * 8, m); has = mask_has_new(m, seen); }
+      const u32 hm = __ballot_sync(0xffffffffu, has);
+      if (hm) {
+        const i32 hit = from - (__ffs(hm) - 1);                // nearest 256-segment with a new symbol
+        // its 16-segments, from the last one down
+        const i32 f16 = (hit << 4) + 15;
+        u32 m[8]; load_mask(s16 + (size_t)(f16 - (i32)(l & 15)) * 8, m);
+        const u32 h16 = __ballot_sync(0xffffffffu, l < 16 && mask_has_new(m, seen));
+        q = (u32)(f16 - (__ffs(h16) - 1) + 1) << 4;
+        located = true;
+      } else {
+        q = (from >= 31) ? (u32)(from - 31) << 8 : 0u;
+      }
     }
   }
-  __syncthreads();
-  // ---- phase B: one warp per remaining position, masks examined 32 at a time ------------------
-  const u32 nh = n_hard, l = lane_id();
-  for (u32 hI = warp_id(); hI < nh; hI += MI_THREADS / 32) {
-    const u32 i = tl.start + hard[hI];
-    const u32 b = d[i];
-    const u32 bw = b >> 5, bbit = 1u << (b & 31);
-    u32 seen[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    u32 mine[8];
-    // own 16-segment (b is known not to occur in it before i)
-    {
-      const u32 p = (i & ~15u) + l;
-      const bool take = l < 16 && p < i;
-#pragma unroll
-      for (int q = 0; q < 8; q++) mine[q] = 0;
-      if (take) seen_set(mine, d[p]);
-      warp_or_into(seen, mine, take);
+  __syncwarp();
+  // symbols never seen: increasing order behind the others
+  if (count < n_used) {
+    for (u32 base = 0; base < 256; base += 32) {
+      const u32 x = base + l;
+      const bool add = ((job.in_use[x >> 5] >> (x & 31)) & 1u) && !seen_has(seen, x);
+      const u32 bm = __ballot_sync(0xffffffffu, add);
+      if (add) lst[count + __popc(bm & lt)] = (u8)x;
+      count += __popc(bm);
     }
-    const i32 g16 = (i32)(i >> 4), g256 = (i32)(i >> 8), tile = (i32)(i >> 12);
-    i32 hit16 = warp_scan_masks(s16, g16 - 1, g256 << 4, bw, bbit, seen);              // own 256-segment
-    if (hit16 < 0) {
-      i32 hit256 = warp_scan_masks(s256, g256 - 1, tile << 4, bw, bbit, seen);         // own tile
-      if (hit256 < 0) {
-        for (i32 t = tile - 1; t >= 0 && hit256 < 0; t -= 32) {                        // earlier tiles
-          const i32 ht = warp_scan_masks(tmk, t, 0, bw, bbit, seen);
-          if (ht >= 0) { hit256 = warp_scan_masks(s256, (ht << 4) + 15, ht << 4, bw, bbit, seen); break; }
-        }
+  }
+  for (u32 i = count + l; i < 256; i += 32) lst[i] = 0;          // unused places (never matched: see `live`)
+  __syncwarp();
+  // ---- 2. the segment, in order ------------------------------------------------------------------
+  u32 v0 = *reinterpret_cast<const u32 *>(lst + 8 * l), v1 = *reinterpret_cast<const u32 *>(lst + 8 * l + 4);
+  // places >= n_used hold padding zeros that must not match symbol 0
+  u32 live0 = 0, live1 = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    if (8 * l + k < n_used) live0 |= 0xFFu << (8 * k);
+    if (8 * l + 4 + k < n_used) live1 |= 0xFFu << (8 * k);
+  }
+  u32 prevb = p0 > 0 ? d[p0 - 1] : 256u;
+  for (u32 b0 = p0; b0 < p1; b0 += 32) {
+    const u32 pi = b0 + l;
+    const u32 mybyte = pi < p1 ? d[pi] : 0u;
+    u32 myidx = 0;
+    // positions whose byte differs from the one before them; the others continue a run (index 0)
+    u32 before = __shfl_up_sync(0xffffffffu, mybyte, 1);
+    if (l == 0) before = prevb;
+    u32 todo = __ballot_sync(0xffffffffu, pi < p1 && mybyte != before);
+    const u32 steps = min(32u, p1 - b0);
+    prevb = __shfl_sync(0xffffffffu, mybyte, steps - 1);
+    while (todo) {
+      const u32 k = (u32)(__ffs(todo) - 1);
+      todo &= todo - 1;
+      const u32 b = __shfl_sync(0xffffffffu, mybyte, k);
+      const u32 sp = b * 0x01010101u;
+      const u32 e0 = __vcmpeq4(v0, sp) & live0, e1 = __vcmpeq4(v1, sp) & live1;
+      const u32 hm = __ballot_sync(0xffffffffu, (e0 | e1) != 0);
+      const u32 h = (u32)(__ffs(hm) - 1);
+      const u32 kk_mine = e0 ? ((u32)(__ffs(e0) - 1) >> 3) : (4u + ((u32)(__ffs(e1) - 1) >> 3));
+      const u32 kk = __shfl_sync(0xffffffffu, kk_mine, h);
+      if (l == k) myidx = 8 * h + kk;
+      // move to front: places below the index shift up by one, b goes to place 0
+      const u32 top = v1 >> 24;
+      u32 carry = __shfl_up_sync(0xffffffffu, top, 1);
+      if (l == 0) carry = b;
+      const u32 s0 = (v0 << 8) | carry, s1 = (v1 << 8) | (v0 >> 24);
+      if (l < h) { v0 = s0; v1 = s1; }
+      else if (l == h) {
+        // bytes 0 .. kk take the shifted value, bytes above kk stay
+        const u32 m0 = kk >= 3 ? 0xFFFFFFFFu : ((1u << (8 * (kk + 1))) - 1u);
+        const u32 m1 = kk < 4 ? 0u : (kk >= 7 ? 0xFFFFFFFFu : ((1u << (8 * (kk - 3))) - 1u));
+        v0 = (s0 & m0) | (v0 & ~m0);
+        v1 = (s1 & m1) | (v1 & ~m1);
       }
-      if (hit256 >= 0) hit16 = warp_scan_masks(s16, (hit256 << 4) + 15, hit256 << 4, bw, bbit, seen);
     }
-    bool found = false;
-    if (hit16 >= 0) {
-      // bytes of the hit segment from its end downwards: lane l looks at byte 15 - l
-      const u32 p = ((u32)hit16 << 4) + 15 - l;
-      const u32 x = l < 16 ? d[p] : 256u;
-      const u32 mt = __ballot_sync(0xffffffffu, x == b);
-      const u32 first = (u32)(__ffs(mt) - 1);
-      const bool take = l < first;
-#pragma unroll
-      for (int q = 0; q < 8; q++) mine[q] = 0;
-      if (take) seen_set(mine, x);
-      warp_or_into(seen, mine, take);
-      found = true;
-    }
-    u32 idx = 0;
-    if (found) {
-#pragma unroll
-      for (int w = 0; w < 8; w++) idx += __popc(seen[w]);
-    } else {
-      // rank of b among used bytes + seen symbols larger than b
-      const u32 bb = b & 31;
-#pragma unroll
-      for (int w = 0; w < 8; w++) {
-        u32 below = (w < (int)bw) ? 0xFFFFFFFFu : ((w == (int)bw) ? ((1u << bb) - 1u) : 0u);
-        u32 above = (w > (int)bw) ? 0xFFFFFFFFu : ((w == (int)bw) ? (bb == 31 ? 0u : (0xFFFFFFFFu << (bb + 1))) : 0u);
-        idx += __popc(job.in_use[w] & below) + __popc(seen[w] & above);
-      }
-    }
-    if (l == 0) idx_out[off + i] = (u8)idx;
+    if (pi < p1) idx_out[off + pi] = (u8)myidx;
   }
 }
 
@@ -274,10 +312,11 @@ k_rle2(B2Job *jobs, const u8 *__restrict__ idx_in, u16 *__restrict__ mtf) {
 }
 
 int b2k_mtf(cudaStream_t st, B2Job *d_jobs, u32 n_jobs, const B2SortTile *d_tiles, u32 n_tiles,
-            const u8 *d_bwt, u32 *d_m16, u32 *d_m256, u32 *d_tilemask, u8 *d_idx, u16 *d_mtf) {
+            const B2SortTile *d_segs, u32 n_segs, const u8 *d_bwt, u32 *d_m16, u32 *d_m256, u32 *d_tilemask, u8 *d_idx,
+            u16 *d_mtf) {
   if (n_tiles) {
     k_mtf_masks<<<n_tiles, MI_THREADS, 0, st>>>(d_tiles, d_jobs, d_bwt, d_m16, d_m256, d_tilemask);
-    k_mtf_index<<<n_tiles, MI_THREADS, 0, st>>>(d_tiles, d_jobs, d_bwt, d_m16, d_m256, d_tilemask, d_idx);
+    k_mtf_seq<<<(n_segs + MS_WARPS - 1) / MS_WARPS, 32 * MS_WARPS, 0, st>>>(d_segs, n_segs, d_jobs, d_bwt, d_m16, d_m256, d_idx);
   }
   if (n_jobs) k_rle2<<<n_jobs, R2_THREADS, 0, st>>>(d_jobs, d_idx, d_mtf);
   B2_CUDA_CHECK(cudaGetLastError());
