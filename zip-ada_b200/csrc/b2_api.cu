@@ -78,7 +78,8 @@ struct Workspace {
   DevBuf<u32> d_hist, d_digit_base;
   DevBuf<i32> d_tile_head, d_carry;
   DevBuf<u32> d_unsorted;
-  DevBuf<u16> d_mtf;
+  DevBuf<u16> d_mtf, d_ghist;
+  DevBuf<u8> d_gdist;
   DevBuf<u32> d_rank3, d_rank4;
   DevBuf<u8> d_sel, d_selprev, d_selpos, d_lens;
   DevBuf<u32> d_ehist, d_leaves, d_estat, d_selcost;
@@ -98,7 +99,7 @@ struct Workspace {
     d_scalars.release(); d_jobs.release(); d_text.release(); d_bwt.release(); d_idx.release(); d_m16.release();
     d_m256.release(); d_tilemask.release(); d_keysA.release(); d_keysB.release(); d_valsA.release(); d_valsB.release();
     d_rank.release(); d_grp.release(); d_slotA.release(); d_slotB.release(); d_sa.release(); d_tile_cnt.release(); d_tiles.release(); d_mtiles.release(); d_msegs.release(); d_sj.release(); d_hist.release();
-    d_digit_base.release(); d_tile_head.release(); d_carry.release(); d_unsorted.release(); d_mtf.release();
+    d_digit_base.release(); d_tile_head.release(); d_carry.release(); d_unsorted.release(); d_mtf.release(); d_ghist.release(); d_gdist.release();
     d_rank3.release(); d_rank4.release(); d_sel.release(); d_selprev.release(); d_selpos.release(); d_lens.release();
     d_ehist.release(); d_leaves.release(); d_estat.release(); d_selcost.release(); d_gcost.release(); d_cost.release();
     d_low.release(); d_bits.release(); d_items.release();
@@ -191,8 +192,8 @@ int ensure_batch_workspace(Workspace *w, size_t T, size_t J) {
   B2_TRY(w->d_hist.ensure(max_tiles * 256)); B2_TRY(w->d_digit_base.ensure(J * 256));
   B2_TRY(w->d_tile_head.ensure(max_tiles)); B2_TRY(w->d_carry.ensure(max_tiles));
   B2_TRY(w->d_unsorted.ensure(J));
-  B2_TRY(w->d_mtf.ensure(T + 16 * J + 64));
-  B2_TRY(w->d_rank3.ensure(GT)); B2_TRY(w->d_rank4.ensure(GT));
+  B2_TRY(w->d_mtf.ensure(T + 16 * J + 64)); B2_TRY(w->d_ghist.ensure(T + 16 * J + 64));
+  B2_TRY(w->d_rank3.ensure(GT)); B2_TRY(w->d_rank4.ensure(GT)); B2_TRY(w->d_gdist.ensure(GT));
   B2_TRY(w->d_sel.ensure(GT * B2_N_TRIPLES + 64)); B2_TRY(w->d_selprev.ensure(GT * B2_N_TRIPLES + 64));
   B2_TRY(w->d_selpos.ensure(GT));
   B2_TRY(w->d_gcost.ensure(GT * B2_N_TRIPLES + 64));
@@ -286,9 +287,14 @@ int run_batch(b2_encoder *e, Workspace *w, const u8 *d_in, std::vector<B2Job> &j
                    w->d_m256.p, w->d_tilemask.p, w->d_idx.p, w->d_mtf.p));
     w->launches += 3;
   }
+  // exact group counts: the ranking heap sorts size their shared memory by the largest block
+  B2_CUDA_CHECK(cudaMemcpyAsync(w->batch_jobs.data(), w->d_jobs.p, J * sizeof(B2Job), cudaMemcpyDeviceToHost, st));
+  B2_CUDA_CHECK(cudaStreamSynchronize(st));
+  max_g = 1;
+  for (u32 j = 0; j < J; j++) max_g = std::max(max_g, w->batch_jobs[j].n_groups);
   {
     StageTimer tm(e, st, w->ev, &w->stage_ms[4]);
-    B2_TRY(b2k_entropy(st, w->d_jobs.p, J, max_g, gpos, w->d_mtf.p, w->d_rank3.p, w->d_rank4.p, w->d_sel.p,
+    B2_TRY(b2k_entropy(st, w->d_jobs.p, J, max_g, gpos, w->d_mtf.p, w->d_ghist.p, w->d_gdist.p, w->d_rank3.p, w->d_rank4.p, w->d_sel.p,
                        w->d_selprev.p, w->d_gcost.p, w->d_ehist.p, w->d_leaves.p, w->d_lens.p, w->d_estat.p, w->d_selcost.p,
                        w->d_cost.p, w->d_low.p, e->level, &w->launches));
   }

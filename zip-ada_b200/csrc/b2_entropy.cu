@@ -47,6 +47,32 @@ k_group_keys(const B2Job *__restrict__ jobs, const u16 *__restrict__ mtf, u32 *_
 }
 
 // ---------------------------------------------------------------------------------------------
+// Sparse histogram of every group of 50 symbols, built once per block and shared by the 20 triples
+// and all their iterations: entries (count << 9 | symbol) in order of first
+// appearance, at the group's own 50 slots; gdist = number of entries.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_group_hist(const B2Job *__restrict__ jobs, const u16 *__restrict__ mtf, u16 *__restrict__ ghist, u8 *__restrict__ gdist) {
+  const B2Job &job = jobs[blockIdx.x];
+  const u32 M = job.n_mtf, G = job.n_groups;
+  const u16 *m = mtf + job.mtf_off;
+  u16 *gh = ghist + job.mtf_off;
+  for (u32 g = threadIdx.x; g < G; g += blockDim.x) {
+    const u32 s0 = g * B2_GROUP_SIZE, s1 = min(s0 + B2_GROUP_SIZE, M);
+    u16 *e = gh + s0;
+    u32 D = 0;
+    for (u32 s = s0; s < s1; s++) {
+      const u32 sym = m[s];
+      u32 k = 0;
+      for (; k < D; k++) if ((e[k] & 511u) == sym) break;
+      if (k < D) e[k] = (u16)(e[k] + 512u);
+      else { e[D] = (u16)(512u | sym); D++; }
+    }
+    gdist[job.grp_off + g] = (u8)D;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Ranking_Sort (:564-568, :619) = GNAT Generic_Constrained_Array_Sort: in-place heap sort,
 // Floyd's variant (sift the hole to a leaf, then climb), compare on key only.  Serial by nature
 // (its tie order is the point); one thread per array, array staged in shared memory.
@@ -97,6 +123,8 @@ k_rank_sort(const B2Job *__restrict__ jobs, u32 *__restrict__ rank3, u32 *__rest
 struct EntArgs {
   const B2Job *jobs;
   const u16 *mtf;
+  const u16 *ghist;                     // sparse group histograms (same layout as mtf)
+  const u8 *gdist;                      // [total_groups] entries per group
   const u32 *rank3, *rank4;
   u8 *sel, *selprev;                    // [triple][total_groups]
   unsigned long long *gcost;            // [triple][total_groups]
@@ -162,19 +190,18 @@ k_ent_hist(EntArgs a) {
   const u32 tid = threadIdx.x;
   for (u32 i = tid; i < (u32)ec * HSTRIDE; i += 256) (&h[0][0])[i] = hg[i];
   __syncthreads();
+  const u16 *gh = a.ghist + job.mtf_off;
+  const u8 *gd = a.gdist + job.grp_off;
   for (u32 g = tid; g < G; g += 256) {
     const u32 c = sel[g], o = selprev[g];
     if (c == o) continue;
-    const u32 s0 = g * B2_GROUP_SIZE, s1 = min(s0 + B2_GROUP_SIZE, M);
-    u32 n0 = 0, n1 = 0;
-    for (u32 s = s0; s < s1; s++) {
-      const u32 sym = m[s];
-      if (sym == 0) n0++;
-      else if (sym == 1) n1++;
-      else { atomicAdd(&h[c - 1][sym], 1u); if (o) atomicSub(&h[o - 1][sym], 1u); }
+    const u16 *e = gh + g * B2_GROUP_SIZE;
+    const u32 D = gd[g];
+    for (u32 k = 0; k < D; k++) {
+      const u32 v = e[k], sym = v & 511u, cn = v >> 9;
+      atomicAdd(&h[c - 1][sym], cn);
+      if (o) atomicSub(&h[o - 1][sym], cn);
     }
-    if (n0) { atomicAdd(&h[c - 1][0], n0); if (o) atomicSub(&h[o - 1][0], n0); }
-    if (n1) { atomicAdd(&h[c - 1][1], n1); if (o) atomicSub(&h[o - 1][1], n1); }
     selprev[g] = (u8)c;
   }
   __syncthreads();
@@ -404,10 +431,13 @@ k_ent_cost(EntArgs a) {
   }
   __syncthreads();
   unsigned long long *gcost = a.gcost + (size_t)t * a.total_groups + job.grp_off;
+  const u16 *gh = a.ghist + job.mtf_off;
+  const u8 *gd = a.gdist + job.grp_off;
   for (u32 g = threadIdx.x; g < G; g += 256) {
-    const u32 s0 = g * B2_GROUP_SIZE, s1 = min(s0 + B2_GROUP_SIZE, M);
+    const u16 *e = gh + g * B2_GROUP_SIZE;
+    const u32 D = gd[g];
     unsigned long long acc = 0;
-    for (u32 s = s0; s < s1; s++) acc += lenpack[m[s]];
+    for (u32 k = 0; k < D; k++) { const u32 v = e[k]; acc += lenpack[v & 511u] * (unsigned long long)(v >> 9); }
     gcost[g] = acc;
   }
 }
@@ -429,36 +459,36 @@ k_ent_sweep(EntArgs a) {
   u8 *sel = a.sel + base;
   SelList L; L.init();
   u32 def = 0;
-  // 8 groups per step, loaded one step ahead (register double buffer) and prefetched into L2 further ahead
-  unsigned long long nx[8];
-  u32 ns0 = 0, ns1 = 0;
-  auto load8 = [&](u32 g0) {
+  // 16 groups per step, loaded one step ahead (register double buffer) and prefetched into L2 further ahead
+  unsigned long long nx[16];
+  u32 ns[4] = {0, 0, 0, 0};
+  auto load16g = [&](u32 g0) {
 #pragma unroll
-    for (int k = 0; k < 8; k++) nx[k] = 0;
-    ns0 = ns1 = 0;
+    for (int k = 0; k < 16; k++) nx[k] = 0;
+    ns[0] = ns[1] = ns[2] = ns[3] = 0;
     if (active && g0 < G) {
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
+      for (int k = 0; k < 8; k++) {
         const ulonglong2 x = *reinterpret_cast<const ulonglong2 *>(gc + g0 + 2 * k);
         nx[2 * k] = x.x; nx[2 * k + 1] = x.y;
       }
-      const uint2 sv = *reinterpret_cast<const uint2 *>(sel + g0);
-      ns0 = sv.x; ns1 = sv.y;
-      if (g0 + 64 < G) asm volatile("prefetch.global.L2 [%0];" ::"l"(gc + g0 + 64));
+      const uint4 sv = *reinterpret_cast<const uint4 *>(sel + g0);
+      ns[0] = sv.x; ns[1] = sv.y; ns[2] = sv.z; ns[3] = sv.w;
+      if (g0 + 128 < G) asm volatile("prefetch.global.L2 [%0];" ::"l"(gc + g0 + 128));
     }
   };
-  load8(0);
-  for (u32 g0 = 0; g0 < G; g0 += 8) {
-    unsigned long long c8[8];
+  load16g(0);
+  for (u32 g0 = 0; g0 < G; g0 += 16) {
+    unsigned long long c16[16];
 #pragma unroll
-    for (int k = 0; k < 8; k++) c8[k] = nx[k];
-    const u32 s0 = ns0, s1 = ns1;
-    load8(g0 + 8);
+    for (int k = 0; k < 16; k++) c16[k] = nx[k];
+    const u32 s4[4] = {ns[0], ns[1], ns[2], ns[3]};
+    load16g(g0 + 16);
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
+    for (int k = 0; k < 16; k++) {
       if (g0 + k < G) {
-        const unsigned long long ck = c8[k];
-        const u32 clk = ((k < 4 ? s0 : s1) >> (8 * (k & 3))) & 255u;
+        const unsigned long long ck = c16[k];
+        const u32 clk = (s4[k >> 2] >> (8 * (k & 3))) & 255u;
         // key = (cost << 6) | (coder0 << 3) | place: the minimum is the cheapest coder, lowest coder
         // on ties (strict "<" scanning cl upward, :691-695), and carries its place along
         u32 key = 0xFFFFFFFFu;
@@ -593,24 +623,26 @@ __global__ void k_choose(B2Job *jobs, u32 n_jobs, const u32 *__restrict__ cost_a
 }
 
 int b2k_entropy(cudaStream_t st, B2Job *d_jobs, u32 n_jobs, u32 max_groups_per_job, u32 total_groups,
-                const u16 *d_mtf, u32 *d_rank3, u32 *d_rank4, u8 *d_sel, u8 *d_selprev, unsigned long long *d_gcost,
+                const u16 *d_mtf, u16 *d_ghist, u8 *d_gdist, u32 *d_rank3, u32 *d_rank4, u8 *d_sel, u8 *d_selprev,
+                unsigned long long *d_gcost,
                 u32 *d_hist, u32 *d_leaves, u8 *d_lens, u32 *d_stat, u32 *d_selcost, u32 *d_cost, u32 *d_low,
                 int level, u64 *launches) {
   B2_CUDA_CHECK(cudaFuncSetAttribute(k_rank_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, 18064 * 4));
   if (n_jobs == 0) return 0;
   const int n_triples = level == 9 ? 20 : 5;
   k_group_keys<<<n_jobs, 256, 0, st>>>(d_jobs, d_mtf, d_rank3, d_rank4);
+  k_group_hist<<<n_jobs, 256, 0, st>>>(d_jobs, d_mtf, d_ghist, d_gdist);
   size_t sort_smem = ((size_t)max_groups_per_job + 2) * 4;
   k_rank_sort<<<n_jobs * 2, 32, sort_smem, st>>>(d_jobs, d_rank3, d_rank4);
   EntArgs a;
-  a.jobs = d_jobs; a.mtf = d_mtf; a.rank3 = d_rank3; a.rank4 = d_rank4; a.sel = d_sel; a.selprev = d_selprev;
+  a.jobs = d_jobs; a.mtf = d_mtf; a.ghist = d_ghist; a.gdist = d_gdist; a.rank3 = d_rank3; a.rank4 = d_rank4; a.sel = d_sel; a.selprev = d_selprev;
   a.gcost = d_gcost; a.hist = d_hist; a.leaves = d_leaves; a.lens = d_lens; a.stat = d_stat; a.selcost = d_selcost;
   a.cost_all = d_cost; a.low_all = d_low; a.total_groups = total_groups; a.level = level; a.n_triples = n_triples;
   a.n_jobs = n_jobs;
   const dim3 grid(n_triples, n_jobs);
   const u32 nq = n_jobs * B2_N_TRIPLES * B2_MAX_CODERS;
   k_ent_init<<<grid, 256, 0, st>>>(a);
-  *launches += 3;
+  *launches += 4;
   for (int it = 0; it <= 10; it++) {
     // iterations 1..10 (:793-802); round 10 is the extra Define_Descriptors for triples still moving (:803-807)
     k_ent_hist<<<grid, 256, 0, st>>>(a);
