@@ -83,12 +83,18 @@ k_cut_s1(const u32 *__restrict__ lastchg, u64 ntiles, u64 *__restrict__ carry_r)
   for (u64 t = a; t < e; t++) { carry_r[t] = run; u32 l = lastchg[t]; if (l) run = t * CT_TILE + l; }
 }
 
-// commits with the runs of the stream: g(p) = size of the piece that ends at p-1 if a piece starts at p
-__device__ __forceinline__ u32 gcommit(u64 p, bool chg, u64 r_prev, u64 r_cur) {
-  if (p == 0) return 0;
-  if (chg) { const u64 Lr = p - r_prev; return enc_size((u32)((Lr - 1) % 259) + 1); }
-  return ((p - r_cur) % 259 == 0) ? 5u : 0u;
+// commits with the runs of the stream: g(p) = size of the piece that ends at p-1 if a piece starts at p.
+// `m` = (p-1 - run start of p-1) mod 259, the index of byte p-1 inside its piece, carried along so that
+// no division is needed per byte; returns g(p) and advances m to the index of byte p.
+__device__ __forceinline__ u32 gstep(bool first_of_stream, bool chg, u32 &m) {
+  u32 g;
+  if (first_of_stream) { m = 0; return 0; }
+  if (chg) { g = enc_size(m + 1); m = 0; }
+  else if (m == 258) { g = 5; m = 0; }                     // forced break at 259 (:1199)
+  else { g = 0; m++; }
+  return g;
 }
+__device__ __forceinline__ u32 mod259(u64 d) { return (d >> 32) ? (u32)(d % 259ull) : ((u32)d % 259u); }
 
 __global__ void __launch_bounds__(CT_THREADS)
 k_cut_b(const u8 *__restrict__ in, u64 n, const u64 *__restrict__ carry_r, u32 *__restrict__ tsum) {
@@ -113,19 +119,15 @@ k_cut_b(const u8 *__restrict__ in, u64 n, const u64 *__restrict__ carry_r, u32 *
   i32 tot;
   const i32 rin = block_excl_max(lc, -1, sm_i, &tot);
   const u64 cr = carry_r[blockIdx.x];
-  u64 r = rin >= 0 ? t0 + (u64)rin : (cr ? cr - 1 : 0);     // run start of byte base-1 (unused when base == 0)
+  const u64 r = rin >= 0 ? t0 + (u64)rin : (cr ? cr - 1 : 0);     // run start of byte base-1 (unused when base == 0)
   u32 local = 0;
   {
+    u32 m = (base > 0 && base <= n) ? mod259(base - 1 - r) : 0;   // index of byte base-1 inside its piece
     u8 pv = prev;
 #pragma unroll
     for (int k = 0; k < 16; k++) {
       const u64 p = base + k;
-      if (p < n) {
-        const bool chg = (p == 0 || b[k] != pv);
-        const u64 rp = r;
-        if (chg) r = p;
-        local += gcommit(p, chg, rp, r);
-      }
+      if (p < n) local += gstep(p == 0, b[k] != pv, m);
       pv = b[k];
     }
   }
@@ -200,32 +202,30 @@ __device__ u64 warp_tile(const u8 *__restrict__ in, u64 n, const u64 *__restrict
   const u64 cr = carry_r[t];
   const u64 r0 = rin >= 0 ? t0 + (u64)rin : (cr ? cr - 1 : 0);
   // my sum
+  const u32 m0 = (base > 0 && base <= n) ? mod259(base - 1 - r0) : 0;   // index of byte base-1 inside its piece
   u32 local = 0;
   {
-    u64 rr = r0;
+    u32 m = m0;
     u8 pv = prev;
 #pragma unroll 8
     for (int k = 0; k < 64; k++) {
       const u64 p = base + k;
       const u8 c = (u8)(w[k >> 2] >> (8 * (k & 3)));
-      if (p < n) { const bool chg = (p == 0 || c != pv); const u64 rp = rr; if (chg) rr = p; local += gcommit(p, chg, rp, rr); }
+      if (p < n) local += gstep(p == 0, c != pv, m);
       pv = c;
     }
   }
   const u32 incl = warp_incl_add(local);
   u64 run = excl + (incl - local);
   {
-    u64 r = r0;
+    u32 m = m0;
     u8 pv = prev;
 #pragma unroll 8
     for (int k = 0; k < 64; k++) {
       const u64 p = base + k;
       const u8 c = (u8)(w[k >> 2] >> (8 * (k & 3)));
       if (p < n) {
-        const bool chg = (p == 0 || c != pv);
-        const u64 rp = r;
-        if (chg) r = p;
-        run += gcommit(p, chg, rp, r);
+        run += gstep(p == 0, c != pv, m);
         if (mode == 0 && p == q) res = run - excl;
         if (mode == 1 && res == ~0ull && run >= target) res = p;
       }

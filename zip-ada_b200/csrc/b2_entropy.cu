@@ -127,7 +127,8 @@ struct EntArgs {
   const u8 *gdist;                      // [total_groups] entries per group
   const u32 *rank3, *rank4;
   u8 *sel, *selprev;                    // [triple][total_groups]
-  unsigned long long *gcost;            // [triple][total_groups]
+  u32 *gpack;                           // [triple][total_groups] cheapest cost (10 bits) + six 3-bit excesses over it
+  u16 *gselcost;                        // [triple][total_groups] exact bits of the group under its current coder
   u32 *hist;                            // [p][6][HSTRIDE] raw cluster histograms
   u32 *leaves;                          // interleaved: [(q / 32)][HSTRIDE][q % 32], q = p * 6 + coder
   u8 *lens;                             // [p][6][B2_MAX_ALPHA]
@@ -430,7 +431,9 @@ k_ent_cost(EntArgs a) {
     lenpack[s] = v;
   }
   __syncthreads();
-  unsigned long long *gcost = a.gcost + (size_t)t * a.total_groups + job.grp_off;
+  u32 *gpack = a.gpack + (size_t)t * a.total_groups + job.grp_off;
+  u16 *gselcost = a.gselcost + (size_t)t * a.total_groups + job.grp_off;
+  const u8 *sel = a.sel + (size_t)t * a.total_groups + job.grp_off;
   const u16 *gh = a.ghist + job.mtf_off;
   const u8 *gd = a.gdist + job.grp_off;
   for (u32 g = threadIdx.x; g < G; g += 256) {
@@ -438,7 +441,20 @@ k_ent_cost(EntArgs a) {
     const u32 D = gd[g];
     unsigned long long acc = 0;
     for (u32 k = 0; k < D; k++) { const u32 v = e[k]; acc += lenpack[v & 511u] * (unsigned long long)(v >> 9); }
-    gcost[g] = acc;
+    // Only cost differences matter to the reclassification, and a coder 7 or more bits above the
+    // cheapest can never win (places cost 1..6, :683-695): keep min + six 3-bit clipped excesses.
+    u32 c[6], mn = 0xFFFFFFFFu;
+#pragma unroll
+    for (int cl = 0; cl < 6; cl++) { c[cl] = (u32)((acc >> (10 * cl)) & 1023u); if (cl < ec) mn = min(mn, c[cl]); }
+    u32 pk = mn;
+#pragma unroll
+    for (int cl = 0; cl < 6; cl++) if (cl < ec) pk |= min(c[cl] - mn, 7u) << (10 + 3 * cl);
+    gpack[g] = pk;
+    const u32 sc = sel[g] - 1;
+    u32 mine = c[0];
+#pragma unroll
+    for (int cl = 1; cl < 6; cl++) mine = (sc == (u32)cl) ? c[cl] : mine;
+    gselcost[g] = (u16)mine;
   }
 }
 
@@ -455,12 +471,12 @@ k_ent_sweep(EntArgs a) {
   int max_len, sw, ec;
   b2_triple(a.level, (int)(t < (u32)a.n_triples ? t : 0), max_len, sw, ec);
   const size_t base = (size_t)(active ? t : 0) * a.total_groups + job.grp_off;
-  const unsigned long long *gc = a.gcost + base;
+  const u32 *gc = a.gpack + base;
   u8 *sel = a.sel + base;
   SelList L; L.init();
   u32 def = 0;
   // 16 groups per step, loaded one step ahead (register double buffer) and prefetched into L2 further ahead
-  unsigned long long nx[16];
+  u32 nx[16];
   u32 ns[4] = {0, 0, 0, 0};
   auto load16g = [&](u32 g0) {
 #pragma unroll
@@ -468,18 +484,18 @@ k_ent_sweep(EntArgs a) {
     ns[0] = ns[1] = ns[2] = ns[3] = 0;
     if (active && g0 < G) {
 #pragma unroll
-      for (int k = 0; k < 8; k++) {
-        const ulonglong2 x = *reinterpret_cast<const ulonglong2 *>(gc + g0 + 2 * k);
-        nx[2 * k] = x.x; nx[2 * k + 1] = x.y;
+      for (int k = 0; k < 4; k++) {
+        const uint4 x = *reinterpret_cast<const uint4 *>(gc + g0 + 4 * k);
+        nx[4 * k] = x.x; nx[4 * k + 1] = x.y; nx[4 * k + 2] = x.z; nx[4 * k + 3] = x.w;
       }
       const uint4 sv = *reinterpret_cast<const uint4 *>(sel + g0);
       ns[0] = sv.x; ns[1] = sv.y; ns[2] = sv.z; ns[3] = sv.w;
-      if (g0 + 128 < G) asm volatile("prefetch.global.L2 [%0];" ::"l"(gc + g0 + 128));
+      if (g0 + 256 < G) asm volatile("prefetch.global.L2 [%0];" ::"l"(gc + g0 + 256));
     }
   };
   load16g(0);
   for (u32 g0 = 0; g0 < G; g0 += 16) {
-    unsigned long long c16[16];
+    u32 c16[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) c16[k] = nx[k];
     const u32 s4[4] = {ns[0], ns[1], ns[2], ns[3]};
@@ -487,7 +503,7 @@ k_ent_sweep(EntArgs a) {
 #pragma unroll
     for (int k = 0; k < 16; k++) {
       if (g0 + k < G) {
-        const unsigned long long ck = c16[k];
+        const u32 ck = c16[k] >> 10;
         const u32 clk = (s4[k >> 2] >> (8 * (k & 3))) & 255u;
         // key = (cost << 6) | (coder0 << 3) | place: the minimum is the cheapest coder, lowest coder
         // on ties (strict "<" scanning cl upward, :691-695), and carries its place along
@@ -495,7 +511,7 @@ k_ent_sweep(EntArgs a) {
 #pragma unroll
         for (int cl = 0; cl < 6; cl++) {
           if (cl < ec) {
-            const u32 cost = (u32)((ck >> (10 * cl)) & 1023u) + L.pos[cl];
+            const u32 cost = ((ck >> (3 * cl)) & 7u) + L.pos[cl];
             key = min(key, (cost << 6) | ((u32)cl << 3) | L.pos[cl]);
           }
         }
@@ -552,7 +568,7 @@ k_ent_final(EntArgs a) {
   b2_triple(a.level, t, max_len, sw, ec);
   const u8 *lens = a.lens + (size_t)p * B2_MAX_CODERS * B2_MAX_ALPHA;
   const u8 *sel = a.sel + (size_t)t * a.total_groups + job.grp_off;
-  const unsigned long long *gcost = a.gcost + (size_t)t * a.total_groups + job.grp_off;
+  const u16 *gselcost = a.gselcost + (size_t)t * a.total_groups + job.grp_off;
   const u32 tid = threadIdx.x;
   if (tid < 8) stat[tid] = 0;
   __syncthreads();
@@ -560,7 +576,7 @@ k_ent_final(EntArgs a) {
   for (u32 g = tid; g < G; g += 256) {
     const u32 c = sel[g];
     atomicAdd(&stat[c], 1u);
-    part += (u32)((gcost[g] >> (10 * (c - 1))) & 1023u);           // data bits (:873-881)
+    part += gselcost[g];                                            // data bits (:873-881)
   }
   for (int i = tid; i < ec * A; i += 256) {                         // code length tables (:839-865)
     const int c = i / A, s = i % A;
@@ -624,7 +640,7 @@ __global__ void k_choose(B2Job *jobs, u32 n_jobs, const u32 *__restrict__ cost_a
 
 int b2k_entropy(cudaStream_t st, B2Job *d_jobs, u32 n_jobs, u32 max_groups_per_job, u32 total_groups,
                 const u16 *d_mtf, u16 *d_ghist, u8 *d_gdist, u32 *d_rank3, u32 *d_rank4, u8 *d_sel, u8 *d_selprev,
-                unsigned long long *d_gcost,
+                u32 *d_gpack, u16 *d_gselcost,
                 u32 *d_hist, u32 *d_leaves, u8 *d_lens, u32 *d_stat, u32 *d_selcost, u32 *d_cost, u32 *d_low,
                 int level, u64 *launches) {
   B2_CUDA_CHECK(cudaFuncSetAttribute(k_rank_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, 18064 * 4));
@@ -636,7 +652,7 @@ int b2k_entropy(cudaStream_t st, B2Job *d_jobs, u32 n_jobs, u32 max_groups_per_j
   k_rank_sort<<<n_jobs * 2, 32, sort_smem, st>>>(d_jobs, d_rank3, d_rank4);
   EntArgs a;
   a.jobs = d_jobs; a.mtf = d_mtf; a.ghist = d_ghist; a.gdist = d_gdist; a.rank3 = d_rank3; a.rank4 = d_rank4; a.sel = d_sel; a.selprev = d_selprev;
-  a.gcost = d_gcost; a.hist = d_hist; a.leaves = d_leaves; a.lens = d_lens; a.stat = d_stat; a.selcost = d_selcost;
+  a.gpack = d_gpack; a.gselcost = d_gselcost; a.hist = d_hist; a.leaves = d_leaves; a.lens = d_lens; a.stat = d_stat; a.selcost = d_selcost;
   a.cost_all = d_cost; a.low_all = d_low; a.total_groups = total_groups; a.level = level; a.n_triples = n_triples;
   a.n_jobs = n_jobs;
   const dim3 grid(n_triples, n_jobs);
