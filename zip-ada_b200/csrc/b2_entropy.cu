@@ -53,22 +53,52 @@ k_group_keys(const B2Job *__restrict__ jobs, const u16 *__restrict__ mtf, u32 *_
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_group_hist(const B2Job *__restrict__ jobs, const u16 *__restrict__ mtf, u16 *__restrict__ ghist, u8 *__restrict__ gdist) {
+  // one warp per group: symbols 0..31 of the group in the lanes, then symbols 32..49; equal symbols
+  // are found with match_any, the second part is merged into the entries of the first
   const B2Job &job = jobs[blockIdx.x];
   const u32 M = job.n_mtf, G = job.n_groups;
   const u16 *m = mtf + job.mtf_off;
   u16 *gh = ghist + job.mtf_off;
-  for (u32 g = threadIdx.x; g < G; g += blockDim.x) {
+  const u32 l = lane_id(), lt = (1u << l) - 1u;
+  for (u32 g = warp_id(); g < G; g += 8) {
     const u32 s0 = g * B2_GROUP_SIZE, s1 = min(s0 + B2_GROUP_SIZE, M);
-    u16 *e = gh + s0;
-    u32 D = 0;
-    for (u32 s = s0; s < s1; s++) {
-      const u32 sym = m[s];
-      u32 k = 0;
-      for (; k < D; k++) if ((e[k] & 511u) == sym) break;
-      if (k < D) e[k] = (u16)(e[k] + 512u);
-      else { e[D] = (u16)(512u | sym); D++; }
+    const u32 nA = min(32u, s1 - s0), nB = (s1 - s0) - nA;
+    // part A
+    const u32 symA = l < nA ? m[s0 + l] : (0x10000u + l);
+    const u32 peersA = __match_any_sync(0xffffffffu, symA);
+    const bool leadA = l < nA && (peersA & lt) == 0;
+    const u32 bmA = __ballot_sync(0xffffffffu, leadA);
+    const u32 DA = __popc(bmA);
+    const u32 slotA = __popc(bmA & lt);                  // entry index of my symbol (leaders)
+    u32 cntA = __popc(peersA);
+    // part B
+    const u32 symB = l < nB ? m[s0 + 32 + l] : (0x20000u + l);
+    const u32 peersB = __match_any_sync(0xffffffffu, symB);
+    const bool leadB = l < nB && (peersB & lt) == 0;
+    const u32 cntB = __popc(peersB);
+    // does my B symbol already have an A entry?  lane j (leader of A) broadcasts its symbol
+    u32 foundAt = 0xFFFFFFFFu;                           // A leader lane holding my B symbol
+    u32 addA = 0;                                        // count to add to my A entry
+    u32 todo = bmA;
+    while (todo) {
+      const u32 j = (u32)(__ffs(todo) - 1);
+      todo &= todo - 1;
+      const u32 sj = __shfl_sync(0xffffffffu, symA, j);
+      const u32 hit = __ballot_sync(0xffffffffu, leadB && symB == sj);
+      if (hit) {
+        const u32 src = (u32)(__ffs(hit) - 1);
+        const u32 cb = __shfl_sync(0xffffffffu, cntB, src);
+        if (l == j) addA = cb;
+        if (l == src) foundAt = j;
+      }
     }
-    gdist[job.grp_off + g] = (u8)D;
+    cntA += addA;
+    const bool newB = leadB && foundAt == 0xFFFFFFFFu;
+    const u32 bmB = __ballot_sync(0xffffffffu, newB);
+    u16 *e = gh + s0;
+    if (leadA) e[slotA] = (u16)((cntA << 9) | symA);
+    if (newB) e[DA + __popc(bmB & lt)] = (u16)((cntB << 9) | symB);
+    if (l == 0) gdist[job.grp_off + g] = (u8)(DA + __popc(bmB));
   }
 }
 
@@ -127,7 +157,7 @@ struct EntArgs {
   const u8 *gdist;                      // [total_groups] entries per group
   const u32 *rank3, *rank4;
   u8 *sel, *selprev;                    // [triple][total_groups]
-  u32 *gpack;                           // [triple][total_groups] cheapest cost (10 bits) + six 3-bit excesses over it
+  u32 *gpack;                           // [triple][total_groups] six 4-bit fields: bits above the cheapest coder, clipped at 7
   u16 *gselcost;                        // [triple][total_groups] exact bits of the group under its current coder
   u32 *hist;                            // [p][6][HSTRIDE] raw cluster histograms
   u32 *leaves;                          // interleaved: [(q / 32)][HSTRIDE][q % 32], q = p * 6 + coder
@@ -389,27 +419,10 @@ k_ent_pm(EntArgs a, u32 nq) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// selector MTF list (:669-717, :816-835) kept as positions: pos[cl] = 1-based place of coder cl+1.
-// Moving the coder at place p to the front increments every place < p and sets its own to 1.
+// The selector MTF list (:669-717, :816-835) is kept as places: a 4-bit field per coder holding its
+// 1-based place.  Moving the coder at place p to the front increments every place < p and sets its
+// own to 1; with 4-bit fields "place < p" for all coders at once is a carry-free add and mask.
 // ---------------------------------------------------------------------------------------------
-struct SelList {
-  u32 pos[6];
-  __device__ __forceinline__ void init() {
-#pragma unroll
-    for (int c = 0; c < 6; c++) pos[c] = (u32)c + 1;
-  }
-  __device__ __forceinline__ u32 place(u32 cl0) const {      // cl0 = coder - 1
-    u32 p = pos[0];
-#pragma unroll
-    for (int c = 1; c < 6; c++) p = (cl0 == (u32)c) ? pos[c] : p;
-    return p;
-  }
-  __device__ __forceinline__ void to_front(u32 cl0, u32 p) {
-#pragma unroll
-    for (int c = 0; c < 6; c++) pos[c] = (cl0 == (u32)c) ? 1u : pos[c] + (pos[c] < p ? 1u : 0u);
-  }
-};
-
 // bits of every group under every coder (:731-737), six 10-bit fields per group
 __global__ void __launch_bounds__(256)
 k_ent_cost(EntArgs a) {
@@ -442,13 +455,14 @@ k_ent_cost(EntArgs a) {
     unsigned long long acc = 0;
     for (u32 k = 0; k < D; k++) { const u32 v = e[k]; acc += lenpack[v & 511u] * (unsigned long long)(v >> 9); }
     // Only cost differences matter to the reclassification, and a coder 7 or more bits above the
-    // cheapest can never win (places cost 1..6, :683-695): keep min + six 3-bit clipped excesses.
+    // cheapest can never win (places cost 1..6, :683-695): keep six clipped excesses in 4-bit fields
+    // (coders beyond ec get 7 and, in the sweep, place 7).
     u32 c[6], mn = 0xFFFFFFFFu;
 #pragma unroll
     for (int cl = 0; cl < 6; cl++) { c[cl] = (u32)((acc >> (10 * cl)) & 1023u); if (cl < ec) mn = min(mn, c[cl]); }
-    u32 pk = mn;
+    u32 pk = 0;
 #pragma unroll
-    for (int cl = 0; cl < 6; cl++) if (cl < ec) pk |= min(c[cl] - mn, 7u) << (10 + 3 * cl);
+    for (int cl = 0; cl < 6; cl++) pk |= (cl < ec ? min(c[cl] - mn, 7u) : 7u) << (4 * cl);
     gpack[g] = pk;
     const u32 sc = sel[g] - 1;
     u32 mine = c[0];
@@ -473,7 +487,9 @@ k_ent_sweep(EntArgs a) {
   const size_t base = (size_t)(active ? t : 0) * a.total_groups + job.grp_off;
   const u32 *gc = a.gpack + base;
   u8 *sel = a.sel + base;
-  SelList L; L.init();
+  u32 posv = 0;                       // place of coder cl in field cl; coders beyond ec sit at place 7
+#pragma unroll
+  for (int cl = 0; cl < 6; cl++) posv |= (cl < ec ? (u32)cl + 1u : 7u) << (4 * cl);
   u32 def = 0;
   // 16 groups per step, loaded one step ahead (register double buffer) and prefetched into L2 further ahead
   u32 nx[16];
@@ -503,21 +519,20 @@ k_ent_sweep(EntArgs a) {
 #pragma unroll
     for (int k = 0; k < 16; k++) {
       if (g0 + k < G) {
-        const u32 ck = c16[k] >> 10;
         const u32 clk = (s4[k >> 2] >> (8 * (k & 3))) & 255u;
-        // key = (cost << 6) | (coder0 << 3) | place: the minimum is the cheapest coder, lowest coder
-        // on ties (strict "<" scanning cl upward, :691-695), and carries its place along
+        // cost of coder cl = excess + place, both in 4-bit fields (no carries: <= 7 + 7).  key = (cost << 3)
+        // | coder0: the minimum is the cheapest coder, lowest coder on ties (strict "<" scanning cl
+        // upward, :691-695).
+        const u32 sum = c16[k] + posv;
         u32 key = 0xFFFFFFFFu;
 #pragma unroll
-        for (int cl = 0; cl < 6; cl++) {
-          if (cl < ec) {
-            const u32 cost = ((ck >> (3 * cl)) & 7u) + L.pos[cl];
-            key = min(key, (cost << 6) | ((u32)cl << 3) | L.pos[cl]);
-          }
-        }
-        const u32 best0 = (key >> 3) & 7u;
+        for (int cl = 0; cl < 6; cl++) key = min(key, (((sum >> (4 * cl)) & 15u) << 3) | (u32)cl);
+        const u32 best0 = key & 7u;
         if (active && best0 + 1 != clk) { def++; sel[g0 + k] = (u8)(best0 + 1); }
-        L.to_front(best0, key & 7u);
+        // move to front (:707-717): places below the chosen one move down by one, the chosen one becomes 1
+        const u32 pl = (posv >> (4 * best0)) & 15u;
+        posv += (~(posv + (8u - pl) * 0x111111u) & 0x888888u) >> 3;
+        posv = (posv & ~(15u << (4 * best0))) | (1u << (4 * best0));
       }
     }
   }
@@ -533,7 +548,7 @@ k_ent_selcost(EntArgs a) {
   const u32 G = job.n_groups;
   const bool active = (int)t < a.n_triples;
   const u8 *sel = a.sel + (size_t)(active ? t : 0) * a.total_groups + job.grp_off;
-  SelList L; L.init();
+  u32 posv = 0x654321u;               // initial list 1, 2, 3, ... (:820-822)
   u32 bits = 0;
   uint4 nx = *reinterpret_cast<const uint4 *>(sel);
   for (u32 g0 = 0; g0 < G; g0 += 16) {
@@ -544,9 +559,10 @@ k_ent_selcost(EntArgs a) {
     for (int k = 0; k < 16; k++) {
       if (g0 + k < G) {
         const u32 cl0 = ((w4[k >> 2] >> (8 * (k & 3))) & 255u) - 1;
-        const u32 pl = L.place(cl0);
+        const u32 pl = (posv >> (4 * cl0)) & 15u;
         bits += pl;
-        L.to_front(cl0, pl);
+        posv += (~(posv + (8u - pl) * 0x111111u) & 0x888888u) >> 3;
+        posv = (posv & ~(15u << (4 * cl0))) | (1u << (4 * cl0));
       }
     }
   }

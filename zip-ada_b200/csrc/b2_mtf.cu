@@ -220,17 +220,26 @@ k_mtf_seq(const B2SortTile *__restrict__ segs, u32 n_segs, const B2Job *__restri
       const u32 kk = __shfl_sync(0xffffffffu, kk_mine, h);
       if (l == k) myidx = 8 * h + kk;
       // move to front: places below the index shift up by one, b goes to place 0
-      const u32 top = v1 >> 24;
-      u32 carry = __shfl_up_sync(0xffffffffu, top, 1);
-      if (l == 0) carry = b;
-      const u32 s0 = (v0 << 8) | carry, s1 = (v1 << 8) | (v0 >> 24);
-      if (l < h) { v0 = s0; v1 = s1; }
-      else if (l == h) {
-        // bytes 0 .. kk take the shifted value, bytes above kk stay
-        const u32 m0 = kk >= 3 ? 0xFFFFFFFFu : ((1u << (8 * (kk + 1))) - 1u);
-        const u32 m1 = kk < 4 ? 0u : (kk >= 7 ? 0xFFFFFFFFu : ((1u << (8 * (kk - 3))) - 1u));
-        v0 = (s0 & m0) | (v0 & ~m0);
-        v1 = (s1 & m1) | (v1 & ~m1);
+      // bytes 0 .. kk of the hit lane take the shifted value, bytes above kk stay
+      const u32 m0 = kk >= 3 ? 0xFFFFFFFFu : ((1u << (8 * (kk + 1))) - 1u);
+      const u32 m1 = kk < 4 ? 0u : (kk >= 7 ? 0xFFFFFFFFu : ((1u << (8 * (kk - 3))) - 1u));
+      if (h == 0) {
+        // common case (index < 8): only lane 0 changes
+        if (l == 0) {
+          const u32 s0 = (v0 << 8) | b, s1 = (v1 << 8) | (v0 >> 24);
+          v0 = (s0 & m0) | (v0 & ~m0);
+          v1 = (s1 & m1) | (v1 & ~m1);
+        }
+      } else {
+        const u32 top = v1 >> 24;
+        u32 carry = __shfl_up_sync(0xffffffffu, top, 1);
+        if (l == 0) carry = b;
+        const u32 s0 = (v0 << 8) | carry, s1 = (v1 << 8) | (v0 >> 24);
+        if (l < h) { v0 = s0; v1 = s1; }
+        else if (l == h) {
+          v0 = (s0 & m0) | (v0 & ~m0);
+          v1 = (s1 & m1) | (v1 & ~m1);
+        }
       }
     }
     if (pi < p1) idx_out[off + pi] = (u8)myidx;
