@@ -104,21 +104,11 @@ __device__ __forceinline__ bool seen_has(const u32 *seen, u32 x) {
   return (w >> (x & 31)) & 1u;
 }
 
-__global__ void __launch_bounds__(32 * MS_WARPS)
-k_mtf_seq(const B2SortTile *__restrict__ segs, u32 n_segs, const B2Job *__restrict__ jobs, const u8 *__restrict__ bwt,
-          const u32 *__restrict__ m16, const u32 *__restrict__ m256, u8 *__restrict__ idx_out) {
-  __shared__ u8 lists[MS_WARPS][256];
-  const u32 unit = blockIdx.x * MS_WARPS + warp_id();
-  if (unit >= n_segs) return;
+// Phase 1 of k_mtf_seq*: the MTF list at position p0 of a block, rebuilt by one warp into lst[0..255]
+// (places >= n_used are padded with zeros).
+__device__ void mtf_build_list(const B2Job &job, const u8 *__restrict__ d, const u32 *__restrict__ s16,
+                               const u32 *__restrict__ s256, u32 p0, u8 *lst) {
   const u32 l = lane_id(), lt = (1u << l) - 1u;
-  const B2SortTile sg = segs[unit];
-  const B2Job &job = jobs[sg.job];
-  const u32 n = job.n, off = job.pos_off;
-  const u8 *d = bwt + off;
-  const u32 *s16 = m16 + (size_t)(off >> 4) * 8;
-  const u32 *s256 = m256 + (size_t)(off >> 8) * 8;
-  u8 *lst = lists[warp_id()];
-  const u32 p0 = sg.start, p1 = min(n, sg.start + B2_MTF_SEG);
   const u32 n_used = job.n_used;
   // ---- 1. list at p0 ---------------------------------------------------------------------------
   u32 seen[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -188,6 +178,24 @@ k_mtf_seq(const B2SortTile *__restrict__ segs, u32 n_segs, const B2Job *__restri
   }
   for (u32 i = count + l; i < 256; i += 32) lst[i] = 0;          // unused places (never matched: see `live`)
   __syncwarp();
+}
+
+__global__ void __launch_bounds__(32 * MS_WARPS)
+k_mtf_seq(const B2SortTile *__restrict__ segs, u32 n_segs, const B2Job *__restrict__ jobs, const u8 *__restrict__ bwt,
+          const u32 *__restrict__ m16, const u32 *__restrict__ m256, u8 *__restrict__ idx_out) {
+  __shared__ u8 lists[MS_WARPS][256];
+  const u32 unit = blockIdx.x * MS_WARPS + warp_id();
+  if (unit >= n_segs) return;
+  const u32 l = lane_id();
+  const B2SortTile sg = segs[unit];
+  const B2Job &job = jobs[sg.job];
+  const u32 n = job.n, off = job.pos_off;
+  const u8 *d = bwt + off;
+  u8 *lst = lists[warp_id()];
+  const u32 p0 = sg.start, p1 = min(n, sg.start + B2_MTF_SEG);
+  const u32 n_used = job.n_used;
+  mtf_build_list(job, d, m16 + (size_t)(off >> 4) * 8, m256 + (size_t)(off >> 8) * 8, p0, lst);
+  __syncwarp();
   // ---- 2. the segment, in order ------------------------------------------------------------------
   u32 v0 = *reinterpret_cast<const u32 *>(lst + 8 * l), v1 = *reinterpret_cast<const u32 *>(lst + 8 * l + 4);
   // places >= n_used hold padding zeros that must not match symbol 0
@@ -243,6 +251,106 @@ k_mtf_seq(const B2SortTile *__restrict__ segs, u32 n_segs, const B2Job *__restri
       }
     }
     if (pi < p1) idx_out[off + pi] = (u8)myidx;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_mtf_seq8: the same for blocks with at most 64 distinct bytes (text).  The list then fits the
+// registers of 8 lanes, so one warp advances FOUR segments at a time, one per group of 8 lanes.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32 * MS_WARPS)
+k_mtf_seq8(const B2SortTile *__restrict__ segs, u32 n_segs, const B2Job *__restrict__ jobs, const u8 *__restrict__ bwt,
+           const u32 *__restrict__ m16, const u32 *__restrict__ m256, u8 *__restrict__ idx_out) {
+  __shared__ u8 lists[MS_WARPS][4][256];
+  const u32 l = lane_id(), gl = l & 7u, grp = l >> 3;
+  const u32 unit0 = (blockIdx.x * MS_WARPS + warp_id()) * 4;
+  if (unit0 >= n_segs) return;
+  // phase 1, one unit after the other with the whole warp
+  for (u32 u = 0; u < 4; u++) {
+    if (unit0 + u < n_segs) {
+      const B2SortTile sg = segs[unit0 + u];
+      const B2Job &job = jobs[sg.job];
+      const u32 off = job.pos_off;
+      mtf_build_list(job, bwt + off, m16 + (size_t)(off >> 4) * 8, m256 + (size_t)(off >> 8) * 8, sg.start, lists[warp_id()][u]);
+    }
+  }
+  __syncwarp();
+  // phase 2, four units side by side
+  const bool have = unit0 + grp < n_segs;
+  const B2SortTile sg = segs[have ? unit0 + grp : unit0];
+  const B2Job &job = jobs[sg.job];
+  const u32 n = job.n, off = job.pos_off;
+  const u8 *d = bwt + off;
+  const u8 *lst = lists[warp_id()][grp];
+  const u32 p0 = sg.start, p1 = have ? min(n, sg.start + B2_MTF_SEG) : sg.start;
+  const u32 n_used = job.n_used;
+  u32 v0 = *reinterpret_cast<const u32 *>(lst + 8 * gl), v1 = *reinterpret_cast<const u32 *>(lst + 8 * gl + 4);
+  u32 live0 = 0, live1 = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    if (8 * gl + k < n_used) live0 |= 0xFFu << (8 * k);
+    if (8 * gl + 4 + k < n_used) live1 |= 0xFFu << (8 * k);
+  }
+  const u32 gbase = grp << 3;                      // first lane of my group
+  u32 prevb = (have && p0 > 0) ? d[p0 - 1] : 256u;
+  const u32 nb = (B2_MTF_SEG / 32);
+  for (u32 it = 0; it < nb; it++) {
+    const u32 b0 = p0 + it * 32;
+    if (!__any_sync(0xffffffffu, b0 < p1)) break;
+    const u32 pi = b0 + 4 * gl;                    // my four positions
+    const u32 word = (b0 < p1) ? *reinterpret_cast<const u32 *>(d + pi) : 0u;   // slots are 256-aligned and padded
+    // bits of my positions whose byte differs from the byte before it
+    u32 before = __shfl_up_sync(0xffffffffu, word >> 24, 1, 8);
+    if (gl == 0) before = prevb;
+    const u32 shifted = (word << 8) | (before & 255u);
+    u32 nib = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const bool differs = ((word >> (8 * j)) & 255u) != ((shifted >> (8 * j)) & 255u) || (j == 0 && gl == 0 && before > 255u);
+      if (differs && pi + j < p1) nib |= 1u << j;
+    }
+    u32 todo = nib << (4 * gl);
+    todo |= __shfl_xor_sync(0xffffffffu, todo, 1);
+    todo |= __shfl_xor_sync(0xffffffffu, todo, 2);
+    todo |= __shfl_xor_sync(0xffffffffu, todo, 4);
+    {
+      // (warp-wide shuffle: executed by every lane, also by groups that have run out of work)
+      const u32 lastpos = (b0 < p1) ? min(31u, p1 - b0 - 1) : 0u;
+      const u32 lw = __shfl_sync(0xffffffffu, word, gbase + (lastpos >> 2));
+      if (b0 < p1) prevb = (lw >> (8 * (lastpos & 3))) & 255u;
+    }
+    u32 myidx4 = 0;
+    while (__any_sync(0xffffffffu, todo != 0)) {
+      const bool act = todo != 0;
+      const u32 k = act ? (u32)(__ffs(todo) - 1) : 0u;
+      todo &= todo - 1;
+      const u32 wk = __shfl_sync(0xffffffffu, word, gbase + (k >> 2));
+      const u32 b = act ? ((wk >> (8 * (k & 3))) & 255u) : 0x100u;
+      const u32 sp = (b & 255u) * 0x01010101u;
+      const u32 e0 = act ? (__vcmpeq4(v0, sp) & live0) : 0u, e1 = act ? (__vcmpeq4(v1, sp) & live1) : 0u;
+      const u32 hm = (__ballot_sync(0xffffffffu, (e0 | e1) != 0) >> gbase) & 0xFFu;
+      const u32 h = hm ? (u32)(__ffs(hm) - 1) : 0u;            // group-relative lane holding b
+      const u32 kk_mine = e0 ? ((u32)(__ffs(e0) - 1) >> 3) : (e1 ? (4u + ((u32)(__ffs(e1) - 1) >> 3)) : 0u);
+      const u32 kk = __shfl_sync(0xffffffffu, kk_mine, gbase + h);
+      if (act && gl == (k >> 2)) myidx4 |= (8 * h + kk) << (8 * (k & 3));
+      const u32 m0 = kk >= 3 ? 0xFFFFFFFFu : ((1u << (8 * (kk + 1))) - 1u);
+      const u32 m1 = kk < 4 ? 0u : (kk >= 7 ? 0xFFFFFFFFu : ((1u << (8 * (kk - 3))) - 1u));
+      const u32 top = v1 >> 24;
+      u32 carry = __shfl_up_sync(0xffffffffu, top, 1, 8);
+      if (gl == 0) carry = b;
+      const u32 s0 = (v0 << 8) | carry, s1 = (v1 << 8) | (v0 >> 24);
+      if (act) {
+        if (gl < h) { v0 = s0; v1 = s1; }
+        else if (gl == h) {
+          v0 = (s0 & m0) | (v0 & ~m0);
+          v1 = (s1 & m1) | (v1 & ~m1);
+        }
+      }
+    }
+    if (b0 < p1) {
+      // four index bytes per lane; positions beyond p1 inside the last word are never read
+      *reinterpret_cast<u32 *>(idx_out + off + pi) = myidx4;
+    }
   }
 }
 
@@ -321,11 +429,15 @@ k_rle2(B2Job *jobs, const u8 *__restrict__ idx_in, u16 *__restrict__ mtf) {
 }
 
 int b2k_mtf(cudaStream_t st, B2Job *d_jobs, u32 n_jobs, const B2SortTile *d_tiles, u32 n_tiles,
-            const B2SortTile *d_segs, u32 n_segs, const u8 *d_bwt, u32 *d_m16, u32 *d_m256, u32 *d_tilemask, u8 *d_idx,
-            u16 *d_mtf) {
+            const B2SortTile *d_segs, u32 n_segs_small, u32 n_segs, const u8 *d_bwt, u32 *d_m16, u32 *d_m256,
+            u32 *d_tilemask, u8 *d_idx, u16 *d_mtf) {
+  // d_segs[0 .. n_segs_small) belong to blocks with <= 64 distinct bytes, the rest to the others
   if (n_tiles) {
     k_mtf_masks<<<n_tiles, MI_THREADS, 0, st>>>(d_tiles, d_jobs, d_bwt, d_m16, d_m256, d_tilemask);
-    k_mtf_seq<<<(n_segs + MS_WARPS - 1) / MS_WARPS, 32 * MS_WARPS, 0, st>>>(d_segs, n_segs, d_jobs, d_bwt, d_m16, d_m256, d_idx);
+    if (n_segs_small)
+      k_mtf_seq8<<<(n_segs_small + 4 * MS_WARPS - 1) / (4 * MS_WARPS), 32 * MS_WARPS, 0, st>>>(d_segs, n_segs_small, d_jobs, d_bwt, d_m16, d_m256, d_idx);
+    if (n_segs > n_segs_small)
+      k_mtf_seq<<<(n_segs - n_segs_small + MS_WARPS - 1) / MS_WARPS, 32 * MS_WARPS, 0, st>>>(d_segs + n_segs_small, n_segs - n_segs_small, d_jobs, d_bwt, d_m16, d_m256, d_idx);
   }
   if (n_jobs) k_rle2<<<n_jobs, R2_THREADS, 0, st>>>(d_jobs, d_idx, d_mtf);
   B2_CUDA_CHECK(cudaGetLastError());
