@@ -22,7 +22,7 @@
 #include "b2_common.cuh"
 #include "b2_kernels.h"
 
-#define ST_THREADS 512
+#define ST_THREADS 256
 #define ST_ITEMS 8
 #define ST_TILE (ST_THREADS * ST_ITEMS)
 #define ST_WARPS (ST_THREADS / 32)
@@ -106,7 +106,7 @@ struct ScatterSmem {
   u32 scan[40];
 };
 
-__global__ void __launch_bounds__(ST_THREADS, 2)
+__global__ void __launch_bounds__(ST_THREADS, 4)
 k_scatter(const B2SortTile *__restrict__ tiles, const B2Job *__restrict__ jobs,
           const u64 *__restrict__ keys_in, const u32 *__restrict__ vals_in,
           u64 *__restrict__ keys_out, u32 *__restrict__ vals_out, int shift, const u32 *__restrict__ hist,

@@ -65,7 +65,7 @@ int b2k_bwt_batch(B2SortCtx *cx, cudaStream_t st, B2Job *d_jobs, const std::vect
 #endif
 // b2_mtf.cu  (tiles of 4096 positions, segments of 256 and 16)
 #define B2_MTF_TILE 4096
-#define B2_SORT_TILE 4096
+#define B2_SORT_TILE 2048
 #define B2_MTF_SEG 32768
 int b2k_mtf(cudaStream_t st, B2Job *d_jobs, u32 n_jobs, const B2SortTile *d_tiles, u32 n_tiles,
             const B2SortTile *d_segs, u32 n_segs_small, u32 n_segs, const u8 *d_bwt, u32 *d_m16, u32 *d_m256,
