@@ -106,7 +106,7 @@ struct ScatterSmem {
   u32 scan[40];
 };
 
-__global__ void __launch_bounds__(ST_THREADS, 4)
+__global__ void __launch_bounds__(ST_THREADS, 6)
 k_scatter(const B2SortTile *__restrict__ tiles, const B2Job *__restrict__ jobs,
           const u64 *__restrict__ keys_in, const u32 *__restrict__ vals_in,
           u64 *__restrict__ keys_out, u32 *__restrict__ vals_out, int shift, const u32 *__restrict__ hist,
@@ -122,14 +122,12 @@ k_scatter(const B2SortTile *__restrict__ tiles, const B2Job *__restrict__ jobs,
   if (tid < 256) S.g_off[tid] = hist[(size_t)blockIdx.x * 256 + tid] + digit_base[(size_t)tl.job * 256 + tid];
   __syncthreads();
   u64 key[ST_ITEMS];
-  u32 val[ST_ITEMS];
   u32 rk[ST_ITEMS];   // rank within (warp, digit) | digit << 16 ; 0xFFFFFFFF = invalid
   const u32 wbase = tl.start + w * ST_WCHUNK;
 #pragma unroll
   for (int k = 0; k < ST_ITEMS; k++) {
     u32 i = wbase + k * 32 + l;
-    if (i < n) { key[k] = keys_in[off + i]; val[k] = vals_in[off + i]; }
-    else { key[k] = 0; val[k] = 0; }
+    key[k] = (i < n) ? keys_in[off + i] : 0;
   }
 #pragma unroll
   for (int k = 0; k < ST_ITEMS; k++) {
@@ -157,6 +155,14 @@ k_scatter(const B2SortTile *__restrict__ tiles, const B2Job *__restrict__ jobs,
     if (tid < 256) S.tile_start[tid] = ts;
   }
   __syncthreads();
+  // the rotation indices are only needed now: fetching them late keeps the register count low
+  // enough for six resident CTAs per SM, whose phases overlap
+  u32 val[ST_ITEMS];
+#pragma unroll
+  for (int k = 0; k < ST_ITEMS; k++) {
+    u32 i = wbase + k * 32 + l;
+    val[k] = (i < n) ? vals_in[off + i] : 0;
+  }
 #pragma unroll
   for (int k = 0; k < ST_ITEMS; k++) {
     if (rk[k] != 0xFFFFFFFFu) {
