@@ -67,6 +67,17 @@ int b2_encode_stream(b2_encoder *enc, const uint8_t *in, uint64_t n, int64_t siz
 int b2_encode_stream_device(b2_encoder *enc, const uint8_t *d_in, uint64_t n, int64_t size_hint,
                             uint8_t *d_out, uint64_t out_cap, uint64_t *out_len);
 
+/* Many independent streams in one call (archive entries: every entry of a Zip archive written with
+ * BZip2_1..3 is its own stream; Zip.Create.Add_Stream calls Compress_Data once per entry,
+ * zip-create.adb:253-265, which is serial per entry).  Entry i is the `sizes[i]` bytes at
+ * `in + in_offsets[i]`, encoded exactly as `Encode (option, size_hints[i])` would (size_hints may be
+ * NULL = unknown_size for all).  The streams are written back to back, each 8-byte aligned, into
+ * `out`; out_offsets[i] / out_lens[i] locate stream i.  Chunks of all entries share the device
+ * batches, so 100 000 small entries are as efficient as one large stream. */
+int b2_encode_batch(b2_encoder *enc, uint32_t n_entries, const uint8_t *in, const uint64_t *in_offsets,
+                    const uint64_t *sizes, const int64_t *size_hints, uint8_t *out, uint64_t out_cap,
+                    uint64_t *out_offsets, uint64_t *out_lens);
+
 /* Last error message of the calling thread (never NULL). */
 const char *b2_last_error(void);
 

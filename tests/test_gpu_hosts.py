@@ -60,3 +60,21 @@ def test_small_batches_and_pipeline_give_identical_bytes(b2mod, monkeypatch):
         ref = ref or out
         assert out == ref
     assert ref == orc.encode_stream(data, 9, data.size)
+
+
+def test_batch_of_entries_equals_one_stream_each(enc9):
+    # config 5 shape (zip_with_many_files): many small entries, sizes log-uniform in 1 B .. 64 KiB,
+    # text and incompressible, plus the edge sizes; every entry is its own BZh9 stream
+    rng = np.random.default_rng(46)
+    entries = [np.zeros(0, np.uint8), np.array([7], np.uint8), np.frombuffer(b"abc", np.uint8)]
+    for i in range(120):
+        n = int(2 ** rng.uniform(0, 16))
+        entries.append(datagen.text(n, 1000 + i) if i % 3 else datagen.random_bytes(n, 1000 + i))
+    entries.append(datagen.mixed(1_300_000, 200_000, 47))        # one entry that spans two chunks
+    entries.append(datagen.text(1_000_000, 48))                  # balancing window when the hint is the size
+    outs = enc9.encode_batch(entries, "size")
+    for e, o in zip(entries, outs):
+        assert o == orc.encode_stream(e, 9, e.size), e.size
+    outs2 = enc9.encode_batch(entries[:40], None)
+    for e, o in zip(entries[:40], outs2):
+        assert o == orc.encode_stream(e, 9, -1), e.size

@@ -41,7 +41,7 @@ class ChunkTrace(C.Structure):
                 ("bytes", C.c_uint64 * 4), ("bits", C.c_uint64 * 4)]
 
 
-EXPORTS = ["b2_create", "b2_destroy", "b2_bound", "b2_encode_stream", "b2_encode_stream_device", "b2_last_error",
+EXPORTS = ["b2_create", "b2_destroy", "b2_bound", "b2_encode_stream", "b2_encode_stream_device", "b2_encode_batch", "b2_last_error",
            "b2_set_timing", "b2_get_stats", "b2_reset_stats", "b2_dbg_block", "b2_get_trace", "b2_get_segments"]
 
 _lib = None
@@ -64,6 +64,8 @@ def lib():
         _lib.b2_encode_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int64, C.c_void_p, C.c_uint64,
                                           C.POINTER(C.c_uint64)]
         _lib.b2_encode_stream_device.argtypes = _lib.b2_encode_stream.argtypes
+        _lib.b2_encode_batch.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_uint64, C.c_void_p, C.c_void_p]
         _lib.b2_set_timing.argtypes = [C.c_void_p, C.c_int]
         _lib.b2_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
         _lib.b2_reset_stats.argtypes = [C.c_void_p]
@@ -131,6 +133,36 @@ class Encoder:
         out_len = C.c_uint64(0)
         _check(lib().b2_encode_stream_device(self._h, d_in, n, int(size_hint), d_out, out_cap, C.byref(out_len)))
         return out_len.value
+
+    def encode_batch(self, entries, size_hints=None):
+        """Many independent streams (archive entries) in one call; returns a list of bytes objects.
+        size_hints: None (unknown_size for all), "size" (each entry's own size, the Zip.Create route,
+        zip-create.adb:256), or a sequence."""
+        arrs = [_u8(x) for x in entries]
+        n = len(arrs)
+        sizes = np.array([a.size for a in arrs], dtype=np.uint64)
+        offs = np.zeros(n, dtype=np.uint64)
+        pos = 0
+        for i, a in enumerate(arrs):
+            offs[i] = pos
+            pos += (a.size + 15) & ~15
+        buf = np.zeros(max(pos, 1), dtype=np.uint8)
+        for i, a in enumerate(arrs):
+            buf[int(offs[i]):int(offs[i]) + a.size] = a
+        if size_hints is None:
+            hints = None
+        elif isinstance(size_hints, str) and size_hints == "size":
+            hints = sizes.astype(np.int64)
+        else:
+            hints = np.asarray(size_hints, dtype=np.int64)
+        cap = int(sum(int(lib().b2_bound(int(s))) + 2048 for s in sizes)) + 64
+        out = np.empty(cap, dtype=np.uint8)
+        out_offs = np.zeros(max(n, 1), dtype=np.uint64)
+        out_lens = np.zeros(max(n, 1), dtype=np.uint64)
+        _check(lib().b2_encode_batch(self._h, n, buf.ctypes.data, offs.ctypes.data, sizes.ctypes.data,
+                                     hints.ctypes.data if hints is not None else None, out.ctypes.data, cap,
+                                     out_offs.ctypes.data, out_lens.ctypes.data))
+        return [out[int(out_offs[i]):int(out_offs[i]) + int(out_lens[i])].tobytes() for i in range(n)]
 
     # -- generic shape of the reference: Read_Byte / More_Bytes / Write_Byte --------------------
     def encode_callbacks(self, read_byte, more_bytes, write_byte, size_hint=unknown_size):

@@ -128,17 +128,21 @@ struct b2_encoder {
   DevBuf<B2Chunk> d_chunks;
   DevBuf<u32> d_scalars;
   DevBuf<u32> d_seg, d_nseg;
+  DevBuf<B2StreamEnd> d_ends;
+  DevBuf<B2PackItem> d_packitems;
+  DevBuf<u8> d_packed;
   DevBuf<u32> d_cut_first, d_cut_last, d_cut_tsum;
   DevBuf<u64> d_cut_carry, d_cut_tincl;
   std::vector<Workspace *> ws;
   // host state of the last call
   std::vector<B2Chunk> chunks;
-  std::vector<u32> nseg, seg;
+  std::vector<u32> nseg;
+  std::vector<std::vector<u32>> seg;     // cut lists of (chunk, profile); empty when the list is just [len]
   std::vector<b2_chunk_trace> trace;
   b2_stats stats;
   B2SortStats sort_stats;
   size_t batch_positions = 512u << 20;  // positions per batch (env B2GPU_BATCH_POSITIONS); big batches amortise the latency-bound kernels
-  size_t batch_jobs_max = 4096;         // blocks per batch    (env B2GPU_BATCH_JOBS)
+  size_t batch_jobs_max = 32768;        // blocks per batch    (env B2GPU_BATCH_JOBS)
   int n_workspaces = 1;                 // batches in flight   (env B2GPU_PIPELINE)
   u64 launches_other = 0;
   cudaEvent_t ev[2] = {nullptr, nullptr};
@@ -336,12 +340,14 @@ int plan_chunk(b2_encoder *e, u32 c, ChunkPlan &P, std::vector<B2Job> &add, size
     }
     for (int k = 0; k < 2; k++) {                                    // segmented_1/2 (:1266-1291)
       u32 ns = e->nseg[2 * c + k];
-      if (ns > B2_MAX_SEG) B2_FAIL(B2_ERR_INTERNAL, "segment table overflow");
       P.n_seg[k] = ns;
-      const u32 *cuts = &e->seg[(size_t)(2 * c + k) * B2_MAX_SEG];
       if (ns == 0) slices[2 + k].push_back({0, 0});                  // seg.Is_Empty -> one empty block (:1283-1284)
-      u32 index_start = 0;
-      for (u32 s = 0; s < ns; s++) { slices[2 + k].push_back({index_start, cuts[s] - index_start}); index_start = cuts[s]; }
+      else if (ns == 1) slices[2 + k].push_back({0, P.len});         // trivial segmentation = [len] (:102-104)
+      else {
+        const std::vector<u32> &cuts = e->seg[2 * c + k];
+        u32 index_start = 0;
+        for (u32 s = 0; s < ns; s++) { slices[2 + k].push_back({index_start, cuts[s] - index_start}); index_start = cuts[s]; }
+      }
     }
   }
   std::map<std::pair<u32, u32>, u32> seen;
@@ -366,81 +372,98 @@ int plan_chunk(b2_encoder *e, u32 c, ChunkPlan &P, std::vector<B2Job> &add, size
   return 0;
 }
 
-struct Resolver {                 // serial state carried from chunk to chunk (:1305-1345)
-  u64 cur_bit = 32;               // after "BZh<level>"
-  u32 combined_crc = 0;
+// One BZip2 stream of a batch call: `n` bytes at d_in + off, reference size_hint `hint`.
+// Filled by encode_streams: where its bytes start in e->d_out and how many there are.
+struct StreamDesc {
+  u64 off, n; i64 hint;
+  u64 out_off, out_len;        // bytes
+  u32 chunk0, n_chunks;
 };
 
-// Winners of the chunks of one finished batch, in order; appends concat items.
-void resolve_batch(b2_encoder *e, Workspace *w, const Batch &B, std::vector<ChunkPlan> &plans, Resolver &R,
-                   std::vector<B2ConcatItem> &items) {
-  for (u32 c = B.c0; c < B.c1; c++) {
-    ChunkPlan &P = plans[c];
-    b2_chunk_trace tr; memset(&tr, 0, sizeof tr);
-    tr.start = P.start; tr.len = P.len; tr.dyn_capacity = P.cap; tr.n_seg1 = P.n_seg[0]; tr.n_seg2 = P.n_seg[1];
-    int best = 0;
-    const u32 in_bits = (u32)(R.cur_bit & 7);
-    for (int t = 0; t < P.n_tactics; t++) {
-      u64 bits = 0;
-      for (u32 id : P.tactic_jobs[t]) bits += w->batch_jobs[id].nbits;
-      tr.bits[t] = bits;
-      tr.bytes[t] = (in_bits + bits) >> 3;      // destination_index: whole bytes flushed
-    }
-    for (int t = 0; t < P.n_tactics; t++) if (tr.bytes[t] < tr.bytes[best]) best = t;
-    tr.winner = best;
-    for (u32 id : P.tactic_jobs[best]) {
-      const B2Job &b = w->batch_jobs[id];
-      items.push_back(B2ConcatItem{b.bits_off, b.nbits, R.cur_bit});
-      R.cur_bit += b.nbits;
-      R.combined_crc = rotl1(R.combined_crc) ^ b.crc;     // (:990)
-    }
-    e->trace[c] = tr;
-  }
-}
-
-// The whole stream, input resident on the device.  Output words land in e->d_out.
-int encode_device(b2_encoder *e, const u8 *d_in, u64 n, i64 size_hint, u64 *out_len) {
+// Encodes streams[*] (all resident in d_in) into disjoint regions of e->d_out.  Every stream is what
+// one `Encode (option, size_hint)` call writes (bzip2-encoding.adb:1413-1431); chunks of all streams
+// share the batches, so many small entries fill the device as well as one large stream.
+int encode_streams(b2_encoder *e, const u8 *d_in, std::vector<StreamDesc> &streams) {
   cudaStream_t st = e->st;
   const int level = e->level;
-  e->stats.streams++; e->stats.input_bytes += n;
   e->trace.clear(); e->chunks.clear(); e->nseg.clear(); e->seg.clear();
   i64 win_lo, win_hi;
   balance_window(level, win_lo, win_hi);
-  // ---- A1 chunk cutting, A3 segmentation -----------------------------------------------------
-  const u32 max_chunks = (u32)(n / (40000ull * level) + 16);
-  u32 n_chunks = 0;
+  const i64 full_cap = (i64)level * 100000;
+  // ---- A1 chunk cutting --------------------------------------------------------------------------
+  std::vector<u32> chunk_stream;          // stream of every chunk
   {
     StageTimer tm(e, st, e->ev, &e->stats.stage_ms[0]);
-    B2_TRY(e->d_chunks.ensure(max_chunks));
-    const size_t ct = (size_t)(n / 2048 + 2);
-    B2_TRY(e->d_cut_first.ensure(ct)); B2_TRY(e->d_cut_last.ensure(ct)); B2_TRY(e->d_cut_tsum.ensure(ct));
-    B2_TRY(e->d_cut_carry.ensure(ct)); B2_TRY(e->d_cut_tincl.ensure(ct));
-    B2CutWork cw{e->d_cut_first.p, e->d_cut_last.p, e->d_cut_tsum.p, e->d_cut_carry.p, e->d_cut_tincl.p};
-    B2_TRY(b2k_cut(st, d_in, n, size_hint, level, win_lo, win_hi, e->d_chunks.p, e->d_scalars.p, max_chunks, &cw));
-    e->launches_other += 5;
-    B2_CUDA_CHECK(cudaMemcpyAsync(&n_chunks, e->d_scalars.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
-    B2_CUDA_CHECK(cudaStreamSynchronize(st));
-    if (n_chunks > max_chunks) B2_FAIL(B2_ERR_INTERNAL, "chunk table overflow");
-    e->chunks.resize(n_chunks);
-    B2_CUDA_CHECK(cudaMemcpyAsync(e->chunks.data(), e->d_chunks.p, n_chunks * sizeof(B2Chunk), cudaMemcpyDeviceToHost, st));
+    // a stream whose RLE1 output cannot reach the smallest possible capacity is a single chunk
+    const u64 small_limit = (u64)((win_lo / 2 - 16) * 4 / 5);
+    for (size_t si = 0; si < streams.size(); si++) {
+      StreamDesc &S = streams[si];
+      e->stats.streams++; e->stats.input_bytes += S.n;
+      S.chunk0 = (u32)e->chunks.size();
+      if (S.n <= small_limit) {
+        const i64 rest = S.hint < 0 ? -1 : S.hint;                        // stream_rest before the first read
+        const i64 cap = (rest >= win_lo && rest <= win_hi) ? rest / 2 : full_cap;   // (:1416-1424)
+        e->chunks.push_back(B2Chunk{S.off, (u32)S.n, (u32)cap, 0, 0});
+      } else {
+        const u32 max_chunks = (u32)(S.n / (40000ull * level) + 16);
+        B2_TRY(e->d_chunks.ensure(max_chunks));
+        const size_t ct = (size_t)(S.n / 2048 + 2);
+        B2_TRY(e->d_cut_first.ensure(ct)); B2_TRY(e->d_cut_last.ensure(ct)); B2_TRY(e->d_cut_tsum.ensure(ct));
+        B2_TRY(e->d_cut_carry.ensure(ct)); B2_TRY(e->d_cut_tincl.ensure(ct));
+        B2CutWork cw{e->d_cut_first.p, e->d_cut_last.p, e->d_cut_tsum.p, e->d_cut_carry.p, e->d_cut_tincl.p};
+        B2_TRY(b2k_cut(st, d_in + S.off, S.n, S.hint, level, win_lo, win_hi, e->d_chunks.p, e->d_scalars.p, max_chunks, &cw));
+        e->launches_other += 5;
+        u32 nc = 0;
+        B2_CUDA_CHECK(cudaMemcpyAsync(&nc, e->d_scalars.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
+        B2_CUDA_CHECK(cudaStreamSynchronize(st));
+        if (nc > max_chunks) B2_FAIL(B2_ERR_INTERNAL, "chunk table overflow");
+        const size_t base = e->chunks.size();
+        e->chunks.resize(base + nc);
+        B2_CUDA_CHECK(cudaMemcpyAsync(e->chunks.data() + base, e->d_chunks.p, nc * sizeof(B2Chunk), cudaMemcpyDeviceToHost, st));
+        B2_CUDA_CHECK(cudaStreamSynchronize(st));
+        for (size_t c = base; c < e->chunks.size(); c++) e->chunks[c].start += S.off;
+      }
+      S.n_chunks = (u32)e->chunks.size() - S.chunk0;
+      for (u32 c = 0; c < S.n_chunks; c++) chunk_stream.push_back((u32)si);
+    }
+  }
+  const u32 n_chunks = (u32)e->chunks.size();
+  e->stats.chunks += n_chunks;
+  e->trace.resize(n_chunks);
+  // ---- A3 segmentation of every chunk --------------------------------------------------------------
+  {
+    StageTimer tm(e, st, e->ev, &e->stats.stage_ms[0]);
+    B2_TRY(e->d_chunks.ensure(n_chunks));
+    B2_CUDA_CHECK(cudaMemcpyAsync(e->d_chunks.p, e->chunks.data(), n_chunks * sizeof(B2Chunk), cudaMemcpyHostToDevice, st));
     if (level == 9) {
       B2_TRY(e->d_seg.ensure((size_t)n_chunks * 2 * B2_MAX_SEG));
       B2_TRY(e->d_nseg.ensure((size_t)n_chunks * 2));
       B2_TRY(b2k_segment(st, d_in, e->d_chunks.p, n_chunks, e->d_T.p, e->d_seg.p, e->d_nseg.p));
       e->nseg.resize((size_t)n_chunks * 2);
-      e->seg.resize((size_t)n_chunks * 2 * B2_MAX_SEG);
       B2_CUDA_CHECK(cudaMemcpyAsync(e->nseg.data(), e->d_nseg.p, e->nseg.size() * sizeof(u32), cudaMemcpyDeviceToHost, st));
-      B2_CUDA_CHECK(cudaMemcpyAsync(e->seg.data(), e->d_seg.p, e->seg.size() * sizeof(u32), cudaMemcpyDeviceToHost, st));
+      B2_CUDA_CHECK(cudaStreamSynchronize(st));
+      // only chunks with a real segmentation need their cut lists (a trivial one is just [len])
+      e->seg.assign((size_t)n_chunks * 2, std::vector<u32>());
+      for (u32 k = 0; k < 2 * n_chunks; k++) {
+        const u32 ns = e->nseg[k];
+        if (ns > B2_MAX_SEG) B2_FAIL(B2_ERR_INTERNAL, "segment table overflow");
+        if (ns > 1) {
+          e->seg[k].resize(ns);
+          B2_CUDA_CHECK(cudaMemcpyAsync(e->seg[k].data(), e->d_seg.p + (size_t)k * B2_MAX_SEG, ns * sizeof(u32), cudaMemcpyDeviceToHost, st));
+        }
+      }
       e->launches_other += 1;
     }
     B2_CUDA_CHECK(cudaStreamSynchronize(st));
   }
-  e->stats.chunks += n_chunks;
-  e->trace.resize(n_chunks);
-  // ---- output buffer -------------------------------------------------------------------------
-  const u64 out_bound = b2_bound(n) + 1024ull * n_chunks;
-  B2_TRY(e->d_out.ensure(out_bound / 4 + 16));
-  B2_CUDA_CHECK(cudaMemsetAsync(e->d_out.p, 0, (out_bound / 4 + 8) * sizeof(u32), st));
+  // ---- output regions ------------------------------------------------------------------------------
+  u64 out_total = 0;
+  for (auto &S : streams) {
+    S.out_off = out_total;
+    out_total += (b2_bound(S.n) + 1024ull * S.n_chunks + 71) & ~7ull;
+  }
+  B2_TRY(e->d_out.ensure(out_total / 4 + 16));
+  B2_CUDA_CHECK(cudaMemsetAsync(e->d_out.p, 0, (out_total / 4 + 8) * sizeof(u32), st));
   // ---- plan: batches of whole chunks ---------------------------------------------------------
   std::vector<ChunkPlan> plans(n_chunks);
   std::vector<Batch> batches;
@@ -468,7 +491,10 @@ int encode_device(b2_encoder *e, const u8 *d_in, u64 n, i64 size_hint, u64 *out_
   }
   B2_CUDA_CHECK(cudaStreamSynchronize(st));           // output zeroed before any concat
   // ---- pipelined batches ---------------------------------------------------------------------
-  Resolver R;
+  // serial state carried from chunk to chunk inside a stream (:1305-1345)
+  std::vector<B2StreamEnd> ends(streams.size());
+  for (size_t si = 0; si < streams.size(); si++) { ends[si].out_off = streams[si].out_off; ends[si].end_bit = 32; ends[si].crc = 0; ends[si].pad = 0; }
+  u64 out_words_needed = 0;
   const int W = (e->timing >= 2) ? 1 : std::max(1, std::min<int>((int)e->ws.size(), (int)batches.size()));
   for (auto *w : e->ws) {
     memset(&w->sort_stats, 0, sizeof w->sort_stats);
@@ -496,9 +522,35 @@ int encode_device(b2_encoder *e, const u8 *d_in, u64 n, i64 size_hint, u64 *out_
       std::unique_lock<std::mutex> lk(mu);
       cv.wait(lk, [&] { return turn == b; });
       if (!rc && !err) {
+        // winners of the chunks of this batch, in order
         std::vector<B2ConcatItem> items;
-        resolve_batch(e, w, batches[b], plans, R, items);
-        if ((R.cur_bit + 128) / 8 > out_bound) { rc = B2_ERR_INTERNAL; b2_set_error(__FILE__, __LINE__, "output bound exceeded"); }
+        for (u32 c = batches[b].c0; c < batches[b].c1; c++) {
+          ChunkPlan &P = plans[c];
+          B2StreamEnd &E = ends[chunk_stream[c]];
+          b2_chunk_trace tr; memset(&tr, 0, sizeof tr);
+          tr.start = P.start - streams[chunk_stream[c]].off; tr.len = P.len; tr.dyn_capacity = P.cap;
+          tr.n_seg1 = P.n_seg[0]; tr.n_seg2 = P.n_seg[1];
+          int best = 0;
+          const u32 in_bits = (u32)(E.end_bit & 7);
+          for (int t = 0; t < P.n_tactics; t++) {
+            u64 bits = 0;
+            for (u32 id : P.tactic_jobs[t]) bits += w->batch_jobs[id].nbits;
+            tr.bits[t] = bits;
+            tr.bytes[t] = (in_bits + bits) >> 3;      // destination_index: whole bytes flushed
+          }
+          for (int t = 0; t < P.n_tactics; t++) if (tr.bytes[t] < tr.bytes[best]) best = t;
+          tr.winner = best;
+          for (u32 id : P.tactic_jobs[best]) {
+            const B2Job &jb = w->batch_jobs[id];
+            items.push_back(B2ConcatItem{jb.bits_off, jb.nbits, E.out_off * 8 + E.end_bit});
+            E.end_bit += jb.nbits;
+            E.crc = rotl1(E.crc) ^ jb.crc;             // (:990)
+          }
+          e->trace[c] = tr;
+          const StreamDesc &S = streams[chunk_stream[c]];
+          const u64 region = (b2_bound(S.n) + 1024ull * S.n_chunks + 71) & ~7ull;
+          if ((E.end_bit + 128) / 8 > region) { rc = B2_ERR_INTERNAL; b2_set_error(__FILE__, __LINE__, "output bound exceeded"); break; }
+        }
         if (!rc) {
           StageTimer tm(e, w->st, w->ev, &w->stage_ms[6]);
           rc = w->d_items.ensure(items.size());
@@ -520,34 +572,16 @@ int encode_device(b2_encoder *e, const u8 *d_in, u64 n, i64 size_hint, u64 *out_
     for (int i = 0; i < W; i++) th.emplace_back(worker, i);
     for (auto &t : th) t.join();
   }
+  (void)out_words_needed;
   if (err) { g_last_error = err_msg; return err; }
-  // ---- header and footer (:1384-1407): 4 + 10 bytes, written through a tiny host staging ------
+  // ---- stream headers and footers (:1384-1407) on the device ----------------------------------------
   {
-    const u64 cur_bit = R.cur_bit;
-    const u32 combined_crc = R.combined_crc;
-    u8 head[4] = {'B', 'Z', 'h', (u8)('0' + level)};
-    // footer bits: 48-bit magic 0x177245385090 + 32-bit combined CRC at bit offset cur_bit
-    u8 foot[16]; memset(foot, 0, sizeof foot);
-    u64 first_byte = cur_bit >> 3;
-    u32 sh = (u32)(cur_bit & 7);
-    const u8 fm[10] = {0x17, 0x72, 0x45, 0x38, 0x50, 0x90, (u8)(combined_crc >> 24), (u8)(combined_crc >> 16),
-                       (u8)(combined_crc >> 8), (u8)combined_crc};
-    for (int i = 0; i < 10; i++) {
-      foot[i] |= (u8)(fm[i] >> sh);
-      if (sh) foot[i + 1] |= (u8)(fm[i] << (8 - sh));
-    }
-    u64 total_bits = cur_bit + 80;
-    u64 total_bytes = (total_bits + 7) >> 3;
-    // merge the partial first footer byte with the last data byte already on the device
-    u8 last = 0;
-    u8 *d_out8 = (u8 *)e->d_out.p;
-    if (sh) B2_CUDA_CHECK(cudaMemcpyAsync(&last, d_out8 + first_byte, 1, cudaMemcpyDeviceToHost, st));
+    B2_TRY(e->d_ends.ensure(ends.size()));
+    B2_CUDA_CHECK(cudaMemcpyAsync(e->d_ends.p, ends.data(), ends.size() * sizeof(B2StreamEnd), cudaMemcpyHostToDevice, st));
+    B2_TRY(b2k_stream_ends(st, e->d_ends.p, (u32)ends.size(), level, e->d_out.p));
+    e->launches_other += 1;
     B2_CUDA_CHECK(cudaStreamSynchronize(st));
-    foot[0] |= last;
-    B2_CUDA_CHECK(cudaMemcpyAsync(d_out8 + first_byte, foot, (size_t)(total_bytes - first_byte), cudaMemcpyHostToDevice, st));
-    B2_CUDA_CHECK(cudaMemcpyAsync(d_out8, head, 4, cudaMemcpyHostToDevice, st));
-    B2_CUDA_CHECK(cudaStreamSynchronize(st));
-    *out_len = total_bytes;
+    for (size_t si = 0; si < streams.size(); si++) streams[si].out_len = (ends[si].end_bit + 80 + 7) >> 3;
   }
   // ---- merge per-workspace statistics -------------------------------------------------------
   for (auto *w : e->ws) {
@@ -569,6 +603,15 @@ int encode_device(b2_encoder *e, const u8 *d_in, u64 n, i64 size_hint, u64 *out_
   e->stats.scatter_elems = e->sort_stats.scatter_elems;
   e->stats.scatter_ms = e->sort_stats.scatter_ms;
   e->stats.kernel_launches = e->launches_other + e->sort_stats.launches;
+  return 0;
+}
+
+// The whole stream, input resident on the device.  Output bytes land at the start of e->d_out.
+int encode_device(b2_encoder *e, const u8 *d_in, u64 n, i64 size_hint, u64 *out_len) {
+  std::vector<StreamDesc> streams(1);
+  streams[0] = StreamDesc{0, n, size_hint, 0, 0, 0, 0};
+  B2_TRY(encode_streams(e, d_in, streams));
+  *out_len = streams[0].out_len;
   return 0;
 }
 
@@ -632,7 +675,7 @@ void b2_destroy(b2_encoder *e) {
   for (auto *w : e->ws) { if (w->st) cudaStreamSynchronize(w->st); w->release(); delete w; }
   e->ws.clear();
   e->d_ct.release(); e->d_T.release(); e->d_in.release(); e->d_out.release(); e->d_chunks.release();
-  e->d_scalars.release(); e->d_seg.release(); e->d_nseg.release(); e->d_cut_first.release(); e->d_cut_last.release();
+  e->d_scalars.release(); e->d_seg.release(); e->d_nseg.release(); e->d_ends.release(); e->d_packitems.release(); e->d_packed.release(); e->d_cut_first.release(); e->d_cut_last.release();
   e->d_cut_tsum.release(); e->d_cut_carry.release(); e->d_cut_tincl.release();
   if (e->ev[0]) cudaEventDestroy(e->ev[0]);
   if (e->ev[1]) cudaEventDestroy(e->ev[1]);
@@ -683,6 +726,43 @@ int b2_encode_stream(b2_encoder *e, const uint8_t *in, uint64_t n, int64_t size_
   return 0;
 }
 
+int b2_encode_batch(b2_encoder *e, uint32_t n_entries, const uint8_t *in, const uint64_t *in_offsets,
+                    const uint64_t *sizes, const int64_t *size_hints, uint8_t *out, uint64_t out_cap,
+                    uint64_t *out_offsets, uint64_t *out_lens) {
+  if (!e || (n_entries && (!in_offsets || !sizes || !out_offsets || !out_lens))) B2_FAIL(B2_ERR_ARGUMENT, "bad argument");
+  B2_CUDA_CHECK(cudaSetDevice(e->device));
+  u64 total_in = 0;
+  for (u32 i = 0; i < n_entries; i++) total_in = std::max<u64>(total_in, in_offsets[i] + sizes[i]);
+  if (total_in && !in) B2_FAIL(B2_ERR_ARGUMENT, "bad argument");
+  B2_TRY(e->d_in.ensure(total_in + 256));
+  if (e->timing) cudaEventRecord(e->ev_call[0], e->st);
+  if (total_in) B2_CUDA_CHECK(cudaMemcpyAsync(e->d_in.p, in, total_in, cudaMemcpyHostToDevice, e->st));
+  B2_CUDA_CHECK(cudaMemsetAsync(e->d_in.p + total_in, 0, 128, e->st));
+  std::vector<StreamDesc> streams(n_entries);
+  for (u32 i = 0; i < n_entries; i++) streams[i] = StreamDesc{in_offsets[i], sizes[i], size_hints ? size_hints[i] : -1, 0, 0, 0, 0};
+  B2_TRY(encode_streams(e, e->d_in.p, streams));
+  // pack the streams back to back (8-byte aligned) and bring them to the host
+  std::vector<B2PackItem> items(n_entries);
+  u64 pos = 0;
+  for (u32 i = 0; i < n_entries; i++) {
+    items[i] = B2PackItem{streams[i].out_off, pos, streams[i].out_len};
+    out_offsets[i] = pos; out_lens[i] = streams[i].out_len;
+    pos += (streams[i].out_len + 7) & ~7ull;
+  }
+  if (pos > out_cap) B2_FAIL(B2_ERR_OUTPUT_TOO_SMALL, "output buffer too small");
+  if (n_entries) {
+    B2_TRY(e->d_packitems.ensure(n_entries));
+    B2_TRY(e->d_packed.ensure(pos + 64));
+    B2_CUDA_CHECK(cudaMemcpyAsync(e->d_packitems.p, items.data(), n_entries * sizeof(B2PackItem), cudaMemcpyHostToDevice, e->st));
+    B2_TRY(b2k_pack_streams(e->st, e->d_packitems.p, n_entries, (const u8 *)e->d_out.p, e->d_packed.p));
+    if (out && pos) B2_CUDA_CHECK(cudaMemcpyAsync(out, e->d_packed.p, pos, cudaMemcpyDeviceToHost, e->st));
+  }
+  if (e->timing) cudaEventRecord(e->ev_call[1], e->st);
+  B2_CUDA_CHECK(cudaStreamSynchronize(e->st));
+  if (e->timing) { float ms = 0; cudaEventElapsedTime(&ms, e->ev_call[0], e->ev_call[1]); e->stats.call_ms += ms; }
+  return 0;
+}
+
 int b2_set_timing(b2_encoder *e, int on) { if (!e) return B2_ERR_ARGUMENT; e->timing = on; return 0; }
 int b2_get_stats(b2_encoder *e, b2_stats *out) { if (!e || !out) return B2_ERR_ARGUMENT; *out = e->stats; return 0; }
 int b2_reset_stats(b2_encoder *e) {
@@ -701,10 +781,12 @@ int b2_get_trace(b2_encoder *e, b2_chunk_trace *out, uint64_t cap, uint64_t *n) 
 
 int b2_get_segments(b2_encoder *e, uint64_t chunk, int profile, uint32_t *cuts, uint32_t cap, uint32_t *n) {
   if (!e || !n || profile < 0 || profile > 1) return B2_ERR_ARGUMENT;
-  if (chunk * 2 + profile >= e->nseg.size()) { *n = 0; return B2_ERR_ARGUMENT; }
-  u32 ns = e->nseg[chunk * 2 + profile];
+  const size_t k = chunk * 2 + profile;
+  if (k >= e->nseg.size()) { *n = 0; return B2_ERR_ARGUMENT; }
+  const u32 ns = e->nseg[k];
   *n = ns;
-  for (u32 i = 0; i < ns && i < cap && i < B2_MAX_SEG; i++) cuts[i] = e->seg[(chunk * 2 + profile) * B2_MAX_SEG + i];
+  if (ns == 1 && cap >= 1) cuts[0] = e->chunks[chunk].len;
+  else for (u32 i = 0; i < ns && i < cap; i++) cuts[i] = e->seg[k][i];
   return 0;
 }
 

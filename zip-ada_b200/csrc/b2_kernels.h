@@ -40,6 +40,8 @@ int b2k_rle1(cudaStream_t st, const u8 *d_in, B2Job *d_jobs, u32 n_jobs, u8 *d_t
 
 struct B2SortJob { u32 job, tile0, ntiles, pad; };
 struct B2ConcatItem { u64 src_word; u64 nbits; u64 dst_bit; };
+struct B2StreamEnd { u64 out_off; u64 end_bit; u32 crc; u32 pad; };   // per stream: region start (bytes), bits written so far
+struct B2PackItem { u64 src_off; u64 dst_off; u64 len; };           // bytes
 
 struct B2SortCtx {
   u64 *keysA, *keysB;
@@ -81,3 +83,5 @@ int b2k_bits_layout(cudaStream_t st, B2Job *d_jobs, u32 n_jobs, u64 *d_total_wor
 int b2k_pack(cudaStream_t st, const B2Job *d_jobs, u32 n_jobs, const u16 *d_mtf, const u8 *d_sel, const u8 *d_lens,
              u8 *d_selpos, u32 *d_bits, int level, u32 total_groups);
 int b2k_concat(cudaStream_t st, const B2ConcatItem *d_items, u32 n_items, const u32 *d_bits, u32 *d_out);
+int b2k_stream_ends(cudaStream_t st, const B2StreamEnd *d_ends, u32 n, int level, u32 *d_out);
+int b2k_pack_streams(cudaStream_t st, const B2PackItem *d_items, u32 n, const u8 *d_src, u8 *d_dst);

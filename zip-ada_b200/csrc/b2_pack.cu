@@ -227,6 +227,30 @@ k_concat(const B2ConcatItem *__restrict__ items, const u32 *__restrict__ bits, u
   }
 }
 
+// Stream header "BZh<level>" (:1384-1391) and footer (:1395-1407): 48-bit magic 0x177245385090 and
+// the combined CRC at the stream's current bit offset; the zero padding to a byte is already there.
+__global__ void k_stream_ends(const B2StreamEnd *__restrict__ ends, u32 n, int level, u32 *__restrict__ out) {
+  const u32 s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const B2StreamEnd E = ends[s];
+  u32 *w = out + (E.out_off >> 2);                 // regions are 8-byte aligned
+  atomicOr(&w[0], bswap32(0x425A6800u | (u32)('0' + level)));
+  u64 p = E.end_bit;
+  put_bits_atomic(w, p, 0x177245u, 24); p += 24;
+  put_bits_atomic(w, p, 0x385090u, 24); p += 24;
+  put_bits_atomic(w, p, E.crc, 32);
+}
+
+// Copies every stream from its region to its packed place (both 8-byte aligned), 8 bytes per thread.
+__global__ void __launch_bounds__(256)
+k_pack_streams(const B2PackItem *__restrict__ items, const u8 *__restrict__ src, u8 *__restrict__ dst) {
+  const B2PackItem it = items[blockIdx.x];
+  const u64 nw = (it.len + 7) >> 3;
+  const u64 *s = reinterpret_cast<const u64 *>(src + it.src_off);
+  u64 *d = reinterpret_cast<u64 *>(dst + it.dst_off);
+  for (u64 i = threadIdx.x; i < nw; i += blockDim.x) d[i] = s[i];
+}
+
 __global__ void k_bits_layout(B2Job *jobs, u32 n_jobs, u64 *total_words) {
   // serial exclusive scan of per-block word counts (<= a few thousand blocks)
   if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -237,6 +261,20 @@ __global__ void k_bits_layout(B2Job *jobs, u32 n_jobs, u64 *total_words) {
     }
     *total_words = run;
   }
+}
+
+int b2k_stream_ends(cudaStream_t st, const B2StreamEnd *d_ends, u32 n, int level, u32 *d_out) {
+  if (n == 0) return 0;
+  k_stream_ends<<<(n + 127) / 128, 128, 0, st>>>(d_ends, n, level, d_out);
+  B2_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int b2k_pack_streams(cudaStream_t st, const B2PackItem *d_items, u32 n, const u8 *d_src, u8 *d_dst) {
+  if (n == 0) return 0;
+  k_pack_streams<<<n, 256, 0, st>>>(d_items, d_src, d_dst);
+  B2_CUDA_CHECK(cudaGetLastError());
+  return 0;
 }
 
 int b2k_bits_layout(cudaStream_t st, B2Job *d_jobs, u32 n_jobs, u64 *d_total_words) {
