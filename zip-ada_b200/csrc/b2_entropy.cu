@@ -170,6 +170,17 @@ struct EntArgs {
   u32 n_jobs;
 };
 
+// Coder counts that the brute force always tries (coder_choices, bzip2-encoding.adb:907-915); the
+// others are tried only when the previous Construct left low_cluster_usage set (:936-939).
+__host__ __device__ inline u32 b2_choice_mask(int level, u32 M) {
+  if (level == 9) {
+    if (M <= 5000) return (1u << 2) | (1u << 3) | (1u << 6);
+    if (M <= 10000) return (1u << 3) | (1u << 4) | (1u << 6);
+    return (1u << 3) | (1u << 4) | (1u << 5) | (1u << 6);
+  }
+  return (1u << 4) | (1u << 6);
+}
+
 __device__ __forceinline__ size_t leaf_index(u32 q, u32 e) { return ((size_t)(q >> 5) * HSTRIDE + e) * 32 + (q & 31); }
 
 // Initial_Clustering_by_Rank (:572-588, :625-631)
@@ -198,7 +209,11 @@ k_ent_init(EntArgs a) {
   for (u32 i = threadIdx.x; i < B2_MAX_CODERS * HSTRIDE; i += 256) h[i] = 0;
   u8 *ln = a.lens + (size_t)p * B2_MAX_CODERS * B2_MAX_ALPHA;
   for (u32 i = threadIdx.x; i < B2_MAX_CODERS * B2_MAX_ALPHA; i += 256) ln[i] = 0;
-  if (threadIdx.x == 0) { a.stat[2 * p] = 1; a.stat[2 * p + 1] = 0; }
+  if (threadIdx.x == 0) {
+    const bool always = (b2_choice_mask(a.level, job.n_mtf) >> ec) & 1u;
+    a.stat[2 * p] = 1;
+    a.stat[2 * p + 1] = always ? 0u : 2u;        // 0 running, 1 finished, 2 not scheduled (gated)
+  }
 }
 
 // Define_Descriptors, first half (:643-652) + Avoid_Zeros (:439-462)
@@ -577,6 +592,7 @@ k_ent_final(EntArgs a) {
   const int t = blockIdx.x;
   const u32 jb = blockIdx.y;
   const u32 p = jb * B2_N_TRIPLES + t;
+  if (a.stat[2 * p + 1] == 2u) return;             // not scheduled (yet)
   const B2Job &job = a.jobs[jb];
   const u32 G = job.n_groups;
   const int A = (int)job.n_used + 2;
@@ -613,7 +629,34 @@ k_ent_final(EntArgs a) {
     for (int c = 1; c <= ec; c++) if (stat[c] < uniform_usage / 2) low = 1;
     a.cost_all[p] = total;
     a.low_all[p] = low;
+    a.stat[2 * p + 1] = 1;                         // finished (converged or all rounds done)
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Schedules the gated triples whose turn has come: a coder count outside coder_choices is tried iff
+// the Construct that ran just before it in the reference's loop (ec from 6 down to 2 inside every
+// (max_code_len, sample_width) pair, :930-952) left low_cluster_usage set.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_ent_gate(EntArgs a, u32 *activated) {
+  const u32 jb = blockIdx.x * blockDim.x + threadIdx.x;
+  if (jb >= a.n_jobs) return;
+  const u32 mask = b2_choice_mask(a.level, a.jobs[jb].n_mtf);
+  u32 count = 0;
+  for (int t0 = 0; t0 < a.n_triples; t0 += 5) {
+    bool low = false;            // low_cluster_usage as the loop reaches each coder count
+    bool known = true;           // false once a Construct that would run has not finished yet
+    for (int c = 0; c < 5 && known; c++) {
+      const int ec = 6 - c;
+      const u32 p = jb * B2_N_TRIPLES + t0 + c;
+      const bool runs = low || ((mask >> ec) & 1u);
+      if (!runs) continue;
+      const u32 f = a.stat[2 * p + 1];
+      if (f == 2u) { a.stat[2 * p + 1] = 0; count++; known = false; }     // schedule it; what follows depends on it
+      else low = a.low_all[p] != 0;
+    }
+  }
+  if (count) atomicAdd(activated, count);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -625,12 +668,7 @@ __global__ void k_choose(B2Job *jobs, u32 n_jobs, const u32 *__restrict__ cost_a
   if (jb >= n_jobs) return;
   B2Job &job = jobs[jb];
   const u32 M = job.n_mtf;
-  u32 choice_mask;   // bit ec set if ec in coder_choices (:907-915)
-  if (level == 9) {
-    if (M <= 5000) choice_mask = (1u << 2) | (1u << 3) | (1u << 6);
-    else if (M <= 10000) choice_mask = (1u << 3) | (1u << 4) | (1u << 6);
-    else choice_mask = (1u << 3) | (1u << 4) | (1u << 5) | (1u << 6);
-  } else choice_mask = (1u << 4) | (1u << 6);
+  const u32 choice_mask = b2_choice_mask(level, M);   // bit ec set if ec in coder_choices (:907-915)
   bool low = false;
   u32 best_cost = 0x7FFFFFFFu, best = 0;
   for (int t = 0; t < n_triples; t++) {
@@ -658,7 +696,7 @@ int b2k_entropy(cudaStream_t st, B2Job *d_jobs, u32 n_jobs, u32 max_groups_per_j
                 const u16 *d_mtf, u16 *d_ghist, u8 *d_gdist, u32 *d_rank3, u32 *d_rank4, u8 *d_sel, u8 *d_selprev,
                 u32 *d_gpack, u16 *d_gselcost,
                 u32 *d_hist, u32 *d_leaves, u8 *d_lens, u32 *d_stat, u32 *d_selcost, u32 *d_cost, u32 *d_low,
-                int level, u64 *launches) {
+                int level, u32 *d_activated, u64 *launches) {
   B2_CUDA_CHECK(cudaFuncSetAttribute(k_rank_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, 18064 * 4));
   if (n_jobs == 0) return 0;
   const int n_triples = level == 9 ? 20 : 5;
@@ -675,17 +713,27 @@ int b2k_entropy(cudaStream_t st, B2Job *d_jobs, u32 n_jobs, u32 max_groups_per_j
   const u32 nq = n_jobs * B2_N_TRIPLES * B2_MAX_CODERS;
   k_ent_init<<<grid, 256, 0, st>>>(a);
   *launches += 4;
-  for (int it = 0; it <= 10; it++) {
-    // iterations 1..10 (:793-802); round 10 is the extra Define_Descriptors for triples still moving (:803-807)
-    k_ent_hist<<<grid, 256, 0, st>>>(a);
-    k_ent_qsort<<<(nq + 31) / 32, 32, 0, st>>>(a, nq);
-    k_ent_pm<<<(nq + PM_WARPS - 1) / PM_WARPS, 32 * PM_WARPS, 0, st>>>(a, nq);
-    k_ent_cost<<<grid, 256, 0, st>>>(a);
-    *launches += 4;
-    if (it < 10) { k_ent_sweep<<<n_jobs, 32, 0, st>>>(a); *launches += 1; }
+  for (int phase = 0; phase < 4; phase++) {
+    for (int it = 0; it <= 10; it++) {
+      // iterations 1..10 (:793-802); round 10 is the extra Define_Descriptors for triples still moving (:803-807)
+      k_ent_hist<<<grid, 256, 0, st>>>(a);
+      k_ent_qsort<<<(nq + 31) / 32, 32, 0, st>>>(a, nq);
+      k_ent_pm<<<(nq + PM_WARPS - 1) / PM_WARPS, 32 * PM_WARPS, 0, st>>>(a, nq);
+      k_ent_cost<<<grid, 256, 0, st>>>(a);
+      *launches += 4;
+      if (it < 10) { k_ent_sweep<<<n_jobs, 32, 0, st>>>(a); *launches += 1; }
+    }
+    k_ent_selcost<<<n_jobs, 32, 0, st>>>(a);
+    k_ent_final<<<grid, 256, 0, st>>>(a);
+    // gated coder counts whose predecessor asked for them (at most three more phases)
+    B2_CUDA_CHECK(cudaMemsetAsync(d_activated, 0, sizeof(u32), st));
+    k_ent_gate<<<(n_jobs + 127) / 128, 128, 0, st>>>(a, d_activated);
+    *launches += 3;
+    u32 activated = 0;
+    B2_CUDA_CHECK(cudaMemcpyAsync(&activated, d_activated, sizeof(u32), cudaMemcpyDeviceToHost, st));
+    B2_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (!activated) break;
   }
-  k_ent_selcost<<<n_jobs, 32, 0, st>>>(a);
-  k_ent_final<<<grid, 256, 0, st>>>(a);
   k_choose<<<(n_jobs + 127) / 128, 128, 0, st>>>(d_jobs, n_jobs, d_cost, d_low, level, n_triples);
   *launches += 3;
   B2_CUDA_CHECK(cudaGetLastError());
