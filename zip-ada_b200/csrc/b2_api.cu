@@ -82,7 +82,7 @@ struct Workspace {
   DevBuf<u8> d_gdist;
   DevBuf<u32> d_rank3, d_rank4;
   DevBuf<u8> d_sel, d_selprev, d_selpos, d_lens;
-  DevBuf<u32> d_ehist, d_leaves, d_estat, d_selcost;
+  DevBuf<u32> d_ehist, d_leaves, d_wl, d_estat, d_selcost;
   DevBuf<u32> d_gpack;
   DevBuf<u16> d_gselcost;
   DevBuf<u32> d_cost, d_low;
@@ -102,7 +102,7 @@ struct Workspace {
     d_rank.release(); d_grp.release(); d_slotA.release(); d_slotB.release(); d_sa.release(); d_tile_cnt.release(); d_tiles.release(); d_mtiles.release(); d_msegs.release(); d_sj.release(); d_hist.release();
     d_digit_base.release(); d_tile_head.release(); d_carry.release(); d_unsorted.release(); d_mtf.release(); d_ghist.release(); d_gdist.release();
     d_rank3.release(); d_rank4.release(); d_sel.release(); d_selprev.release(); d_selpos.release(); d_lens.release();
-    d_ehist.release(); d_leaves.release(); d_estat.release(); d_selcost.release(); d_gpack.release(); d_gselcost.release(); d_cost.release();
+    d_ehist.release(); d_leaves.release(); d_wl.release(); d_estat.release(); d_selcost.release(); d_gpack.release(); d_gselcost.release(); d_cost.release();
     d_low.release(); d_bits.release(); d_items.release();
     if (h_unsorted) cudaFreeHost(h_unsorted);
     h_unsorted = nullptr; h_unsorted_cap = 0;
@@ -203,7 +203,7 @@ int ensure_batch_workspace(Workspace *w, size_t T, size_t J) {
   B2_TRY(w->d_selpos.ensure(GT));
   B2_TRY(w->d_gpack.ensure(GT * B2_N_TRIPLES + 64)); B2_TRY(w->d_gselcost.ensure(GT * B2_N_TRIPLES + 64));
   B2_TRY(w->d_ehist.ensure(J * B2_N_TRIPLES * B2_MAX_CODERS * 260));
-  B2_TRY(w->d_leaves.ensure((J * B2_N_TRIPLES * B2_MAX_CODERS + 64) * 260));
+  B2_TRY(w->d_leaves.ensure((J * B2_N_TRIPLES * B2_MAX_CODERS + 64) * 260)); B2_TRY(w->d_wl.ensure(J * B2_N_TRIPLES * B2_MAX_CODERS + 64));
   B2_TRY(w->d_estat.ensure(J * B2_N_TRIPLES * 2)); B2_TRY(w->d_selcost.ensure(J * B2_N_TRIPLES));
   B2_TRY(w->d_lens.ensure(J * B2_N_TRIPLES * B2_MAX_CODERS * B2_MAX_ALPHA));
   B2_TRY(w->d_cost.ensure(J * B2_N_TRIPLES)); B2_TRY(w->d_low.ensure(J * B2_N_TRIPLES));
@@ -302,7 +302,7 @@ int run_batch(b2_encoder *e, Workspace *w, const u8 *d_in, std::vector<B2Job> &j
   {
     StageTimer tm(e, st, w->ev, &w->stage_ms[4]);
     B2_TRY(b2k_entropy(st, w->d_jobs.p, J, max_g, gpos, w->d_mtf.p, w->d_ghist.p, w->d_gdist.p, w->d_rank3.p, w->d_rank4.p, w->d_sel.p,
-                       w->d_selprev.p, w->d_gpack.p, w->d_gselcost.p, w->d_ehist.p, w->d_leaves.p, w->d_lens.p, w->d_estat.p, w->d_selcost.p,
+                       w->d_selprev.p, w->d_gpack.p, w->d_gselcost.p, w->d_ehist.p, w->d_leaves.p, w->d_wl.p, w->d_lens.p, w->d_estat.p, w->d_selcost.p,
                        w->d_cost.p, w->d_low.p, e->level, w->d_scalars.p + 8, &w->launches));
   }
   {

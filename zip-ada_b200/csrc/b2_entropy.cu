@@ -160,7 +160,8 @@ struct EntArgs {
   u32 *gpack;                           // [triple][total_groups] six 4-bit fields: bits above the cheapest coder, clipped at 7
   u16 *gselcost;                        // [triple][total_groups] exact bits of the group under its current coder
   u32 *hist;                            // [p][6][HSTRIDE] raw cluster histograms
-  u32 *leaves;                          // interleaved: [(q / 32)][HSTRIDE][q % 32], q = p * 6 + coder
+  u32 *leaves;                          // interleaved: [(slot / 32)][HSTRIDE][slot % 32], slot = place in the work list
+  u32 *wl, *wl_count;                   // work list of this round: q = p * 6 + coder of every coder to (re)build
   u8 *lens;                             // [p][6][B2_MAX_ALPHA]
   u32 *stat;                            // [p][2]: defectors of the last sweep, finished flag
   u32 *selcost;                         // [p]
@@ -252,18 +253,23 @@ k_ent_hist(EntArgs a) {
   }
   __syncthreads();
   for (u32 i = tid; i < (u32)ec * HSTRIDE; i += 256) hg[i] = (&h[0][0])[i];
+  // the coders of this problem join the round's work list (compact: finished problems cost nothing)
+  __shared__ u32 slot0;
+  if (tid == 0) slot0 = atomicAdd(a.wl_count, (u32)ec);
+  __syncthreads();
   const u32 w = warp_id(), l = lane_id();
   if ((int)w < ec) {
     u32 zeroes = 0;
     for (int s = l; s < A; s += 32) zeroes += (h[w][s] == 0);
 #pragma unroll
     for (int o = 16; o; o >>= 1) zeroes += __shfl_xor_sync(0xffffffffu, zeroes, o);
-    const u32 q = p * B2_MAX_CODERS + w;
+    const u32 slot = slot0 + w;
+    if (l == 0) a.wl[slot] = p * B2_MAX_CODERS + w;
     for (int s = l; s < A; s += 32) {
       u32 v = h[w][s];
       if (zeroes > 0 && zeroes <= 100) v = max(1u, v);
       else if (zeroes > 100) v = (v == 0) ? 1u : v * 2u;
-      a.leaves[leaf_index(q, (u32)s)] = (v << 9) | (u32)s;      // alphabet order (:230-235); every count is > 0 here
+      a.leaves[leaf_index(slot, (u32)s)] = (v << 9) | (u32)s;   // alphabet order (:230-235); every count is > 0 here
     }
   }
 }
@@ -279,14 +285,14 @@ k_ent_qsort(EntArgs a, u32 nq) {
   __shared__ u32 s[HSTRIDE * 32];
   __shared__ u32 stk[16 * 32];                 // per-lane stack of (first << 16 | count)
   const u32 l = threadIdx.x;
-  const u32 q = blockIdx.x * 32 + l;
+  const u32 slot = blockIdx.x * 32 + l;
+  const u32 count = min(*a.wl_count, nq);
+  if (blockIdx.x * 32 >= count) return;
   u32 n = 0;
-  if (q < nq) {
-    const u32 p = q / B2_MAX_CODERS, c = q % B2_MAX_CODERS;
-    const u32 jb = p / B2_N_TRIPLES, t = p % B2_N_TRIPLES;
-    int max_len, sw, ec;
-    b2_triple(a.level, (int)t, max_len, sw, ec);
-    if ((int)t < a.n_triples && jb < a.n_jobs && (int)c < ec && !a.stat[2 * p + 1]) n = a.jobs[jb].n_used + 2;
+  if (slot < count) {
+    const u32 q = a.wl[slot];
+    const u32 jb = (q / B2_MAX_CODERS) / B2_N_TRIPLES;
+    n = a.jobs[jb].n_used + 2;
   }
   const u32 nmax = __reduce_max_sync(0xffffffffu, n);
   if (nmax == 0) return;
@@ -420,15 +426,15 @@ __global__ void __launch_bounds__(32 * PM_WARPS)
 k_ent_pm(EntArgs a, u32 nq) {
   __shared__ LLScratch S[PM_WARPS];
   const u32 w = warp_id(), l = lane_id();
-  const u32 q = blockIdx.x * PM_WARPS + w;
-  if (q >= nq) return;
+  const u32 slot = blockIdx.x * PM_WARPS + w;
+  if (slot >= min(*a.wl_count, nq)) return;
+  const u32 q = a.wl[slot];
   const u32 p = q / B2_MAX_CODERS, c = q % B2_MAX_CODERS;
   const u32 jb = p / B2_N_TRIPLES, t = p % B2_N_TRIPLES;
   int max_len, sw, ec;
   b2_triple(a.level, (int)t, max_len, sw, ec);
-  if ((int)t >= a.n_triples || (int)c >= ec || a.stat[2 * p + 1]) return;
   const int ns = (int)a.jobs[jb].n_used + 2;
-  for (int e = l; e < ns; e += 32) S[w].leaf[e] = a.leaves[leaf_index(q, (u32)e)];
+  for (int e = l; e < ns; e += 32) S[w].leaf[e] = a.leaves[leaf_index(slot, (u32)e)];
   __syncwarp();
   ll_package_merge_warp(S[w], ns, max_len, a.lens + ((size_t)p * B2_MAX_CODERS + c) * B2_MAX_ALPHA);
 }
@@ -695,7 +701,7 @@ __global__ void k_choose(B2Job *jobs, u32 n_jobs, const u32 *__restrict__ cost_a
 int b2k_entropy(cudaStream_t st, B2Job *d_jobs, u32 n_jobs, u32 max_groups_per_job, u32 total_groups,
                 const u16 *d_mtf, u16 *d_ghist, u8 *d_gdist, u32 *d_rank3, u32 *d_rank4, u8 *d_sel, u8 *d_selprev,
                 u32 *d_gpack, u16 *d_gselcost,
-                u32 *d_hist, u32 *d_leaves, u8 *d_lens, u32 *d_stat, u32 *d_selcost, u32 *d_cost, u32 *d_low,
+                u32 *d_hist, u32 *d_leaves, u32 *d_wl, u8 *d_lens, u32 *d_stat, u32 *d_selcost, u32 *d_cost, u32 *d_low,
                 int level, u32 *d_activated, u64 *launches) {
   B2_CUDA_CHECK(cudaFuncSetAttribute(k_rank_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, 18064 * 4));
   if (n_jobs == 0) return 0;
@@ -706,7 +712,7 @@ int b2k_entropy(cudaStream_t st, B2Job *d_jobs, u32 n_jobs, u32 max_groups_per_j
   k_rank_sort<<<n_jobs * 2, 32, sort_smem, st>>>(d_jobs, d_rank3, d_rank4);
   EntArgs a;
   a.jobs = d_jobs; a.mtf = d_mtf; a.ghist = d_ghist; a.gdist = d_gdist; a.rank3 = d_rank3; a.rank4 = d_rank4; a.sel = d_sel; a.selprev = d_selprev;
-  a.gpack = d_gpack; a.gselcost = d_gselcost; a.hist = d_hist; a.leaves = d_leaves; a.lens = d_lens; a.stat = d_stat; a.selcost = d_selcost;
+  a.gpack = d_gpack; a.gselcost = d_gselcost; a.hist = d_hist; a.leaves = d_leaves; a.wl = d_wl; a.wl_count = d_activated + 1; a.lens = d_lens; a.stat = d_stat; a.selcost = d_selcost;
   a.cost_all = d_cost; a.low_all = d_low; a.total_groups = total_groups; a.level = level; a.n_triples = n_triples;
   a.n_jobs = n_jobs;
   const dim3 grid(n_triples, n_jobs);
@@ -716,6 +722,7 @@ int b2k_entropy(cudaStream_t st, B2Job *d_jobs, u32 n_jobs, u32 max_groups_per_j
   for (int phase = 0; phase < 4; phase++) {
     for (int it = 0; it <= 10; it++) {
       // iterations 1..10 (:793-802); round 10 is the extra Define_Descriptors for triples still moving (:803-807)
+      B2_CUDA_CHECK(cudaMemsetAsync(a.wl_count, 0, sizeof(u32), st));
       k_ent_hist<<<grid, 256, 0, st>>>(a);
       k_ent_qsort<<<(nq + 31) / 32, 32, 0, st>>>(a, nq);
       k_ent_pm<<<(nq + PM_WARPS - 1) / PM_WARPS, 32 * PM_WARPS, 0, st>>>(a, nq);
