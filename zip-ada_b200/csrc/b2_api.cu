@@ -298,12 +298,16 @@ int run_batch(b2_encoder *e, Workspace *w, const u8 *d_in, std::vector<B2Job> &j
   B2_CUDA_CHECK(cudaMemcpyAsync(w->batch_jobs.data(), w->d_jobs.p, J * sizeof(B2Job), cudaMemcpyDeviceToHost, st));
   B2_CUDA_CHECK(cudaStreamSynchronize(st));
   max_g = 1;
-  for (u32 j = 0; j < J; j++) max_g = std::max(max_g, w->batch_jobs[j].n_groups);
+  u32 max_alpha = 2;
+  for (u32 j = 0; j < J; j++) {
+    max_g = std::max(max_g, w->batch_jobs[j].n_groups);
+    max_alpha = std::max(max_alpha, w->batch_jobs[j].n_used + 2);
+  }
   {
     StageTimer tm(e, st, w->ev, &w->stage_ms[4]);
     B2_TRY(b2k_entropy(st, w->d_jobs.p, J, max_g, gpos, w->d_mtf.p, w->d_ghist.p, w->d_gdist.p, w->d_rank3.p, w->d_rank4.p, w->d_sel.p,
                        w->d_selprev.p, w->d_gpack.p, w->d_gselcost.p, w->d_ehist.p, w->d_leaves.p, w->d_wl.p, w->d_lens.p, w->d_estat.p, w->d_selcost.p,
-                       w->d_cost.p, w->d_low.p, e->level, w->d_scalars.p + 8, &w->launches));
+                       w->d_cost.p, w->d_low.p, e->level, max_alpha, w->d_scalars.p + 8, &w->launches));
   }
   {
     StageTimer tm(e, st, w->ev, &w->stage_ms[5]);

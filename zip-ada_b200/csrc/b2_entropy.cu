@@ -281,9 +281,10 @@ k_ent_hist(EntArgs a) {
 // (element e of lane l at e*32+l: conflict free).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32)
-k_ent_qsort(EntArgs a, u32 nq) {
-  __shared__ u32 s[HSTRIDE * 32];
-  __shared__ u32 stk[16 * 32];                 // per-lane stack of (first << 16 | count)
+k_ent_qsort(EntArgs a, u32 nq, u32 alpha_max) {
+  extern __shared__ u32 qs_smem[];             // alpha_max x 32 elements, then 16 x 32 stack words
+  u32 *s = qs_smem;
+  u32 *stk = qs_smem + alpha_max * 32;         // per-lane stack of (first << 16 | count)
   const u32 l = threadIdx.x;
   const u32 slot = blockIdx.x * 32 + l;
   const u32 count = min(*a.wl_count, nq);
@@ -300,44 +301,48 @@ k_ent_qsort(EntArgs a, u32 nq) {
   for (u32 e = 0; e < nmax; e++) s[e * 32 + l] = g[e * 32 + l];
   __syncwarp();
 #define EL(x) s[(x) * 32 + l]
-  enum { POP = 0, SI = 1, SJ = 2, CK = 3 };
-  int sp = 0, st = POP;
-  u32 f = 0, nn = 0, pw = 0;
-  i32 i = 0, j = 0;
-  if (n >= 2) { stk[l] = n; sp = 1; }
+  // Every lane walks scan-up -> scan-down -> check in ONE pass of the loop body, so that a lane whose
+  // scans stop at once (the common case with many equal weights) completes a swap per pass.
+  enum { SI = 1, SJ = 2, CK = 3 };
+  int sp = 0, st = SI;
+  u32 f = 0, nn = n, pw = 0;
+  i32 i = 0, j = (i32)n - 1;
   bool active = n >= 2;
+  if (active) pw = EL(nn / 2) >> 9;
   while (__any_sync(0xffffffffu, active)) {
     if (active) {
-      if (st == POP) {
-        if (sp == 0) active = false;
-        else {
-          sp--;
-          const u32 v = stk[sp * 32 + l];
-          f = v >> 16; nn = v & 0xFFFFu;
-          pw = EL(f + nn / 2) >> 9;
-          i = 0; j = (i32)nn - 1;
-          st = SI;
-        }
-      } else if (st == SI) {
+      if (st == SI) {
 #pragma unroll
         for (int u = 0; u < 4; u++) { if (st == SI) { if ((EL(f + i) >> 9) < pw) i++; else st = SJ; } }
-      } else if (st == SJ) {
+      }
+      if (st == SJ) {
 #pragma unroll
         for (int u = 0; u < 4; u++) { if (st == SJ) { if (pw < (EL(f + j) >> 9)) j--; else st = CK; } }
-      } else {
+      }
+      if (st == CK) {
         if (i >= j) {
-          // Quick_sort (a (first .. first+i-1)); Quick_sort (a (first+i .. last)); larger range pushed first
+          // Quick_sort (a (first .. first+i-1)); Quick_sort (a (first+i .. last)): the smaller range is
+          // sorted next, the larger one waits on the stack (the ranges are disjoint, order is free)
           const u32 n1 = (u32)i, n2 = nn - (u32)i;
-          const u32 r1 = (f << 16) | n1, r2 = ((f + (u32)i) << 16) | n2;
-          if (n1 > n2) { if (n1 >= 2) stk[(sp++) * 32 + l] = r1; if (n2 >= 2) stk[(sp++) * 32 + l] = r2; }
-          else { if (n2 >= 2) stk[(sp++) * 32 + l] = r2; if (n1 >= 2) stk[(sp++) * 32 + l] = r1; }
-          st = POP;
+          u32 fa = f, na = n1, fb = f + (u32)i, nb = n2;       // a = next, b = later
+          if (n1 > n2) { fa = f + (u32)i; na = n2; fb = f; nb = n1; }
+          if (na < 2) { fa = fb; na = nb; nb = 0; }
+          if (nb >= 2) stk[(sp++) * 32 + l] = (fb << 16) | nb;
+          if (na < 2) {
+            if (sp == 0) active = false;
+            else { const u32 v = stk[(--sp) * 32 + l]; fa = v >> 16; na = v & 0xFFFFu; }
+          }
+          if (active) {
+            f = fa; nn = na;
+            pw = EL(f + nn / 2) >> 9;
+            i = 0; j = (i32)nn - 1;
+          }
         } else {
           const u32 x = EL(f + i), y = EL(f + j);
           EL(f + i) = y; EL(f + j) = x;
           i++; j--;
-          st = SI;
         }
+        st = SI;
       }
     }
   }
@@ -702,9 +707,13 @@ int b2k_entropy(cudaStream_t st, B2Job *d_jobs, u32 n_jobs, u32 max_groups_per_j
                 const u16 *d_mtf, u16 *d_ghist, u8 *d_gdist, u32 *d_rank3, u32 *d_rank4, u8 *d_sel, u8 *d_selprev,
                 u32 *d_gpack, u16 *d_gselcost,
                 u32 *d_hist, u32 *d_leaves, u32 *d_wl, u8 *d_lens, u32 *d_stat, u32 *d_selcost, u32 *d_cost, u32 *d_low,
-                int level, u32 *d_activated, u64 *launches) {
+                int level, u32 max_alpha, u32 *d_activated, u64 *launches) {
   B2_CUDA_CHECK(cudaFuncSetAttribute(k_rank_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, 18064 * 4));
+  B2_CUDA_CHECK(cudaFuncSetAttribute(k_ent_qsort, cudaFuncAttributeMaxDynamicSharedMemorySize, (HSTRIDE + 16) * 32 * 4));
   if (n_jobs == 0) return 0;
+  if (max_alpha < 2) max_alpha = 2;
+  if (max_alpha > HSTRIDE) max_alpha = HSTRIDE;
+  const size_t qs_smem = ((size_t)max_alpha + 16) * 32 * 4;
   const int n_triples = level == 9 ? 20 : 5;
   k_group_keys<<<n_jobs, 256, 0, st>>>(d_jobs, d_mtf, d_rank3, d_rank4);
   k_group_hist<<<n_jobs, 256, 0, st>>>(d_jobs, d_mtf, d_ghist, d_gdist);
@@ -724,7 +733,7 @@ int b2k_entropy(cudaStream_t st, B2Job *d_jobs, u32 n_jobs, u32 max_groups_per_j
       // iterations 1..10 (:793-802); round 10 is the extra Define_Descriptors for triples still moving (:803-807)
       B2_CUDA_CHECK(cudaMemsetAsync(a.wl_count, 0, sizeof(u32), st));
       k_ent_hist<<<grid, 256, 0, st>>>(a);
-      k_ent_qsort<<<(nq + 31) / 32, 32, 0, st>>>(a, nq);
+      k_ent_qsort<<<(nq + 31) / 32, 32, qs_smem, st>>>(a, nq, max_alpha);
       k_ent_pm<<<(nq + PM_WARPS - 1) / PM_WARPS, 32 * PM_WARPS, 0, st>>>(a, nq);
       k_ent_cost<<<grid, 256, 0, st>>>(a);
       *launches += 4;

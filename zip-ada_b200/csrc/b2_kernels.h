@@ -77,7 +77,7 @@ int b2k_entropy(cudaStream_t st, B2Job *d_jobs, u32 n_jobs, u32 max_groups_per_j
                 const u16 *d_mtf, u16 *d_ghist, u8 *d_gdist, u32 *d_rank3, u32 *d_rank4, u8 *d_sel, u8 *d_selprev,
                 u32 *d_gpack, u16 *d_gselcost,
                 u32 *d_hist, u32 *d_leaves, u32 *d_wl, u8 *d_lens, u32 *d_stat, u32 *d_selcost, u32 *d_cost, u32 *d_low,
-                int level, u32 *d_activated, u64 *launches);
+                int level, u32 max_alpha, u32 *d_activated, u64 *launches);
 // b2_pack.cu
 int b2k_bits_layout(cudaStream_t st, B2Job *d_jobs, u32 n_jobs, u64 *d_total_words);
 int b2k_pack(cudaStream_t st, const B2Job *d_jobs, u32 n_jobs, const u16 *d_mtf, const u8 *d_sel, const u8 *d_lens,
