@@ -29,6 +29,7 @@ extern "C" {
 #define B2_ERR_ALLOC 3
 #define B2_ERR_CUDA 10
 #define B2_ERR_INTERNAL 11
+#define B2_ERR_DUPLICATE_NAME 20   /* Zip.Create.Duplicate_name (zip-create.ads, zip-create.adb:138-147) */
 
 /* Compression_Option (bzip2-encoding.ads:40-43): block_100k / block_400k / block_900k.
  * Zip.Compress.BZip2_E maps BZip2_1/2/3 to them (zip-compress-bzip2_e.adb:122-126). */
@@ -77,6 +78,46 @@ int b2_encode_stream_device(b2_encoder *enc, const uint8_t *d_in, uint64_t n, in
 int b2_encode_batch(b2_encoder *enc, uint32_t n_entries, const uint8_t *in, const uint64_t *in_offsets,
                     const uint64_t *sizes, const int64_t *size_hints, uint8_t *out, uint64_t out_cap,
                     uint64_t *out_offsets, uint64_t *out_lens);
+
+/* ---- Archive side: batched Zip.Create for BZip2 entries ------------------------------------------
+ * One call = Create_Archive, Add_Stream for every entry, Finish (zip-create.adb:194-297, :645-756)
+ * with Compress_Method = BZip2_1/2/3 (the level of `enc`), no password.  The bytes written to `out`
+ * are the archive the reference leaves in its output Zipstream:
+ *   per entry  local header PK\3\4 (zip-headers.adb:243-277) with needed_extract_version 10, the
+ *              entry name with '\\' turned into '/' (Unixify, zip-create.adb:180-192), the short Zip64
+ *              extension when the size or the offset needs it (:233-251, :279-292), then the payload:
+ *              the BZip2 stream of the entry (method 12, size_hint = size), or the bytes themselves
+ *              (method 0) when the stream is not smaller than the input (Compression_inefficient,
+ *              zip-compress.adb:468-490 -> Store, :224-237);
+ *   then       central headers PK\1\2 (made_by_version 23, zip-create.adb:122-131,
+ *              zip-headers.adb:167-192), Zip64 end record + locator when needed (:727-749), end
+ *              record PK\5\6.
+ * The Zip CRC-32 of every entry (zip-crc_crypto.adb:31-61; the reference updates it per byte in the
+ * Read_Byte callback, zip-compress-bzip2_e.adb:70-98) is computed on the device.
+ * names: all entry names back to back; name i = names[name_offsets[i] .. name_offsets[i+1]).
+ * dos_times: Zip_Streams.Time values as stored in the headers (NULL = Zip_Streams.default_time).
+ * flags: B2_ZIP_* bits per entry (NULL = 0).  duplicates: Duplicate_name_policy.
+ * info (may be NULL) receives crc, final method (Final_Method), compressed size (Compressed_Size)
+ * and header offset of every entry.  Encryption, comments and Preselection are outside this path. */
+#define B2_ZIP_UNICODE_NAME 1u        /* Zip_Streams.Is_Unicode_Name -> Language_Encoding_Flag_Bit */
+#define B2_ZIP_READ_ONLY 2u           /* Stream.Is_Read_Only -> external_attributes bit 0 */
+#define B2_ZIP_ADMIT_DUPLICATES 0
+#define B2_ZIP_ERROR_ON_DUPLICATE 1
+typedef struct b2_zip_entry_info {
+  uint32_t crc32;
+  uint16_t zip_type;                  /* 12 = bzip2_code, 0 = store_code */
+  uint16_t reserved;
+  uint64_t compressed_size;
+  uint64_t local_header_offset;
+} b2_zip_entry_info;
+uint64_t b2_zip_bound(uint32_t n_entries, uint64_t total_name_bytes, uint64_t total_input_bytes);
+int b2_zip_create(b2_encoder *enc, uint32_t n_entries, const uint8_t *in, const uint64_t *in_offsets,
+                  const uint64_t *sizes, const char *names, const uint32_t *name_offsets,
+                  const uint32_t *dos_times, const uint32_t *flags, int duplicates,
+                  uint8_t *out, uint64_t out_cap, uint64_t *out_len, b2_zip_entry_info *info);
+
+/* Zip CRC-32 of a host buffer, computed on the device (zip-crc_crypto.adb:31-61: Init, Update, Final). */
+int b2_zip_crc32(b2_encoder *enc, const uint8_t *in, uint64_t n, uint32_t *crc);
 
 /* Last error message of the calling thread (never NULL). */
 const char *b2_last_error(void);

@@ -24,8 +24,8 @@ _lib = None
 
 
 def build():
-    src = os.path.join(ROOT, "oracle", "b2_oracle.cpp")
-    if (not os.path.exists(_SO)) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    srcs = [os.path.join(ROOT, "oracle", f) for f in ("b2_oracle.cpp", "zip_oracle.cpp")]
+    if (not os.path.exists(_SO)) or os.path.getmtime(_SO) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
 
 
@@ -35,6 +35,7 @@ def lib():
         build()
         _lib = C.CDLL(_SO)
         _lib.orc_crc32.restype = C.c_uint32
+        _lib.orc_zip_crc32.restype = C.c_uint32
     return _lib
 
 
@@ -132,3 +133,45 @@ def balance_window(level):
     lo, hi = C.c_int64(0), C.c_int64(0)
     lib().orc_balance_window(level, C.byref(lo), C.byref(hi))
     return lo.value, hi.value
+
+
+def pack_entries(entries):
+    """entries: list of (name, bytes-like).  Returns the flat arrays both archive entry points take."""
+    datas = [_u8(d) for _, d in entries]
+    sizes = np.array([d.size for d in datas], np.uint64)
+    offs = np.zeros(len(entries), np.uint64)
+    pos = 0
+    for i, d in enumerate(datas):
+        offs[i] = pos
+        pos += (d.size + 15) & ~15
+    flat = np.zeros(max(pos, 1), np.uint8)
+    for o, d in zip(offs, datas):
+        flat[int(o):int(o) + d.size] = d
+    nb = [n.encode("utf-8") if isinstance(n, str) else bytes(n) for n, _ in entries]
+    name_offs = np.zeros(len(entries) + 1, np.uint32)
+    name_offs[1:] = np.cumsum([len(b) for b in nb])
+    names = b"".join(nb)
+    return flat, offs, sizes, names, name_offs
+
+
+def zip_crc32(data):
+    a = _u8(data)
+    return int(lib().orc_zip_crc32(a.ctypes.data_as(C.c_void_p), C.c_uint64(a.size)))
+
+
+def zip_create(entries, level=9, dos_times=None, flags=None):
+    """Oracle archive (oracle/zip_oracle.cpp): returns (archive bytes, [method per entry])."""
+    flat, offs, sizes, names, name_offs = pack_entries(entries)
+    n = len(entries)
+    cap = int(sizes.sum()) + int(name_offs[-1]) * 2 + n * 124 + 200
+    out = np.empty(cap, np.uint8)
+    out_len = C.c_uint64(0)
+    methods = np.zeros(max(n, 1), np.uint16)
+    t = None if dos_times is None else np.ascontiguousarray(dos_times, np.uint32)
+    f = None if flags is None else np.ascontiguousarray(flags, np.uint32)
+    rc = lib().orc_zip_create(level, C.c_uint32(n), flat.ctypes.data_as(C.c_void_p), offs.ctypes.data_as(C.c_void_p),
+                              sizes.ctypes.data_as(C.c_void_p), C.c_char_p(names), name_offs.ctypes.data_as(C.c_void_p),
+                              None if t is None else t.ctypes.data_as(C.c_void_p), None if f is None else f.ctypes.data_as(C.c_void_p),
+                              out.ctypes.data_as(C.c_void_p), C.c_uint64(cap), C.byref(out_len), methods.ctypes.data_as(C.c_void_p))
+    assert rc == 0, rc
+    return out[:out_len.value].tobytes(), [int(m) for m in methods[:n]]

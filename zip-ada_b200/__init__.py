@@ -29,6 +29,11 @@ class Stats(C.Structure):
                [("scatter_ms", C.c_double), ("stage_ms", C.c_double * 8), ("call_ms", C.c_double)]
 
 
+class ZipEntryInfo(C.Structure):
+    _fields_ = [("crc32", C.c_uint32), ("zip_type", C.c_uint16), ("reserved", C.c_uint16),
+                ("compressed_size", C.c_uint64), ("local_header_offset", C.c_uint64)]
+
+
 class BlockInfo(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in
                 ("n_rle", "origin", "crc", "n_mtf", "eob", "n_used", "n_sel", "ec_count", "max_len",
@@ -42,7 +47,8 @@ class ChunkTrace(C.Structure):
 
 
 EXPORTS = ["b2_create", "b2_destroy", "b2_bound", "b2_encode_stream", "b2_encode_stream_device", "b2_encode_batch", "b2_last_error",
-           "b2_set_timing", "b2_get_stats", "b2_reset_stats", "b2_dbg_block", "b2_get_trace", "b2_get_segments"]
+           "b2_set_timing", "b2_get_stats", "b2_reset_stats", "b2_dbg_block", "b2_get_trace", "b2_get_segments",
+           "b2_zip_bound", "b2_zip_create", "b2_zip_crc32"]
 
 _lib = None
 
@@ -66,6 +72,12 @@ def lib():
         _lib.b2_encode_stream_device.argtypes = _lib.b2_encode_stream.argtypes
         _lib.b2_encode_batch.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_uint64, C.c_void_p, C.c_void_p]
+        _lib.b2_zip_bound.restype = C.c_uint64
+        _lib.b2_zip_bound.argtypes = [C.c_uint32, C.c_uint64, C.c_uint64]
+        _lib.b2_zip_create.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64),
+                                       C.c_void_p]
+        _lib.b2_zip_crc32.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint32)]
         _lib.b2_set_timing.argtypes = [C.c_void_p, C.c_int]
         _lib.b2_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
         _lib.b2_reset_stats.argtypes = [C.c_void_p]
@@ -163,6 +175,51 @@ class Encoder:
                                      hints.ctypes.data if hints is not None else None, out.ctypes.data, cap,
                                      out_offs.ctypes.data, out_lens.ctypes.data))
         return [out[int(out_offs[i]):int(out_offs[i]) + int(out_lens[i])].tobytes() for i in range(n)]
+
+    # -- archive side: Zip.Create for BZip2 entries (zip-create.adb:194-297, :645-756) -------------
+    def zip_create(self, entries, dos_times=None, flags=None, duplicates=0, want_info=False):
+        """Create_Archive + Add_Stream per entry + Finish in one call.  entries: list of
+        (name, bytes-like).  Returns the archive bytes (and the per-entry ZipEntryInfo list)."""
+        n = len(entries)
+        arrs = [_u8(d) for _, d in entries]
+        sizes = np.array([a.size for a in arrs], dtype=np.uint64)
+        offs = np.zeros(n, dtype=np.uint64)
+        pos = 0
+        for i, a in enumerate(arrs):
+            offs[i] = pos
+            pos += (a.size + 15) & ~15
+        buf = np.zeros(max(pos, 1), dtype=np.uint8)
+        for i, a in enumerate(arrs):
+            buf[int(offs[i]):int(offs[i]) + a.size] = a
+        nb = [nm.encode("utf-8") if isinstance(nm, str) else bytes(nm) for nm, _ in entries]
+        name_offs = np.zeros(n + 1, dtype=np.uint32)
+        if n:
+            name_offs[1:] = np.cumsum([len(b) for b in nb])
+        names = b"".join(nb)
+        return self.zip_create_flat(buf, offs, sizes, names, name_offs, dos_times, flags, duplicates, want_info)
+
+    def zip_create_flat(self, buf, offs, sizes, names, name_offs, dos_times=None, flags=None, duplicates=0, want_info=False):
+        """Same, on the flat arrays of the C ABI (no per-entry Python work)."""
+        n = int(sizes.size)
+        cap = int(lib().b2_zip_bound(n, int(name_offs[-1]), int(sizes.sum())))
+        out = np.empty(cap, dtype=np.uint8)
+        out_len = C.c_uint64(0)
+        t = None if dos_times is None else np.ascontiguousarray(dos_times, dtype=np.uint32)
+        f = None if flags is None else np.ascontiguousarray(flags, dtype=np.uint32)
+        info = (ZipEntryInfo * max(n, 1))()
+        _check(lib().b2_zip_create(self._h, n, buf.ctypes.data, offs.ctypes.data, sizes.ctypes.data, C.c_char_p(names),
+                                   name_offs.ctypes.data, None if t is None else t.ctypes.data,
+                                   None if f is None else f.ctypes.data, int(duplicates), out.ctypes.data, cap,
+                                   C.byref(out_len), info))
+        res = out[:out_len.value]
+        return (res, [info[i] for i in range(n)]) if want_info else res
+
+    def zip_crc32(self, data):
+        """Zip CRC-32 (zip-crc_crypto.adb:31-61) computed on the device."""
+        a = _u8(data)
+        c = C.c_uint32(0)
+        _check(lib().b2_zip_crc32(self._h, a.ctypes.data if a.size else None, a.size, C.byref(c)))
+        return int(c.value)
 
     # -- generic shape of the reference: Read_Byte / More_Bytes / Write_Byte --------------------
     def encode_callbacks(self, read_byte, more_bytes, write_byte, size_hint=unknown_size):

@@ -24,6 +24,7 @@
 #include <string>
 #include <thread>
 #include <vector>
+#include <unordered_set>
 
 static thread_local std::string g_last_error = "";
 void b2_set_error(const char *file, int line, const char *msg) {
@@ -133,6 +134,12 @@ struct b2_encoder {
   DevBuf<u8> d_packed;
   DevBuf<u32> d_cut_first, d_cut_last, d_cut_tsum;
   DevBuf<u64> d_cut_carry, d_cut_tincl;
+  // archive side (b2_zip_create)
+  DevBuf<B2ZipCrcTables> d_zt;
+  DevBuf<B2ZipTile> d_ztiles;
+  DevBuf<B2ZipEntry> d_zents;
+  DevBuf<B2ZipCopy> d_zcopies;
+  DevBuf<u32> d_zpartial, d_zcrc;
   std::vector<Workspace *> ws;
   // host state of the last call
   std::vector<B2Chunk> chunks;
@@ -622,6 +629,50 @@ int encode_device(b2_encoder *e, const u8 *d_in, u64 n, i64 size_hint, u64 *out_
 }  // namespace
 
 // =============================================================================================
+// ---- archive side -----------------------------------------------------------------------------------
+namespace {
+int zip_crc_device(b2_encoder *e, const u8 *d_in, u32 n_entries, const u64 *offs, const u64 *sizes) {
+  // Zip CRC-32 of every entry (zip-crc_crypto.adb:31-61), results in e->d_zcrc
+  if (!e->d_zt.p) {
+    B2ZipCrcTables *zt = new B2ZipCrcTables();
+    b2k_make_zipcrc_tables(zt);
+    int rc = e->d_zt.ensure(1);
+    if (!rc && cudaMemcpy(e->d_zt.p, zt, sizeof(B2ZipCrcTables), cudaMemcpyHostToDevice) != cudaSuccess) rc = B2_ERR_CUDA;
+    delete zt;
+    if (rc) B2_FAIL(rc, "zip crc tables");
+  }
+  std::vector<B2ZipTile> tiles;
+  std::vector<B2ZipEntry> ents(n_entries);
+  for (u32 i = 0; i < n_entries; i++) {
+    const u64 nt = (sizes[i] + B2_ZIP_TILE - 1) / B2_ZIP_TILE;
+    ents[i] = B2ZipEntry{sizes[i], (u32)tiles.size(), (u32)nt};
+    for (u64 k = 0; k < nt; k++) tiles.push_back(B2ZipTile{offs[i], offs[i] + sizes[i] - (nt - 1 - k) * (u64)B2_ZIP_TILE});
+  }
+  if (tiles.size() >= (1ull << 31)) B2_FAIL(B2_ERR_ARGUMENT, "too much input for one archive call");
+  B2_TRY(e->d_ztiles.ensure(tiles.size() + 1));
+  B2_TRY(e->d_zents.ensure(n_entries + 1));
+  B2_TRY(e->d_zpartial.ensure(tiles.size() + 1));
+  B2_TRY(e->d_zcrc.ensure(n_entries + 1));
+  if (!tiles.empty()) B2_CUDA_CHECK(cudaMemcpyAsync(e->d_ztiles.p, tiles.data(), tiles.size() * sizeof(B2ZipTile), cudaMemcpyHostToDevice, e->st));
+  if (n_entries) B2_CUDA_CHECK(cudaMemcpyAsync(e->d_zents.p, ents.data(), n_entries * sizeof(B2ZipEntry), cudaMemcpyHostToDevice, e->st));
+  B2_TRY(b2k_zipcrc(e->st, d_in, e->d_ztiles.p, (u32)tiles.size(), e->d_zents.p, n_entries, e->d_zt.p, e->d_zpartial.p, e->d_zcrc.p));
+  e->launches_other += 2;
+  B2_CUDA_CHECK(cudaStreamSynchronize(e->st));     // the host vectors above go out of scope
+  return 0;
+}
+
+struct ByteSink {                                   // little-endian fields (zip-headers.adb:54-70)
+  std::vector<u8> b;
+  void u16le(u32 v) { b.push_back((u8)v); b.push_back((u8)(v >> 8)); }
+  void u32le(u64 v) { for (int k = 0; k < 4; k++) b.push_back((u8)(v >> (8 * k))); }
+  void u64le(u64 v) { for (int k = 0; k < 8; k++) b.push_back((u8)(v >> (8 * k))); }
+  void sig(u8 c1, u8 c2) { b.push_back(0x50); b.push_back(0x4B); b.push_back(c1); b.push_back(c2); }
+  void str(const std::string &s) { b.insert(b.end(), s.begin(), s.end()); }
+};
+struct HeaderSpan { u64 dst; std::vector<u8> bytes; };
+}  // namespace
+
+
 extern "C" {
 
 const char *b2_last_error(void) { return g_last_error.c_str(); }
@@ -681,6 +732,7 @@ void b2_destroy(b2_encoder *e) {
   e->d_ct.release(); e->d_T.release(); e->d_in.release(); e->d_out.release(); e->d_chunks.release();
   e->d_scalars.release(); e->d_seg.release(); e->d_nseg.release(); e->d_ends.release(); e->d_packitems.release(); e->d_packed.release(); e->d_cut_first.release(); e->d_cut_last.release();
   e->d_cut_tsum.release(); e->d_cut_carry.release(); e->d_cut_tincl.release();
+  e->d_zt.release(); e->d_ztiles.release(); e->d_zents.release(); e->d_zcopies.release(); e->d_zpartial.release(); e->d_zcrc.release();
   if (e->ev[0]) cudaEventDestroy(e->ev[0]);
   if (e->ev[1]) cudaEventDestroy(e->ev[1]);
   if (e->ev_call[0]) cudaEventDestroy(e->ev_call[0]);
@@ -763,6 +815,160 @@ int b2_encode_batch(b2_encoder *e, uint32_t n_entries, const uint8_t *in, const 
   }
   if (e->timing) cudaEventRecord(e->ev_call[1], e->st);
   B2_CUDA_CHECK(cudaStreamSynchronize(e->st));
+  if (e->timing) { float ms = 0; cudaEventElapsedTime(&ms, e->ev_call[0], e->ev_call[1]); e->stats.call_ms += ms; }
+  return 0;
+}
+
+// ---- archive side: Zip.Create for BZip2 entries ----
+uint64_t b2_zip_bound(uint32_t n_entries, uint64_t total_name_bytes, uint64_t total_input_bytes) {
+  // per entry: local header 30 + name + 20 (Zip64 extension), payload <= input (store fallback);
+  // central header 46 + name + 28; end records 56 + 20 + 22
+  return (u64)n_entries * (30 + 20 + 46 + 28) + 2 * total_name_bytes + total_input_bytes + 56 + 20 + 22;
+}
+
+int b2_zip_crc32(b2_encoder *e, const uint8_t *in, uint64_t n, uint32_t *crc) {
+  if (!e || !crc || (n && !in)) B2_FAIL(B2_ERR_ARGUMENT, "bad argument");
+  B2_CUDA_CHECK(cudaSetDevice(e->device));
+  B2_TRY(e->d_in.ensure(n + 256));
+  if (n) B2_CUDA_CHECK(cudaMemcpyAsync(e->d_in.p, in, n, cudaMemcpyHostToDevice, e->st));
+  const u64 off = 0;
+  B2_TRY(zip_crc_device(e, e->d_in.p, 1, &off, &n));
+  B2_CUDA_CHECK(cudaMemcpy(crc, e->d_zcrc.p, sizeof(u32), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int b2_zip_create(b2_encoder *e, uint32_t n_entries, const uint8_t *in, const uint64_t *in_offsets, const uint64_t *sizes,
+                  const char *names, const uint32_t *name_offsets, const uint32_t *dos_times, const uint32_t *flags,
+                  int duplicates, uint8_t *out, uint64_t out_cap, uint64_t *out_len, b2_zip_entry_info *info) {
+  if (!e || !out_len || (n_entries && (!in_offsets || !sizes || !names || !name_offsets))) B2_FAIL(B2_ERR_ARGUMENT, "bad argument");
+  B2_CUDA_CHECK(cudaSetDevice(e->device));
+  // entry names: back slashes become forward slashes (Unixify, zip-create.adb:180-192)
+  std::vector<std::string> nm(n_entries);
+  {
+    std::unordered_set<std::string> seen;
+    for (u32 i = 0; i < n_entries; i++) {
+      if (name_offsets[i + 1] < name_offsets[i] || name_offsets[i + 1] - name_offsets[i] > 65535u) B2_FAIL(B2_ERR_ARGUMENT, "bad entry name length");
+      nm[i].assign(names + name_offsets[i], names + name_offsets[i + 1]);
+      for (char &c : nm[i]) if (c == '\\') c = '/';
+      if (duplicates == B2_ZIP_ERROR_ON_DUPLICATE && !seen.insert(nm[i]).second) {   // Duplicate_name (zip-create.adb:138-147)
+        g_last_error = "Duplicate_name: Entry name = " + nm[i];
+        return B2_ERR_DUPLICATE_NAME;
+      }
+    }
+  }
+  u64 total_in = 0;
+  for (u32 i = 0; i < n_entries; i++) total_in = std::max<u64>(total_in, in_offsets[i] + sizes[i]);
+  if (total_in && !in) B2_FAIL(B2_ERR_ARGUMENT, "bad argument");
+  B2_TRY(e->d_in.ensure(total_in + 256));
+  if (e->timing) cudaEventRecord(e->ev_call[0], e->st);
+  if (total_in) B2_CUDA_CHECK(cudaMemcpyAsync(e->d_in.p, in, total_in, cudaMemcpyHostToDevice, e->st));
+  B2_CUDA_CHECK(cudaMemsetAsync(e->d_in.p + total_in, 0, 128, e->st));
+  B2_TRY(zip_crc_device(e, e->d_in.p, n_entries, in_offsets, sizes));
+  std::vector<u32> crc(n_entries);
+  if (n_entries) B2_CUDA_CHECK(cudaMemcpyAsync(crc.data(), e->d_zcrc.p, n_entries * sizeof(u32), cudaMemcpyDeviceToHost, e->st));
+  // every entry is one Encode call with the size known (zip-compress-bzip2_e.adb:122-129)
+  std::vector<StreamDesc> streams(n_entries);
+  for (u32 i = 0; i < n_entries; i++) streams[i] = StreamDesc{in_offsets[i], sizes[i], (i64)sizes[i], 0, 0, 0, 0};
+  B2_TRY(encode_streams(e, e->d_in.p, streams));
+  B2_CUDA_CHECK(cudaStreamSynchronize(e->st));
+
+  // ---- layout: what Add_Stream (zip-create.adb:194-297) and Finish (:645-756) leave in the stream ----
+  const u64 four_gib = 1ull << 32, max_size = 0x1FFFFFFFFFFFFFFFull;
+  const u64 margin = 22 + 56 + 20 + 65536 + 10;                    // Check_Size (:161-179)
+  bool zip64 = false;
+  auto check_size = [&](u64 value) -> int {
+    if (!zip64 && value >= four_gib - margin) {
+      zip64 = true;
+      if (value >= max_size - margin) return 1;
+    }
+    return 0;
+  };
+  std::vector<HeaderSpan> spans;
+  std::vector<B2ZipCopy> copies;
+  struct Cat { u64 usize, csize, offset; u32 crc, time, ext_attr; u16 flag, method; };
+  std::vector<Cat> cat(n_entries);
+  u64 pos = 0;
+  for (u32 i = 0; i < n_entries; i++) {
+    Cat &c = cat[i];
+    const u32 fl = flags ? flags[i] : 0;
+    c.flag = (fl & B2_ZIP_UNICODE_NAME) ? 0x0800 : 0;              // Language_Encoding_Flag_Bit (:222-224)
+    c.ext_attr = (fl & B2_ZIP_READ_ONLY) ? 1u : 0u;                // (:228-230)
+    c.time = dos_times ? dos_times[i] : 16789u * 65536u;           // Zip_Streams.default_time
+    c.usize = sizes[i];
+    c.crc = crc[i];
+    if (check_size(sizes[i])) B2_FAIL(B2_ERR_ARGUMENT, "Zip_Capacity_Exceeded: archive too large");
+    c.offset = pos;
+    // decided BEFORE compression, with compressed_size = uncompressed_size (:233-243)
+    const bool ext = sizes[i] >= 0xFFFFFFFFull || c.offset >= 0xFFFFFFFFull;
+    // Compression_inefficient <=> the stream is not smaller than the input (zip-compress.adb:468-490) -> Store (:224-237)
+    const bool stored = streams[i].out_len >= sizes[i];
+    c.method = stored ? 0 : 12;
+    c.csize = stored ? sizes[i] : streams[i].out_len;
+    ByteSink h;
+    h.sig(3, 4);
+    h.u16le(10); h.u16le(c.flag); h.u16le(c.method); h.u32le(c.time); h.u32le(c.crc);
+    if (ext) { h.u32le(0xFFFFFFFFu); h.u32le(0xFFFFFFFFu); } else { h.u32le(c.csize); h.u32le(c.usize); }
+    h.u16le((u32)nm[i].size()); h.u16le(ext ? 20 : 0);
+    h.str(nm[i]);
+    if (ext) { h.u16le(1); h.u16le(16); h.u64le(c.usize); h.u64le(c.csize); }
+    const u64 payload = pos + h.b.size();
+    spans.push_back(HeaderSpan{pos, std::move(h.b)});
+    const u64 src = stored ? in_offsets[i] : streams[i].out_off;
+    for (u64 o = 0; o < c.csize; o += 65536) copies.push_back(B2ZipCopy{src + o, payload + o, (u32)std::min<u64>(65536, c.csize - o), stored ? 1u : 0u});
+    pos = payload + c.csize;
+    if (info) { info[i].crc32 = c.crc; info[i].zip_type = c.method; info[i].reserved = 0; info[i].compressed_size = c.csize; info[i].local_header_offset = c.offset; }
+  }
+  {
+    ByteSink d;
+    const u64 cd_offset = pos;
+    u64 cd_size = 0;
+    if (!zip64 && n_entries >= 65535u) zip64 = true;               // too many entries for Zip_32 (:680-685)
+    for (u32 i = 0; i < n_entries; i++) {
+      const Cat &c = cat[i];
+      const bool ext = c.csize >= 0xFFFFFFFFull || c.usize >= 0xFFFFFFFFull || c.offset >= 0xFFFFFFFFull;
+      if (ext) zip64 = true;
+      d.sig(1, 2);
+      d.u16le(23); d.u16le(10); d.u16le(c.flag); d.u16le(c.method); d.u32le(c.time); d.u32le(c.crc);
+      d.u32le(ext ? 0xFFFFFFFFull : c.csize); d.u32le(ext ? 0xFFFFFFFFull : c.usize);
+      d.u16le((u32)nm[i].size()); d.u16le(ext ? 28 : 0);
+      d.u16le(0); d.u16le(0); d.u16le(0); d.u32le(c.ext_attr);
+      d.u32le(ext ? 0xFFFFFFFFull : c.offset);
+      d.str(nm[i]);
+      if (ext) { d.u16le(1); d.u16le(24); d.u64le(c.usize); d.u64le(c.csize); d.u64le(c.offset); }
+      cd_size += 46 + nm[i].size() + (ext ? 28 : 0);
+    }
+    if (n_entries) { if (check_size(cd_offset + cd_size + 1)) B2_FAIL(B2_ERR_ARGUMENT, "Zip_Capacity_Exceeded: archive too large"); }
+    u64 tot = n_entries, dtot = n_entries, cds = cd_size, cdo = cd_offset;
+    if (zip64) {
+      d.sig(6, 6);
+      d.u64le(44); d.u16le(0x2D); d.u16le(0x2D); d.u32le(0); d.u32le(0); d.u64le(n_entries); d.u64le(n_entries); d.u64le(cd_size); d.u64le(cd_offset);
+      d.sig(6, 7);
+      d.u32le(0); d.u64le(cd_offset + cd_size); d.u32le(1);
+      tot = dtot = 0xFFFF; cds = 0xFFFFFFFFull; cdo = 0xFFFFFFFFull;
+    }
+    d.sig(5, 6);
+    d.u16le(0); d.u16le(0); d.u16le((u32)dtot); d.u16le((u32)tot); d.u32le(cds); d.u32le(cdo); d.u16le(0);
+    const u64 n = d.b.size();
+    spans.push_back(HeaderSpan{pos, std::move(d.b)});
+    pos += n;
+  }
+  *out_len = pos;
+  if (pos > out_cap) B2_FAIL(B2_ERR_OUTPUT_TOO_SMALL, "output buffer too small");
+  if (!out) B2_FAIL(B2_ERR_ARGUMENT, "out is NULL");
+  // payloads: gathered into the archive image on the device, one copy back; headers written by the host
+  if (!copies.empty()) {
+    if (copies.size() >= (1ull << 31)) B2_FAIL(B2_ERR_ARGUMENT, "too much output for one archive call");
+    B2_TRY(e->d_zcopies.ensure(copies.size()));
+    B2_TRY(e->d_packed.ensure(pos + 64));
+    B2_CUDA_CHECK(cudaMemcpyAsync(e->d_zcopies.p, copies.data(), copies.size() * sizeof(B2ZipCopy), cudaMemcpyHostToDevice, e->st));
+    B2_TRY(b2k_zip_gather(e->st, e->d_zcopies.p, (u32)copies.size(), (const u8 *)e->d_out.p, e->d_in.p, e->d_packed.p));
+    e->launches_other += 1;
+    const u64 first = copies.front().dst_off, last = copies.back().dst_off + copies.back().len;
+    B2_CUDA_CHECK(cudaMemcpyAsync(out + first, e->d_packed.p + first, last - first, cudaMemcpyDeviceToHost, e->st));
+  }
+  if (e->timing) cudaEventRecord(e->ev_call[1], e->st);
+  B2_CUDA_CHECK(cudaStreamSynchronize(e->st));
+  for (const HeaderSpan &sp : spans) memcpy(out + sp.dst, sp.bytes.data(), sp.bytes.size());
   if (e->timing) { float ms = 0; cudaEventElapsedTime(&ms, e->ev_call[0], e->ev_call[1]); e->stats.call_ms += ms; }
   return 0;
 }

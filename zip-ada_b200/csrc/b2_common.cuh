@@ -112,4 +112,16 @@ __device__ __forceinline__ i32 block_excl_max(i32 v, i32 ident, i32 *sm, i32 *to
   if (total) *total = sm[32];
   return r;
 }
+// ---- GF(2) polynomial arithmetic for the CRCs (bzip2.adb:34-118; zip-crc_crypto.adb:31-61) ------
+#define CRC_POLY 0x04C11DB7u
+__device__ __forceinline__ u32 gf_mulmod(u32 a, u32 b) {
+  // (a * b) mod P over GF(2); bit i = coefficient of x^i
+  u32 r = 0;
+#pragma unroll 4
+  for (int i = 31; i >= 0; i--) {
+    r = (r << 1) ^ ((r & 0x80000000u) ? CRC_POLY : 0u);
+    if ((b >> i) & 1u) r ^= a;
+  }
+  return r;
+}
 #endif

@@ -85,3 +85,18 @@ int b2k_pack(cudaStream_t st, const B2Job *d_jobs, u32 n_jobs, const u16 *d_mtf,
 int b2k_concat(cudaStream_t st, const B2ConcatItem *d_items, u32 n_items, const u32 *d_bits, u32 *d_out);
 int b2k_stream_ends(cudaStream_t st, const B2StreamEnd *d_ends, u32 n, int level, u32 *d_out);
 int b2k_pack_streams(cudaStream_t st, const B2PackItem *d_items, u32 n, const u8 *d_src, u8 *d_dst);
+
+// ---- archive side (b2_zip.cu) --------------------------------------------------------------------
+#define B2_ZIP_TILE 65536
+struct B2ZipCrcTables {
+  u32 byte_tab[256];      // MSB-first table of 0x04C11DB7 (fed with bit-reversed bytes)
+  u32 xp_thread[1024];    // x^(8*64*(1023-t))
+  u32 pw2[48];            // x^(8*2^k)
+};
+struct B2ZipTile { u64 begin; u64 end; };               // bytes [max(begin, end-65536), end) of the input arena
+struct B2ZipEntry { u64 len; u32 tile0; u32 n_tiles; };
+struct B2ZipCopy { u64 src_off; u64 dst_off; u32 len; u32 which; };
+void b2k_make_zipcrc_tables(B2ZipCrcTables *t);
+int b2k_zipcrc(cudaStream_t st, const u8 *d_in, const B2ZipTile *d_tiles, u32 n_tiles, const B2ZipEntry *d_ents, u32 n_entries,
+               const B2ZipCrcTables *d_zt, u32 *d_partial, u32 *d_crc);
+int b2k_zip_gather(cudaStream_t st, const B2ZipCopy *d_items, u32 n, const u8 *d_src0, const u8 *d_src1, u8 *d_dst);

@@ -11,19 +11,6 @@
 #define RLE_THREADS 1024
 #define RLE_BYTES 16
 #define RLE_TILE (RLE_THREADS * RLE_BYTES)
-#define CRC_POLY 0x04C11DB7u
-
-__device__ __forceinline__ u32 gf_mulmod(u32 a, u32 b) {
-  // (a * b) mod P over GF(2); bit i = coefficient of x^i
-  u32 r = 0;
-#pragma unroll 4
-  for (int i = 31; i >= 0; i--) {
-    r = (r << 1) ^ ((r & 0x80000000u) ? CRC_POLY : 0u);
-    if ((b >> i) & 1u) r ^= a;
-  }
-  return r;
-}
-
 __global__ void __launch_bounds__(RLE_THREADS, 1)
 k_rle1(const u8 *__restrict__ in, B2Job *jobs, u8 *__restrict__ text, const B2CrcTables *__restrict__ ct) {
   __shared__ u32 crc_tab[256];
