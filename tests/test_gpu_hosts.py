@@ -78,3 +78,21 @@ def test_batch_of_entries_equals_one_stream_each(enc9):
     outs2 = enc9.encode_batch(entries[:40], None)
     for e, o in zip(entries[:40], outs2):
         assert o == orc.encode_stream(e, 9, -1), e.size
+
+
+def test_cpp_zip_create_mirror(tmp_path):
+    """host/zip_create.hpp (Create_Archive / Add_File / Finish) through host/b2zip.cpp, against the oracle archive."""
+    import io
+    import zipfile
+    exe = tmp_path / "b2zip"
+    pkg = os.path.join(ROOT, "zip-ada_b200")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", os.path.join(pkg, "host", "b2zip.cpp"), "-L" + pkg, "-lb2gpu",
+                           "-Wl,-rpath," + pkg, "-o", str(exe)])
+    files = {"t.txt": datagen.text(120_000, 81).tobytes(), "r.bin": datagen.random_bytes(4_000, 82).tobytes(), "e": b""}
+    for k, v in files.items():
+        (tmp_path / k).write_bytes(v)
+    subprocess.check_call([str(exe), "-eb3", "out.zip", "t.txt", "r.bin", "e"], cwd=str(tmp_path))
+    arc = (tmp_path / "out.zip").read_bytes()
+    assert arc == orc.zip_create(list(files.items()), 9)[0]
+    z = zipfile.ZipFile(io.BytesIO(arc))
+    assert z.testzip() is None and z.read("t.txt") == files["t.txt"]
