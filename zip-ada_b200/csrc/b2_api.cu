@@ -210,7 +210,7 @@ int ensure_batch_workspace(Workspace *w, size_t T, size_t J) {
   B2_TRY(w->d_selpos.ensure(GT));
   B2_TRY(w->d_gpack.ensure(GT * B2_N_TRIPLES + 64)); B2_TRY(w->d_gselcost.ensure(GT * B2_N_TRIPLES + 64));
   B2_TRY(w->d_ehist.ensure(J * B2_N_TRIPLES * B2_MAX_CODERS * 260));
-  B2_TRY(w->d_leaves.ensure((J * B2_N_TRIPLES * B2_MAX_CODERS + 64) * 260)); B2_TRY(w->d_wl.ensure(J * B2_N_TRIPLES * B2_MAX_CODERS + 64));
+  B2_TRY(w->d_leaves.ensure((J * B2_N_TRIPLES * B2_MAX_CODERS + 64) * 260)); B2_TRY(w->d_wl.ensure(J * B2_N_TRIPLES * (B2_MAX_CODERS + 1) + J / 64 + 256));
   B2_TRY(w->d_estat.ensure(J * B2_N_TRIPLES * 2)); B2_TRY(w->d_selcost.ensure(J * B2_N_TRIPLES));
   B2_TRY(w->d_lens.ensure(J * B2_N_TRIPLES * B2_MAX_CODERS * B2_MAX_ALPHA));
   B2_TRY(w->d_cost.ensure(J * B2_N_TRIPLES)); B2_TRY(w->d_low.ensure(J * B2_N_TRIPLES));

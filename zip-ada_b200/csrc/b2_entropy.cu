@@ -26,6 +26,7 @@
 #include "b2_kernels.h"
 
 #define HSTRIDE 260                    // padded alphabet stride of hist / leaves rows
+#define QS_SMALL 100                   // alphabets up to this size are sorted by a launch with less shared memory per warp
 
 // ---------------------------------------------------------------------------------------------
 // Ranking keys (:593-614): key(group) = number of symbols in run_a .. min(EOB-1, sample_width-1)
@@ -162,6 +163,7 @@ struct EntArgs {
   u32 *hist;                            // [p][6][HSTRIDE] raw cluster histograms
   u32 *leaves;                          // interleaved: [(slot / 32)][HSTRIDE][slot % 32], slot = place in the work list
   u32 *wl, *wl_count;                   // work list of this round: q = p * 6 + coder of every coder to (re)build
+  u32 *wl_off;                          // [p] first slot of problem p in the work list (k_ent_wl_scan)
   u8 *lens;                             // [p][6][B2_MAX_ALPHA]
   u32 *stat;                            // [p][2]: defectors of the last sweep, finished flag
   u32 *selcost;                         // [p]
@@ -217,6 +219,43 @@ k_ent_init(EntArgs a) {
   }
 }
 
+// Places of the unfinished problems in the round's work list, in (block, triple) order: neighbours in
+// the list then belong to the same block and share its alphabet size, which the 32 lock-step sorts of a
+// warp need (k_ent_qsort), and finished problems cost nothing.
+#define WL_TILE 2048
+__device__ __forceinline__ u32 wl_items(const EntArgs &a, u32 p) {       // coders problem p adds to the work list
+  const int t = (int)(p % B2_N_TRIPLES);
+  if (p >= a.n_jobs * B2_N_TRIPLES || t >= a.n_triples || a.stat[2 * p + 1] != 0) return 0;
+  int ml, sw, ec;
+  b2_triple(a.level, t, ml, sw, ec);
+  return (u32)ec;
+}
+__global__ void __launch_bounds__(1024)
+k_ent_wl_sum(EntArgs a, u32 *tile_sum) {
+  __shared__ u32 sm[40];
+  const u32 p = blockIdx.x * WL_TILE + 2 * threadIdx.x;
+  u32 total;
+  block_excl_add(wl_items(a, p) + wl_items(a, p + 1), sm, &total);
+  if (threadIdx.x == 0) tile_sum[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(1024)
+k_ent_wl_scan(EntArgs a, const u32 *tile_sum) {
+  __shared__ u32 sm[40];
+  u32 before = 0;
+  for (u32 b = threadIdx.x; b < blockIdx.x; b += 1024) before += tile_sum[b];
+  u32 base;
+  block_excl_add(before, sm, &base);
+  __syncthreads();
+  const u32 P = a.n_jobs * B2_N_TRIPLES;
+  const u32 p = blockIdx.x * WL_TILE + 2 * threadIdx.x;
+  const u32 c0 = wl_items(a, p), c1 = wl_items(a, p + 1);
+  u32 total;
+  const u32 ex = block_excl_add(c0 + c1, sm, &total);
+  if (p < P) a.wl_off[p] = base + ex;
+  if (p + 1 < P) a.wl_off[p + 1] = base + ex + c0;
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *a.wl_count = base + total;
+}
+
 // Define_Descriptors, first half (:643-652) + Avoid_Zeros (:439-462)
 __global__ void __launch_bounds__(256)
 k_ent_hist(EntArgs a) {
@@ -254,9 +293,7 @@ k_ent_hist(EntArgs a) {
   __syncthreads();
   for (u32 i = tid; i < (u32)ec * HSTRIDE; i += 256) hg[i] = (&h[0][0])[i];
   // the coders of this problem join the round's work list (compact: finished problems cost nothing)
-  __shared__ u32 slot0;
-  if (tid == 0) slot0 = atomicAdd(a.wl_count, (u32)ec);
-  __syncthreads();
+  const u32 slot0 = a.wl_off[p];
   const u32 w = warp_id(), l = lane_id();
   if ((int)w < ec) {
     u32 zeroes = 0;
@@ -281,7 +318,7 @@ k_ent_hist(EntArgs a) {
 // (element e of lane l at e*32+l: conflict free).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32)
-k_ent_qsort(EntArgs a, u32 nq, u32 alpha_max) {
+k_ent_qsort(EntArgs a, u32 nq, u32 alpha_max, u32 n_lo, u32 n_hi) {
   extern __shared__ u32 qs_smem[];             // alpha_max x 32 elements, then 16 x 32 stack words
   u32 *s = qs_smem;
   u32 *stk = qs_smem + alpha_max * 32;         // per-lane stack of (first << 16 | count)
@@ -296,7 +333,7 @@ k_ent_qsort(EntArgs a, u32 nq, u32 alpha_max) {
     n = a.jobs[jb].n_used + 2;
   }
   const u32 nmax = __reduce_max_sync(0xffffffffu, n);
-  if (nmax == 0) return;
+  if (nmax <= n_lo || nmax > n_hi) return;     // launched once per alphabet class (shared memory per warp)
   u32 *g = a.leaves + (size_t)blockIdx.x * HSTRIDE * 32;
   for (u32 e = 0; e < nmax; e++) s[e * 32 + l] = g[e * 32 + l];
   __syncwarp();
@@ -372,6 +409,7 @@ k_ent_qsort(EntArgs a, u32 nq, u32 alpha_max) {
 struct LLScratch {
   u32 leaf[B2_MAX_ALPHA + 2];              // (weight << 9) | symbol, sorted
   u32 lvl[2][LL_MAXITEMS];                 // merged weights of two consecutive lists
+  u32 pk[B2_MAX_ALPHA + 2];                // pair sums of the list below
   u32 pkgbits[LL_MAXBITS][LL_BITWORDS];    // bit p set <=> item p of the list is a package
 };
 
@@ -387,16 +425,17 @@ __device__ void ll_package_merge_warp(LLScratch &S, int ns, int max_bits, u8 *le
     u32 *cur = S.lvl[lev & 1];
     const int npk = len_prev >> 1;
     if (l < LL_BITWORDS) S.pkgbits[lev][l] = 0;
+    for (int b = l; b < npk; b += 32) S.pk[b] = prev[2 * b] + prev[2 * b + 1];      // the packages of the list below
     __syncwarp();
     for (int a = l; a < ns; a += 32) {
       const u32 w = S.leaf[a] >> 9;
       int lo = 0, hi = npk;                                 // packages with sum <= w go before this leaf
-      while (lo < hi) { int mid = (lo + hi) >> 1; if (prev[2 * mid] + prev[2 * mid + 1] <= w) lo = mid + 1; else hi = mid; }
+      while (lo < hi) { int mid = (lo + hi) >> 1; if (S.pk[mid] <= w) lo = mid + 1; else hi = mid; }
       const int pos = a + lo;
       if (pos < need) cur[pos] = w;
     }
     for (int b = l; b < npk; b += 32) {
-      const u32 pk = prev[2 * b] + prev[2 * b + 1];
+      const u32 pk = S.pk[b];
       int lo = 0, hi = ns;                                  // leaves with weight < sum go before this package
       while (lo < hi) { int mid = (lo + hi) >> 1; if ((S.leaf[mid] >> 9) < pk) lo = mid + 1; else hi = mid; }
       const int pos = b + lo;
@@ -721,22 +760,31 @@ int b2k_entropy(cudaStream_t st, B2Job *d_jobs, u32 n_jobs, u32 max_groups_per_j
   k_rank_sort<<<n_jobs * 2, 32, sort_smem, st>>>(d_jobs, d_rank3, d_rank4);
   EntArgs a;
   a.jobs = d_jobs; a.mtf = d_mtf; a.ghist = d_ghist; a.gdist = d_gdist; a.rank3 = d_rank3; a.rank4 = d_rank4; a.sel = d_sel; a.selprev = d_selprev;
-  a.gpack = d_gpack; a.gselcost = d_gselcost; a.hist = d_hist; a.leaves = d_leaves; a.wl = d_wl; a.wl_count = d_activated + 1; a.lens = d_lens; a.stat = d_stat; a.selcost = d_selcost;
+  a.gpack = d_gpack; a.gselcost = d_gselcost; a.hist = d_hist; a.leaves = d_leaves; a.wl = d_wl; a.wl_count = d_activated + 1; a.wl_off = d_wl + (size_t)n_jobs * B2_N_TRIPLES * B2_MAX_CODERS + 32; a.lens = d_lens; a.stat = d_stat; a.selcost = d_selcost;
   a.cost_all = d_cost; a.low_all = d_low; a.total_groups = total_groups; a.level = level; a.n_triples = n_triples;
   a.n_jobs = n_jobs;
   const dim3 grid(n_triples, n_jobs);
   const u32 nq = n_jobs * B2_N_TRIPLES * B2_MAX_CODERS;
+  const u32 wl_tiles = (n_jobs * B2_N_TRIPLES + WL_TILE - 1) / WL_TILE;
+  u32 *wl_tile_sum = a.wl_off + (size_t)n_jobs * B2_N_TRIPLES + 32;
   k_ent_init<<<grid, 256, 0, st>>>(a);
   *launches += 4;
   for (int phase = 0; phase < 4; phase++) {
     for (int it = 0; it <= 10; it++) {
       // iterations 1..10 (:793-802); round 10 is the extra Define_Descriptors for triples still moving (:803-807)
-      B2_CUDA_CHECK(cudaMemsetAsync(a.wl_count, 0, sizeof(u32), st));
+      k_ent_wl_sum<<<wl_tiles, 1024, 0, st>>>(a, wl_tile_sum);
+      k_ent_wl_scan<<<wl_tiles, 1024, 0, st>>>(a, wl_tile_sum);
       k_ent_hist<<<grid, 256, 0, st>>>(a);
-      k_ent_qsort<<<(nq + 31) / 32, 32, qs_smem, st>>>(a, nq, max_alpha);
+      if (max_alpha > QS_SMALL) {             // small alphabets keep their high occupancy next to large ones
+        k_ent_qsort<<<(nq + 31) / 32, 32, ((size_t)QS_SMALL + 16) * 32 * 4, st>>>(a, nq, QS_SMALL, 0, QS_SMALL);
+        k_ent_qsort<<<(nq + 31) / 32, 32, qs_smem, st>>>(a, nq, max_alpha, QS_SMALL, HSTRIDE);
+        *launches += 1;
+      } else {
+        k_ent_qsort<<<(nq + 31) / 32, 32, qs_smem, st>>>(a, nq, max_alpha, 0, HSTRIDE);
+      }
       k_ent_pm<<<(nq + PM_WARPS - 1) / PM_WARPS, 32 * PM_WARPS, 0, st>>>(a, nq);
       k_ent_cost<<<grid, 256, 0, st>>>(a);
-      *launches += 4;
+      *launches += 6;
       if (it < 10) { k_ent_sweep<<<n_jobs, 32, 0, st>>>(a); *launches += 1; }
     }
     k_ent_selcost<<<n_jobs, 32, 0, st>>>(a);
