@@ -427,22 +427,32 @@ __device__ void ll_package_merge_warp(LLScratch &S, int ns, int max_bits, u8 *le
     if (l < LL_BITWORDS) S.pkgbits[lev][l] = 0;
     for (int b = l; b < npk; b += 32) S.pk[b] = prev[2 * b] + prev[2 * b + 1];      // the packages of the list below
     __syncwarp();
+    bool changed = false;
     for (int a = l; a < ns; a += 32) {
       const u32 w = S.leaf[a] >> 9;
       int lo = 0, hi = npk;                                 // packages with sum <= w go before this leaf
       while (lo < hi) { int mid = (lo + hi) >> 1; if (S.pk[mid] <= w) lo = mid + 1; else hi = mid; }
       const int pos = a + lo;
-      if (pos < need) cur[pos] = w;
+      if (pos < need) { changed |= (pos >= len_prev) || prev[pos] != w; cur[pos] = w; }
     }
     for (int b = l; b < npk; b += 32) {
       const u32 pk = S.pk[b];
       int lo = 0, hi = ns;                                  // leaves with weight < sum go before this package
       while (lo < hi) { int mid = (lo + hi) >> 1; if ((S.leaf[mid] >> 9) < pk) lo = mid + 1; else hi = mid; }
       const int pos = b + lo;
-      if (pos < need) { cur[pos] = pk; atomicOr(&S.pkgbits[lev][pos >> 5], 1u << (pos & 31)); }
+      if (pos < need) { changed |= (pos >= len_prev) || prev[pos] != pk; cur[pos] = pk; atomicOr(&S.pkgbits[lev][pos >> 5], 1u << (pos & 31)); }
     }
-    len_prev = min(need, ns + npk);
+    const int len_cur = min(need, ns + npk);
+    changed = __any_sync(0xffffffffu, changed) || len_cur != len_prev;
+    len_prev = len_cur;
     __syncwarp();
+    if (!changed) {
+      // the list repeats the one below: every list above is built from the same packages, hence equal
+      // to this one, items and package flags alike
+      if (l < LL_BITWORDS) { const u32 v = S.pkgbits[lev][l]; for (int q = lev + 1; q < max_bits; q++) S.pkgbits[q][l] = v; }
+      __syncwarp();
+      break;
+    }
   }
   // walk down from the last list
   u32 cnt[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
