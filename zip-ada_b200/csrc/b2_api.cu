@@ -75,6 +75,7 @@ struct Workspace {
   DevBuf<u64> d_keysA, d_keysB;
   DevBuf<u32> d_valsA, d_valsB, d_rank, d_grp, d_slotA, d_slotB, d_sa, d_tile_cnt;
   DevBuf<B2SortTile> d_tiles, d_mtiles, d_msegs;
+  DevBuf<B2SortTileRR> d_tiles_rr;
   DevBuf<B2SortJob> d_sj;
   DevBuf<u32> d_hist, d_digit_base;
   DevBuf<i32> d_tile_head, d_carry;
@@ -100,7 +101,7 @@ struct Workspace {
   void release() {
     d_scalars.release(); d_jobs.release(); d_text.release(); d_bwt.release(); d_idx.release(); d_m16.release();
     d_m256.release(); d_tilemask.release(); d_keysA.release(); d_keysB.release(); d_valsA.release(); d_valsB.release();
-    d_rank.release(); d_grp.release(); d_slotA.release(); d_slotB.release(); d_sa.release(); d_tile_cnt.release(); d_tiles.release(); d_mtiles.release(); d_msegs.release(); d_sj.release(); d_hist.release();
+    d_rank.release(); d_grp.release(); d_slotA.release(); d_slotB.release(); d_sa.release(); d_tile_cnt.release(); d_tiles.release(); d_tiles_rr.release(); d_mtiles.release(); d_msegs.release(); d_sj.release(); d_hist.release();
     d_digit_base.release(); d_tile_head.release(); d_carry.release(); d_unsorted.release(); d_mtf.release(); d_ghist.release(); d_gdist.release();
     d_rank3.release(); d_rank4.release(); d_sel.release(); d_selprev.release(); d_selpos.release(); d_lens.release();
     d_ehist.release(); d_leaves.release(); d_wl.release(); d_estat.release(); d_selcost.release(); d_gpack.release(); d_gselcost.release(); d_cost.release();
@@ -198,10 +199,10 @@ int ensure_batch_workspace(Workspace *w, size_t T, size_t J) {
   B2_TRY(w->d_valsA.ensure(T)); B2_TRY(w->d_valsB.ensure(T));
   B2_TRY(w->d_rank.ensure(T)); B2_TRY(w->d_grp.ensure(T));
   B2_TRY(w->d_slotA.ensure(T)); B2_TRY(w->d_slotB.ensure(T)); B2_TRY(w->d_sa.ensure(T)); B2_TRY(w->d_tile_cnt.ensure(max_tiles));
-  B2_TRY(w->d_tiles.ensure(max_tiles)); B2_TRY(w->d_mtiles.ensure(max_mtiles));
+  B2_TRY(w->d_tiles.ensure(max_tiles)); B2_TRY(w->d_tiles_rr.ensure(max_tiles)); B2_TRY(w->d_mtiles.ensure(max_mtiles));
   B2_TRY(w->d_tilemask.ensure(max_mtiles * 8)); B2_TRY(w->d_msegs.ensure(T / B2_MTF_SEG + J + 8));
   B2_TRY(w->d_sj.ensure(J));
-  B2_TRY(w->d_hist.ensure(max_tiles * 256)); B2_TRY(w->d_digit_base.ensure(J * 256));
+  B2_TRY(w->d_hist.ensure(max_tiles * 256)); B2_TRY(w->d_digit_base.ensure(J * 8 * 256 + 256));
   B2_TRY(w->d_tile_head.ensure(max_tiles)); B2_TRY(w->d_carry.ensure(max_tiles));
   B2_TRY(w->d_unsorted.ensure(J));
   B2_TRY(w->d_mtf.ensure(T + 16 * J + 64)); B2_TRY(w->d_ghist.ensure(T + 16 * J + 64));
@@ -281,7 +282,7 @@ int run_batch(b2_encoder *e, Workspace *w, const u8 *d_in, std::vector<B2Job> &j
     cx.keysA = w->d_keysA.p; cx.keysB = w->d_keysB.p; cx.valsA = w->d_valsA.p; cx.valsB = w->d_valsB.p;
     cx.rank = w->d_rank.p; cx.grp = w->d_grp.p; cx.d_tiles = w->d_tiles.p; cx.d_sj = w->d_sj.p;
     cx.slotA = w->d_slotA.p; cx.slotB = w->d_slotB.p; cx.sa_full = w->d_sa.p; cx.d_tile_cnt = w->d_tile_cnt.p;
-    cx.d_hist = w->d_hist.p; cx.d_digit_base = w->d_digit_base.p; cx.d_tile_head = w->d_tile_head.p; cx.d_carry = w->d_carry.p;
+    cx.d_hist = w->d_hist.p; cx.d_digit_base = w->d_digit_base.p; cx.d_tiles_rr = w->d_tiles_rr.p; cx.d_ticket = w->d_digit_base.p + w->d_digit_base.cap - 256; cx.d_tile_head = w->d_tile_head.p; cx.d_carry = w->d_carry.p;
     cx.d_unsorted = w->d_unsorted.p; cx.h_unsorted = w->h_unsorted;
     cx.max_tiles = w->d_tiles.cap; cx.max_jobs = w->d_sj.cap; cx.timing = e->timing >= 1;
     cx.stats = w->sort_stats;

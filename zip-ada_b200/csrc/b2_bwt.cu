@@ -55,45 +55,53 @@ k_keys0(const B2SortTile *__restrict__ tiles, const B2Job *__restrict__ jobs, co
   }
 }
 
-// ---- histogram of one digit per tile -----------------------------------------------------------
+// ---- digit histograms of every pass of a round, per block, from one read of the keys -----------------
+// (LSD passes only permute the keys of a block, so the totals of all digits are known up front.)
+// A CTA walks HG_TILES consecutive tiles and flushes its counts when the block changes.
+#define HG_TILES 8
+#define ST_MAXPASS 8
 __global__ void __launch_bounds__(ST_THREADS)
-k_hist(const B2SortTile *__restrict__ tiles, const B2Job *__restrict__ jobs, const u64 *__restrict__ keys,
-       int shift, u32 *__restrict__ hist) {
-  __shared__ u32 h[256];
-  const B2SortTile tl = tiles[blockIdx.x];
-  const B2Job &job = jobs[tl.job];
-  const u32 n = job.na;
-  const u64 *kp = keys + job.pos_off;
-  if (threadIdx.x < 256) h[threadIdx.x] = 0;
+k_hist_all(const B2SortTile *__restrict__ tiles, u32 n_tiles, const B2Job *__restrict__ jobs, const u64 *__restrict__ keys,
+           int npass, u32 *__restrict__ jobhist) {
+  __shared__ u32 h[ST_MAXPASS][256];
+  const u32 tid = threadIdx.x;
+  for (int p = 0; p < npass; p++) h[p][tid] = 0;
   __syncthreads();
+  const u32 t0 = blockIdx.x * HG_TILES, t1 = min(n_tiles, t0 + HG_TILES);
+  u32 cur_job = tiles[t0].job;
+  for (u32 t = t0; t < t1; t++) {
+    const B2SortTile tl = tiles[t];
+    if (tl.job != cur_job) {
+      __syncthreads();
+      for (int p = 0; p < npass; p++) { const u32 c = h[p][tid]; if (c) atomicAdd(&jobhist[((size_t)cur_job * ST_MAXPASS + p) * 256 + tid], c); h[p][tid] = 0; }
+      __syncthreads();
+      cur_job = tl.job;
+    }
+    const B2Job &job = jobs[tl.job];
+    const u32 n = job.na;
+    const u64 *kp = keys + job.pos_off;
 #pragma unroll 4
-  for (int k = 0; k < ST_ITEMS; k++) {
-    u32 i = tl.start + threadIdx.x + k * ST_THREADS;
-    if (i < n) atomicAdd(&h[(u32)(kp[i] >> shift) & 255u], 1u);
+    for (int k = 0; k < ST_ITEMS; k++) {
+      const u32 i = tl.start + tid + k * ST_THREADS;
+      if (i < n) {
+        const u64 key = kp[i];
+        for (int p = 0; p < npass; p++) atomicAdd(&h[p][(u32)(key >> (8 * p)) & 255u], 1u);
+      }
+    }
   }
   __syncthreads();
-  if (threadIdx.x < 256) hist[(size_t)blockIdx.x * 256 + threadIdx.x] = h[threadIdx.x];
+  for (int p = 0; p < npass; p++) { const u32 c = h[p][tid]; if (c) atomicAdd(&jobhist[((size_t)cur_job * ST_MAXPASS + p) * 256 + tid], c); }
 }
 
-// ---- per-block exclusive scan over (digit major, tile minor) ------------------------------------
+// ---- per (block, pass): exclusive scan over the digits, in place ---------------------------------------
 __global__ void __launch_bounds__(256)
-k_scan(const B2SortJob *__restrict__ sj, u32 *__restrict__ hist, u32 *__restrict__ digit_base) {
+k_scan_jobs(const B2SortJob *__restrict__ sj, u32 *__restrict__ jobhist) {
   __shared__ u32 sm[40];
   const B2SortJob s = sj[blockIdx.x];
-  const u32 d = threadIdx.x;
-  u32 *h = hist + (size_t)s.tile0 * 256 + d;
-  u32 total = 0;
-  u32 t = 0;
-  for (; t + 8 <= s.ntiles; t += 8) {             // 8 independent loads in flight per thread
-    u32 c[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) c[k] = h[(size_t)(t + k) * 256];
-#pragma unroll
-    for (int k = 0; k < 8; k++) { h[(size_t)(t + k) * 256] = total; total += c[k]; }
-  }
-  for (; t < s.ntiles; t++) { u32 c = h[(size_t)t * 256]; h[(size_t)t * 256] = total; total += c; }
-  u32 base = block_excl_add(total, sm, nullptr);
-  digit_base[(size_t)s.job * 256 + d] = base;     // added by the scatter kernel
+  u32 *h = jobhist + ((size_t)s.job * ST_MAXPASS + blockIdx.y) * 256;
+  const u32 c = h[threadIdx.x];
+  const u32 base = block_excl_add(c, sm, nullptr);
+  h[threadIdx.x] = base;
 }
 
 // ---- stable scatter of one digit ---------------------------------------------------------------
@@ -106,21 +114,39 @@ struct ScatterSmem {
   u32 scan[40];
 };
 
+// Tile states of the decoupled look-back: [31:30] 1 = this tile's count, 2 = count of this tile and all
+// tiles of the block before it; [29:22] pass tag (states of other passes read as "not there yet");
+// [21:0] the count (a block has at most 1 125 000 rows).
+#define LB_AGG 0x40000000u
+#define LB_INC 0x80000000u
+// tile states are single self-describing words: relaxed device-scope accesses are all that is needed
+__device__ __forceinline__ void lb_store(u32 *p, u32 v) { asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ u32 lb_load(const u32 *p) { u32 v; asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+
 __global__ void __launch_bounds__(ST_THREADS, 6)
-k_scatter(const B2SortTile *__restrict__ tiles, const B2Job *__restrict__ jobs,
+k_scatter(const B2SortTileRR *__restrict__ tiles, const B2Job *__restrict__ jobs,
           const u64 *__restrict__ keys_in, const u32 *__restrict__ vals_in,
-          u64 *__restrict__ keys_out, u32 *__restrict__ vals_out, int shift, const u32 *__restrict__ hist,
-          const u32 *__restrict__ digit_base) {
+          u64 *__restrict__ keys_out, u32 *__restrict__ vals_out, int shift, u32 *__restrict__ state,
+          const u32 *__restrict__ jobhist, u32 *__restrict__ lb_error, u32 tag) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ScatterSmem &S = *reinterpret_cast<ScatterSmem *>(smem_raw);
-  const B2SortTile tl = tiles[blockIdx.x];
+  const u32 tid = threadIdx.x, w = warp_id(), l = lane_id();
+  // Tiles are dispatched in blockIdx order, and that order interleaves the blocks of a group (tile k of
+  // every block, then tile k + 1 of every block): the tile before mine in my block was dispatched a whole
+  // row of blocks ago and has usually published its inclusive counts, so the look-back below is one early
+  // load and no wait.  (A same-address ticket counter costs more than the look-back itself; the wait is
+  // bounded and reports through *lb_error instead of hanging should a predecessor never show up.)
+  for (int i = tid; i < ST_WARPS * 256; i += ST_THREADS) (&S.warp_cnt[0][0])[i] = 0;
+  __syncthreads();
+  const u32 tix = blockIdx.x;
+  const B2SortTileRR tl = tiles[tix];
   const B2Job &job = jobs[tl.job];
   const u32 n = job.na, off = job.pos_off;
-  const u32 tid = threadIdx.x, w = warp_id(), l = lane_id();
   const u32 lt_mask = (1u << l) - 1u;
-  for (int i = tid; i < ST_WARPS * 256; i += ST_THREADS) (&S.warp_cnt[0][0])[i] = 0;
-  if (tid < 256) S.g_off[tid] = hist[(size_t)blockIdx.x * 256 + tid] + digit_base[(size_t)tl.job * 256 + tid];
-  __syncthreads();
+  // early look at the state of the tile before mine (usually final by now) and at my digit's base
+  S.g_off[tid] = jobhist[((size_t)tl.job * ST_MAXPASS + (u32)(shift >> 3)) * 256 + tid];
+  u32 v_early = LB_INC | tag;
+  if (tl.prev != 0xFFFFFFFFu) v_early = lb_load(state + (size_t)tl.prev * 256 + tid);   // only trusted when final
   u64 key[ST_ITEMS];
   u32 rk[ST_ITEMS];   // rank within (warp, digit) | digit << 16 ; 0xFFFFFFFF = invalid
   const u32 wbase = tl.start + w * ST_WCHUNK;
@@ -147,12 +173,37 @@ k_scatter(const B2SortTile *__restrict__ tiles, const B2Job *__restrict__ jobs,
   // per digit: exclusive over warps, tile count
   {
     u32 run = 0;
-    if (tid < 256) {
 #pragma unroll
-      for (int ww = 0; ww < ST_WARPS; ww++) { u32 c = S.warp_cnt[ww][tid]; S.warp_cnt[ww][tid] = run; run += c; }
-    }
+    for (int ww = 0; ww < ST_WARPS; ww++) { u32 c = S.warp_cnt[ww][tid]; S.warp_cnt[ww][tid] = run; run += c; }
     u32 ts = block_excl_add(run, S.scan, nullptr);
-    if (tid < 256) S.tile_start[tid] = ts;
+    S.tile_start[tid] = ts;
+    // rows of my digit in the tiles of this block before mine: decoupled look-back, one digit per thread
+    {
+      u32 *stt = state + (size_t)tix * 256 + tid;
+      u32 excl = 0;
+      if (tl.prev == 0xFFFFFFFFu) {
+        lb_store(stt, LB_INC | tag | run);
+      } else {
+        if ((v_early & 0xFFC00000u) == (LB_INC | tag)) {
+          excl = v_early & 0x3FFFFFu;                       // the usual case: no wait, no AGG state needed
+        } else {
+          lb_store(stt, LB_AGG | tag | run);
+          u32 p = tl.prev;
+          while (p != 0xFFFFFFFFu) {
+            const u32 *pp = state + (size_t)p * 256 + tid;
+            u32 v, spins = 0;
+            do { v = lb_load(pp); } while (((v & 0x3FC00000u) != tag || (v >> 30) == 0u) && ++spins < (1u << 24));
+            if (spins >= (1u << 24)) { *lb_error = 1u; break; }
+            excl += v & 0x3FFFFFu;
+            if (v & LB_INC) break;
+            p = tiles[p].prev;
+          }
+        }
+        lb_store(stt, LB_INC | tag | (excl + run));
+      }
+      // first place of my digit's rows of this tile in the block, minus their place in the staged tile
+      S.g_off[tid] += excl - ts;
+    }
   }
   __syncthreads();
   // the rotation indices are only needed now: fetching them late keeps the register count low
@@ -180,7 +231,7 @@ k_scatter(const B2SortTile *__restrict__ tiles, const B2Job *__restrict__ jobs,
     if (q < cnt) {
       u64 kk = S.keys[q];
       u32 d = (u32)(kk >> shift) & 255u;
-      u32 dst = off + S.g_off[d] + (q - S.tile_start[d]);
+      u32 dst = off + S.g_off[d] + q;
       keys_out[dst] = kk;
       vals_out[dst] = S.vals[q];
     }
@@ -349,6 +400,8 @@ k_bwt_out(const B2SortTile *__restrict__ tiles, B2Job *jobs, const u32 *__restri
 // =============================================================================================
 // Host driver
 // =============================================================================================
+#include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 static int build_tiles(const std::vector<u32> &job_ids, const std::vector<u32> &job_n,
@@ -364,6 +417,23 @@ static int build_tiles(const std::vector<u32> &job_ids, const std::vector<u32> &
   return 0;
 }
 
+// The scatter's dispatch order: blocks are taken in groups of `group`; inside a group, tile k of every
+// block, then tile k + 1 of every block, ...  The tile before mine in my block is then `group` tiles
+// ahead of me (far enough to have published its counts), while the output runs of a block still arrive
+// close enough in time for the L2 to merge them into full lines.
+static void build_tiles_rr(const std::vector<B2SortJob> &sj, std::vector<B2SortTileRR> &rr, size_t group) {
+  rr.clear();
+  std::vector<u32> last(sj.size(), 0xFFFFFFFFu);
+  for (size_t g0 = 0; g0 < sj.size(); g0 += group) {
+    const size_t g1 = std::min(sj.size(), g0 + group);
+    u32 max_nt = 0;
+    for (size_t j = g0; j < g1; j++) max_nt = std::max(max_nt, sj[j].ntiles);
+    for (u32 k = 0; k < max_nt; k++)
+      for (size_t j = g0; j < g1; j++)
+        if (sj[j].ntiles > k) { const u32 pos = (u32)rr.size(); rr.push_back(B2SortTileRR{sj[j].job, k * ST_TILE, last[j], 0}); last[j] = pos; }
+  }
+}
+
 struct EvPair { cudaEvent_t a, b; };
 
 // job_n[k] = post-RLE1 size of block job_ids[k]; the device copies have na == n on entry.
@@ -372,6 +442,9 @@ int b2k_bwt_batch(B2SortCtx *cx, cudaStream_t st, B2Job *d_jobs, const std::vect
   // per device and cheap; set on every call so that handles on several devices / threads all have it
   B2_CUDA_CHECK(cudaFuncSetAttribute(k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
   std::vector<B2SortTile> tiles;
+  std::vector<B2SortTileRR> tiles_rr;
+  size_t rr_group = 128;
+  if (const char *e = getenv("B2GPU_RR_GROUP")) { long v = atol(e); if (v >= 1) rr_group = (size_t)v; }
   std::vector<B2SortJob> sj;
   std::vector<u32> ids, ns, nas;             // active blocks: id, size, active rows
   for (size_t k = 0; k < job_ids.size(); k++) if (job_n[k] > 0) { ids.push_back(job_ids[k]); ns.push_back(job_n[k]); }
@@ -388,13 +461,37 @@ int b2k_bwt_batch(B2SortCtx *cx, cudaStream_t st, B2Job *d_jobs, const std::vect
     B2_CUDA_CHECK(cudaMemcpyAsync(cx->d_sj, sj.data(), sj.size() * sizeof(B2SortJob), cudaMemcpyHostToDevice, st));
     return 0;
   };
+  auto upload_rr = [&]() -> int {
+    build_tiles_rr(sj, tiles_rr, rr_group);
+    B2_CUDA_CHECK(cudaMemcpyAsync(cx->d_tiles_rr, tiles_rr.data(), tiles_rr.size() * sizeof(B2SortTileRR), cudaMemcpyHostToDevice, st));
+    return 0;
+  };
+  // digit totals of all passes of a round (one read of the keys), then their exclusive scans
+  u32 max_job = 0;
+  for (u32 id : ids) max_job = std::max(max_job, id);
+  auto round_hist = [&](int npass) -> int {
+    u32 nt = (u32)tiles.size();
+    B2_CUDA_CHECK(cudaMemsetAsync(cx->d_digit_base, 0, ((size_t)max_job + 1) * ST_MAXPASS * 256 * sizeof(u32), st));
+    k_hist_all<<<(nt + HG_TILES - 1) / HG_TILES, ST_THREADS, 0, st>>>(cx->d_tiles, nt, d_jobs, kA, npass, cx->d_digit_base);
+    k_scan_jobs<<<dim3((u32)sj.size(), (u32)npass), 256, 0, st>>>(cx->d_sj, cx->d_digit_base);
+    B2_CUDA_CHECK(cudaGetLastError());
+    cx->stats.launches += 2;
+    return 0;
+  };
+  const size_t nt0 = tiles.size();       // later rounds never have more tiles than the first
+  u32 pass_no = 0;                       // tag of the look-back states; the state array is cleared when it wraps
   auto radix_pass = [&](int shift) -> int {
     u32 nt = (u32)tiles.size();
-    k_hist<<<nt, ST_THREADS, 0, st>>>(cx->d_tiles, d_jobs, kA, shift, cx->d_hist);
-    k_scan<<<(u32)sj.size(), 256, 0, st>>>(cx->d_sj, cx->d_hist, cx->d_digit_base);
+    if ((pass_no & 255u) == 0) {
+      B2_CUDA_CHECK(cudaMemsetAsync(cx->d_hist, 0, nt0 * 256 * sizeof(u32), st));
+      B2_CUDA_CHECK(cudaMemsetAsync(cx->d_ticket, 0, sizeof(u32), st));
+    }
+    const u32 tag = (pass_no & 255u) << 22;
     EvPair ev{nullptr, nullptr};
     if (cx->timing) { cudaEventCreate(&ev.a); cudaEventCreate(&ev.b); cudaEventRecord(ev.a, st); }
-    k_scatter<<<nt, ST_THREADS, sizeof(ScatterSmem), st>>>(cx->d_tiles, d_jobs, kA, vA, kB, vB, shift, cx->d_hist, cx->d_digit_base);
+    k_scatter<<<(u32)tiles_rr.size(), ST_THREADS, sizeof(ScatterSmem), st>>>(cx->d_tiles_rr, d_jobs, kA, vA, kB, vB, shift, cx->d_hist, cx->d_digit_base,
+                                                           cx->d_ticket, tag);
+    pass_no++;
     if (cx->timing) { cudaEventRecord(ev.b, st); evs.push_back(ev); }
     B2_CUDA_CHECK(cudaGetLastError());
     std::swap(kA, kB); std::swap(vA, vB);
@@ -402,7 +499,7 @@ int b2k_bwt_batch(B2SortCtx *cx, cudaStream_t st, B2Job *d_jobs, const std::vect
     for (u32 x : nas) el += x;
     cx->stats.scatter_launches++;
     cx->stats.scatter_elems += el;
-    cx->stats.launches += 3;
+    cx->stats.launches += 1;
     return 0;
   };
   // heads -> ranks -> compaction; afterwards vA holds the compacted rotation indices, slotA their slots
@@ -417,7 +514,10 @@ int b2k_bwt_batch(B2SortCtx *cx, cudaStream_t st, B2Job *d_jobs, const std::vect
     B2_CUDA_CHECK(cudaGetLastError());
     std::swap(vA, vB); std::swap(slotA, slotB);
     B2_CUDA_CHECK(cudaMemcpyAsync(cx->h_unsorted, cx->d_unsorted, nj * sizeof(u32), cudaMemcpyDeviceToHost, st));
+    u32 lb_err = 0;
+    B2_CUDA_CHECK(cudaMemcpyAsync(&lb_err, cx->d_ticket, sizeof(u32), cudaMemcpyDeviceToHost, st));
     B2_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (lb_err) { b2_set_error(__FILE__, __LINE__, "radix scatter: a tile's predecessor never published its counts"); return 11; }
     return 0;
   };
 
@@ -429,6 +529,8 @@ int b2k_bwt_batch(B2SortCtx *cx, cudaStream_t st, B2Job *d_jobs, const std::vect
   }
   k_keys0<<<(u32)tiles.size(), ST_THREADS, 0, st>>>(cx->d_tiles, d_jobs, d_text, kA, vA);
   cx->stats.launches += 1;
+  if ((rc = upload_rr())) return rc;
+  if ((rc = round_hist(8))) return rc;
   for (int p = 0; p < 8; p++) if ((rc = radix_pass(8 * p))) return rc;
   if ((rc = ranks(true))) return rc;
   cx->stats.rounds++;
@@ -458,6 +560,8 @@ int b2k_bwt_batch(B2SortCtx *cx, cudaStream_t st, B2Job *d_jobs, const std::vect
     }
     k_keys<<<(u32)tiles.size(), ST_THREADS, 0, st>>>(cx->d_tiles, d_jobs, vA, cx->grp, cx->rank, kA, (u32)(reflect));
     cx->stats.launches += 1;
+    if ((rc = upload_rr())) return rc;
+    if ((rc = round_hist(5))) return rc;
     for (int p = 0; p < 5; p++) if ((rc = radix_pass(8 * p))) return rc;
     if ((rc = ranks(false))) return rc;
     cx->stats.rounds++;

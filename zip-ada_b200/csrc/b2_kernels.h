@@ -14,6 +14,7 @@ struct B2CrcTables {
 };
 
 struct B2SortTile { u32 job; u32 start; };
+struct B2SortTileRR { u32 job; u32 start; u32 prev; u32 pad; };   // scatter order: prev = place of the block's tile before this one
 
 // statistics of the BWT sort for the roofline report
 struct B2SortStats {
@@ -49,7 +50,9 @@ struct B2SortCtx {
   u32 *slotA, *slotB, *sa_full, *d_tile_cnt;
   B2SortTile *d_tiles;
   B2SortJob *d_sj;
-  u32 *d_hist, *d_digit_base;
+  u32 *d_hist, *d_digit_base;    // look-back tile states [tile][256]; digit bases [block][8 passes][256]
+  B2SortTileRR *d_tiles_rr;
+  u32 *d_ticket;                 // error flag of the look-back
   i32 *d_tile_head, *d_carry;
   u32 *d_unsorted, *h_unsorted;
   size_t max_tiles, max_jobs;
