@@ -279,7 +279,7 @@ def main():
     alg_bytes = 24.0 * st.scatter_elems          # 8 B key + 4 B index, read once + written once
     achieved = alg_bytes / (st.scatter_ms / 1000.0) / 1e9 if st.scatter_ms > 0 else 0.0
     tr = ncu_traffic()
-    roofline = {"bound": "hbm", "kernel": "k_scatter (LSD radix pass of the BWT rotation sort)",
+    roofline = {"bound": "hbm", "kernel": "k_scatter (one LSD radix pass of the BWT rotation sort: ranking, decoupled look-back and scatter in one kernel)",
                 "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                 "peak_source": peak_src, "traffic": tr.get("dram_bytes_per_launch") if tr else None,
                 "algorithmic_bytes_per_launch": alg_bytes / max(1, st.scatter_launches),

@@ -286,6 +286,12 @@ int run_batch(b2_encoder *e, Workspace *w, const u8 *d_in, std::vector<B2Job> &j
     cx.d_unsorted = w->d_unsorted.p; cx.h_unsorted = w->h_unsorted;
     cx.max_tiles = w->d_tiles.cap; cx.max_jobs = w->d_sj.cap; cx.timing = e->timing >= 1;
     cx.stats = w->sort_stats;
+    {
+      u32 max_used = 1;
+      for (u32 j = 0; j < J; j++) max_used = std::max(max_used, w->batch_jobs[j].n_used);
+      cx.sym_bits = 1;
+      while ((1u << cx.sym_bits) < max_used) cx.sym_bits++;
+    }
     int rc = b2k_bwt_batch(&cx, st, w->d_jobs.p, ids, ns, w->d_text.p, w->d_bwt.p);
     w->sort_stats = cx.stats;
     if (rc) return rc;

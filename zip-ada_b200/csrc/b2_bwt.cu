@@ -29,13 +29,27 @@
 #define ST_WCHUNK (32 * ST_ITEMS)      // elements per warp
 
 // ---- round-0 keys: first 8 bytes of each rotation, cyclic ------------------------------------
+// The bytes are replaced by their rank among the bytes in use (order preserving, so the order of the
+// rotations is unchanged) and packed with `bits` bits each: a batch whose blocks all use at most 2^bits
+// distinct bytes sorts round 0 in `bits` radix passes instead of 8.  bits = 8 keeps the bytes as they are.
 __global__ void __launch_bounds__(ST_THREADS)
 k_keys0(const B2SortTile *__restrict__ tiles, const B2Job *__restrict__ jobs, const u8 *__restrict__ text,
-        u64 *__restrict__ keys, u32 *__restrict__ vals) {
+        u64 *__restrict__ keys, u32 *__restrict__ vals, int bits) {
+  __shared__ u8 code[256];
   const B2SortTile tl = tiles[blockIdx.x];
   const B2Job &job = jobs[tl.job];
   const u32 n = job.n, off = job.pos_off;
   const u8 *tx = text + off;
+  {
+    const u32 t = threadIdx.x, wd = t >> 5;
+    u32 c = t;
+    if (bits < 8) {
+      c = __popc(job.in_use[wd] & ((1u << (t & 31u)) - 1u));
+      for (u32 q = 0; q < wd; q++) c += __popc(job.in_use[q]);
+    }
+    code[t] = (u8)c;
+  }
+  __syncthreads();
 #pragma unroll 4
   for (int k = 0; k < ST_ITEMS; k++) {
     u32 i = tl.start + threadIdx.x + k * ST_THREADS;
@@ -43,11 +57,11 @@ k_keys0(const B2SortTile *__restrict__ tiles, const B2Job *__restrict__ jobs, co
       u64 key = 0;
       if (i + 8 <= n) {
 #pragma unroll
-        for (int j = 0; j < 8; j++) key = (key << 8) | tx[i + j];
+        for (int j = 0; j < 8; j++) key = (key << bits) | code[tx[i + j]];
       } else {
         u32 p = i;
 #pragma unroll
-        for (int j = 0; j < 8; j++) { key = (key << 8) | tx[p]; p++; if (p >= n) p = 0; }
+        for (int j = 0; j < 8; j++) { key = (key << bits) | code[tx[p]]; p++; if (p >= n) p = 0; }
       }
       keys[off + i] = key;
       vals[off + i] = i;
@@ -527,11 +541,12 @@ int b2k_bwt_batch(B2SortCtx *cx, cudaStream_t st, B2Job *d_jobs, const std::vect
     u64 el = 0; for (u32 x : ns) el += x;
     cx->stats.sorted_elems_round0 += el;
   }
-  k_keys0<<<(u32)tiles.size(), ST_THREADS, 0, st>>>(cx->d_tiles, d_jobs, d_text, kA, vA);
+  const int sym_bits = (cx->sym_bits >= 1 && cx->sym_bits <= 8) ? cx->sym_bits : 8;   // 8 characters of sym_bits bits = sym_bits passes
+  k_keys0<<<(u32)tiles.size(), ST_THREADS, 0, st>>>(cx->d_tiles, d_jobs, d_text, kA, vA, sym_bits);
   cx->stats.launches += 1;
   if ((rc = upload_rr())) return rc;
-  if ((rc = round_hist(8))) return rc;
-  for (int p = 0; p < 8; p++) if ((rc = radix_pass(8 * p))) return rc;
+  if ((rc = round_hist(sym_bits))) return rc;
+  for (int p = 0; p < sym_bits; p++) if ((rc = radix_pass(8 * p))) return rc;
   if ((rc = ranks(true))) return rc;
   cx->stats.rounds++;
   u64 reflect = 8;
