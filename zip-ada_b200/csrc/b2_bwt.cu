@@ -118,11 +118,21 @@ k_scan_jobs(const B2SortJob *__restrict__ sj, u32 *__restrict__ jobhist) {
   h[threadIdx.x] = base;
 }
 
+// The scatter has its own tile geometry (env-free compile-time choice): larger tiles give longer output
+// runs per digit and fewer look-back states.
+#ifndef SC_THREADS
+#define SC_THREADS 512
+#endif
+#define SC_ITEMS 8
+#define SC_TILE (SC_THREADS * SC_ITEMS)
+#define SC_WARPS (SC_THREADS / 32)
+#define SC_WCHUNK (32 * SC_ITEMS)
+#define SC_MINCTAS (1536 / SC_THREADS)
 // ---- stable scatter of one digit ---------------------------------------------------------------
 struct ScatterSmem {
-  u64 keys[ST_TILE];
-  u32 vals[ST_TILE];
-  u32 warp_cnt[ST_WARPS][256];
+  u64 keys[SC_TILE];
+  u32 vals[SC_TILE];
+  u32 warp_cnt[SC_WARPS][256];
   u32 tile_start[256];
   u32 g_off[256];
   u32 scan[40];
@@ -137,7 +147,7 @@ struct ScatterSmem {
 __device__ __forceinline__ void lb_store(u32 *p, u32 v) { asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ u32 lb_load(const u32 *p) { u32 v; asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 
-__global__ void __launch_bounds__(ST_THREADS, 6)
+__global__ void __launch_bounds__(SC_THREADS, SC_MINCTAS)
 k_scatter(const B2SortTileRR *__restrict__ tiles, const B2Job *__restrict__ jobs,
           const u64 *__restrict__ keys_in, const u32 *__restrict__ vals_in,
           u64 *__restrict__ keys_out, u32 *__restrict__ vals_out, int shift, u32 *__restrict__ state,
@@ -150,7 +160,7 @@ k_scatter(const B2SortTileRR *__restrict__ tiles, const B2Job *__restrict__ jobs
   // row of blocks ago and has usually published its inclusive counts, so the look-back below is one early
   // load and no wait.  (A same-address ticket counter costs more than the look-back itself; the wait is
   // bounded and reports through *lb_error instead of hanging should a predecessor never show up.)
-  for (int i = tid; i < ST_WARPS * 256; i += ST_THREADS) (&S.warp_cnt[0][0])[i] = 0;
+  for (int i = tid; i < SC_WARPS * 256; i += SC_THREADS) (&S.warp_cnt[0][0])[i] = 0;
   __syncthreads();
   const u32 tix = blockIdx.x;
   const B2SortTileRR tl = tiles[tix];
@@ -158,24 +168,33 @@ k_scatter(const B2SortTileRR *__restrict__ tiles, const B2Job *__restrict__ jobs
   const u32 n = job.na, off = job.pos_off;
   const u32 lt_mask = (1u << l) - 1u;
   // early look at the state of the tile before mine (usually final by now) and at my digit's base
-  S.g_off[tid] = jobhist[((size_t)tl.job * ST_MAXPASS + (u32)(shift >> 3)) * 256 + tid];
   u32 v_early = LB_INC | tag;
-  if (tl.prev != 0xFFFFFFFFu) v_early = lb_load(state + (size_t)tl.prev * 256 + tid);   // only trusted when final
-  u64 key[ST_ITEMS];
-  u32 rk[ST_ITEMS];   // rank within (warp, digit) | digit << 16 ; 0xFFFFFFFF = invalid
-  const u32 wbase = tl.start + w * ST_WCHUNK;
+  if (tid < 256) {
+    S.g_off[tid] = jobhist[((size_t)tl.job * ST_MAXPASS + (u32)(shift >> 3)) * 256 + tid];
+    if (tl.prev != 0xFFFFFFFFu) v_early = lb_load(state + (size_t)tl.prev * 256 + tid);   // only trusted when final
+  }
+  u64 key[SC_ITEMS];
+  u32 rk[SC_ITEMS];   // rank within (warp, digit) | digit << 16 ; 0xFFFFFFFF = invalid
+  const u32 wbase = tl.start + w * SC_WCHUNK;
 #pragma unroll
-  for (int k = 0; k < ST_ITEMS; k++) {
+  for (int k = 0; k < SC_ITEMS; k++) {
     u32 i = wbase + k * 32 + l;
     key[k] = (i < n) ? keys_in[off + i] : 0;
   }
 #pragma unroll
-  for (int k = 0; k < ST_ITEMS; k++) {
+  for (int k = 0; k < SC_ITEMS; k++) {
     u32 i = wbase + k * 32 + l;
     bool valid = i < n;
     u32 d = (u32)(key[k] >> shift) & 255u;
-    u32 mk = valid ? d : (256u + l);
-    u32 peers = __match_any_sync(0xffffffffu, mk);
+    // lanes holding the same digit: eight ballots (one per digit bit) cost the same for every digit
+    // distribution, whereas match.any slows down with the number of distinct digits in the warp
+    u32 peers = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+    for (int bb = 0; bb < 8; bb++) {
+      const bool bit = (d >> bb) & 1u;
+      const u32 m = __ballot_sync(0xffffffffu, bit);
+      peers &= bit ? m : ~m;
+    }
     u32 r = __popc(peers & lt_mask);
     u32 base = valid ? S.warp_cnt[w][d] : 0;
     __syncwarp();
@@ -187,12 +206,14 @@ k_scatter(const B2SortTileRR *__restrict__ tiles, const B2Job *__restrict__ jobs
   // per digit: exclusive over warps, tile count
   {
     u32 run = 0;
+    if (tid < 256) {
 #pragma unroll
-    for (int ww = 0; ww < ST_WARPS; ww++) { u32 c = S.warp_cnt[ww][tid]; S.warp_cnt[ww][tid] = run; run += c; }
+      for (int ww = 0; ww < SC_WARPS; ww++) { u32 c = S.warp_cnt[ww][tid]; S.warp_cnt[ww][tid] = run; run += c; }
+    }
     u32 ts = block_excl_add(run, S.scan, nullptr);
-    S.tile_start[tid] = ts;
     // rows of my digit in the tiles of this block before mine: decoupled look-back, one digit per thread
-    {
+    if (tid < 256) {
+      S.tile_start[tid] = ts;
       u32 *stt = state + (size_t)tix * 256 + tid;
       u32 excl = 0;
       if (tl.prev == 0xFFFFFFFFu) {
@@ -222,14 +243,14 @@ k_scatter(const B2SortTileRR *__restrict__ tiles, const B2Job *__restrict__ jobs
   __syncthreads();
   // the rotation indices are only needed now: fetching them late keeps the register count low
   // enough for six resident CTAs per SM, whose phases overlap
-  u32 val[ST_ITEMS];
+  u32 val[SC_ITEMS];
 #pragma unroll
-  for (int k = 0; k < ST_ITEMS; k++) {
+  for (int k = 0; k < SC_ITEMS; k++) {
     u32 i = wbase + k * 32 + l;
     val[k] = (i < n) ? vals_in[off + i] : 0;
   }
 #pragma unroll
-  for (int k = 0; k < ST_ITEMS; k++) {
+  for (int k = 0; k < SC_ITEMS; k++) {
     if (rk[k] != 0xFFFFFFFFu) {
       u32 d = rk[k] >> 16;
       u32 lp = S.tile_start[d] + S.warp_cnt[w][d] + (rk[k] & 0xFFFFu);
@@ -238,10 +259,10 @@ k_scatter(const B2SortTileRR *__restrict__ tiles, const B2Job *__restrict__ jobs
     }
   }
   __syncthreads();
-  const u32 cnt = (n - tl.start) < ST_TILE ? (n - tl.start) : ST_TILE;
+  const u32 cnt = (n - tl.start) < SC_TILE ? (n - tl.start) : SC_TILE;
 #pragma unroll 4
-  for (int k = 0; k < ST_ITEMS; k++) {
-    u32 q = tid + k * ST_THREADS;
+  for (int k = 0; k < SC_ITEMS; k++) {
+    u32 q = tid + k * SC_THREADS;
     if (q < cnt) {
       u64 kk = S.keys[q];
       u32 d = (u32)(kk >> shift) & 255u;
@@ -440,11 +461,12 @@ static void build_tiles_rr(const std::vector<B2SortJob> &sj, std::vector<B2SortT
   std::vector<u32> last(sj.size(), 0xFFFFFFFFu);
   for (size_t g0 = 0; g0 < sj.size(); g0 += group) {
     const size_t g1 = std::min(sj.size(), g0 + group);
+    const u32 per = SC_TILE / ST_TILE;                       // sort tiles per scatter tile
     u32 max_nt = 0;
-    for (size_t j = g0; j < g1; j++) max_nt = std::max(max_nt, sj[j].ntiles);
+    for (size_t j = g0; j < g1; j++) max_nt = std::max(max_nt, (sj[j].ntiles + per - 1) / per);
     for (u32 k = 0; k < max_nt; k++)
       for (size_t j = g0; j < g1; j++)
-        if (sj[j].ntiles > k) { const u32 pos = (u32)rr.size(); rr.push_back(B2SortTileRR{sj[j].job, k * ST_TILE, last[j], 0}); last[j] = pos; }
+        if ((sj[j].ntiles + per - 1) / per > k) { const u32 pos = (u32)rr.size(); rr.push_back(B2SortTileRR{sj[j].job, k * SC_TILE, last[j], 0}); last[j] = pos; }
   }
 }
 
@@ -503,7 +525,7 @@ int b2k_bwt_batch(B2SortCtx *cx, cudaStream_t st, B2Job *d_jobs, const std::vect
     const u32 tag = (pass_no & 255u) << 22;
     EvPair ev{nullptr, nullptr};
     if (cx->timing) { cudaEventCreate(&ev.a); cudaEventCreate(&ev.b); cudaEventRecord(ev.a, st); }
-    k_scatter<<<(u32)tiles_rr.size(), ST_THREADS, sizeof(ScatterSmem), st>>>(cx->d_tiles_rr, d_jobs, kA, vA, kB, vB, shift, cx->d_hist, cx->d_digit_base,
+    k_scatter<<<(u32)tiles_rr.size(), SC_THREADS, sizeof(ScatterSmem), st>>>(cx->d_tiles_rr, d_jobs, kA, vA, kB, vB, shift, cx->d_hist, cx->d_digit_base,
                                                            cx->d_ticket, tag);
     pass_no++;
     if (cx->timing) { cudaEventRecord(ev.b, st); evs.push_back(ev); }
