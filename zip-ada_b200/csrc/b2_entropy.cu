@@ -110,7 +110,7 @@ k_group_hist(const B2Job *__restrict__ jobs, const u16 *__restrict__ mtf, u16 *_
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32)
 k_rank_sort(const B2Job *__restrict__ jobs, u32 *__restrict__ rank3, u32 *__restrict__ rank4) {
-  extern __shared__ u32 a[];   // 1-based: a[1..G]
+  extern __shared__ __align__(16) u32 a[];   // 1-based: a[1..G]
   const B2Job &job = jobs[blockIdx.x >> 1];
   u32 *arr = ((blockIdx.x & 1) ? rank4 : rank3) + job.grp_off;
   const i32 G = (i32)job.n_groups;
@@ -122,6 +122,19 @@ k_rank_sort(const B2Job *__restrict__ jobs, u32 *__restrict__ rank3, u32 *__rest
 #define KEY(x) ((x) >> 16)
     auto sift = [&](i32 s) {
       i32 c = s;
+      // two levels per trip while both are complete: the children and the grandchildren are fetched
+      // together (one 8-byte and one 16-byte load), which halves the chain of dependent loads
+      while (4 * c + 3 <= mx) {
+        const uint2 pr = *reinterpret_cast<const uint2 *>(&a[2 * c]);
+        const uint4 qd = *reinterpret_cast<const uint4 *>(&a[4 * c]);
+        const bool r1 = KEY(pr.x) < KEY(pr.y);
+        const i32 s1 = 2 * c + (r1 ? 1 : 0);
+        const u32 g0 = r1 ? qd.z : qd.x, g1 = r1 ? qd.w : qd.y;
+        const bool r2 = KEY(g0) < KEY(g1);
+        a[c] = r1 ? pr.y : pr.x;
+        a[s1] = r2 ? g1 : g0;
+        c = 2 * s1 + (r2 ? 1 : 0);
+      }
       for (;;) {
         i32 son = 2 * c;
         if (son > mx) break;

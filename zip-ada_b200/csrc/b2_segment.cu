@@ -32,6 +32,8 @@
 
 typedef long long i64s;
 
+__device__ __forceinline__ double pow2d(int e) { return __longlong_as_double((long long)(e + 1023) << 52); }   // 2^e, -1022 <= e <= 1023
+
 // k -> k + a[k mod N], N = 2 (one binade: only the parity of k matters) or 4 (two binades)
 template <int N> struct PF { i64s a[N]; };
 
@@ -116,7 +118,7 @@ template <int N> __device__ __forceinline__ void seg_scan(SegSmem &S, double E, 
   // predicted grid of each of my four results: from E and my own terms (the drift of the sum over
   // the steps before me is small; a wrong guess is caught below)
   u32 coarse = 0;
-  PF<N> inc;
+  PF<N> inc, mine_f;
   {
     double v = E;
 #pragma unroll
@@ -127,6 +129,7 @@ template <int N> __device__ __forceinline__ void seg_scan(SegSmem &S, double E, 
       const PF<N> fj = pf_term<N>(part ? d[j] * scale : 0.0, cj);
       inc = j == 0 ? fj : pf_compose<N>(inc, fj);
     }
+    mine_f = inc;
   }
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -154,6 +157,14 @@ template <int N> __device__ __forceinline__ void seg_scan(SegSmem &S, double E, 
   }
   pre = pf_compose<N>(pre, excl);
   kb = K0 + pf_pick<N>(pre, K0);                           // the sum before my step, in units of u'
+  if (N == 2) {
+    // One binade is only chosen when E is at least 0.75 away from both ends of its binade: a term is at
+    // most 1/e = 0.368 and the sum moves by less than 256 * 2 * ln (16000) / 16000 = 0.31 over a batch, so
+    // no intermediate sum can leave the binade and nothing has to be checked.
+    k = K0 + pf_pick<N>(pf_compose<N>(pre, mine_f), K0);
+    mybad = false;
+    return;
+  }
   k = kb;
   const i64s lo = 1ll << 52, mid = 1ll << 53, hi = N == 2 ? mid : (1ll << 54);
   mybad = false;
@@ -283,18 +294,18 @@ k_segment(const u8 *__restrict__ in, const B2Chunk *__restrict__ chunks, u32 n_c
           // one binade when no add of this batch can leave the binade of E (every term is below 0.37 and
           // the sum moves by less than 0.3 over a batch), else the two binades [2^B, 2^(B+2)) around E: the
           // one below when E sits in the lower half of its own
-          const int eb = ilogb(E);
-          const double blo = ldexp(1.0, eb);
+          const int eb = (int)((__double_as_longlong(E) >> 52) & 0x7FF) - 1023;       // E is normal and positive here
+          const double blo = pow2d(eb);
           const bool one = (E - blo >= 0.75) && (2.0 * blo - E > 0.75);
           const int B = one ? eb : ((E < 1.5 * blo) ? eb - 1 : eb);
-          const double scale = ldexp(1.0, 52 - B), inv = ldexp(1.0, B - 52);
+          const double scale = pow2d(52 - B), inv = pow2d(B - 52);
           const bool part = valid && tid >= start;
           if (tid == 0) S.firstbad = 0xFFFFFFFFu;
           const double d[4] = {-c1, c2, -c3, c4};
           i64s kb, k;
           bool mybad;
-          if (one) seg_scan<2>(S, E, scale, ldexp(1.0, B + 1), part, d, kb, k, mybad);
-          else seg_scan<4>(S, E, scale, ldexp(1.0, B + 1), part, d, kb, k, mybad);
+          if (one) seg_scan<2>(S, E, scale, pow2d(B + 1), part, d, kb, k, mybad);
+          else seg_scan<4>(S, E, scale, pow2d(B + 1), part, d, kb, k, mybad);
           if (__syncthreads_or(mybad) == 0) {
             if (part) mine = (double)k * inv;
             if ((int)tid == steps - 1) S.entropy = mine;
