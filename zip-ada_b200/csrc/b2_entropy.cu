@@ -124,6 +124,25 @@ k_rank_sort(const B2Job *__restrict__ jobs, u32 *__restrict__ rank3, u32 *__rest
       i32 c = s;
       // two levels per trip while both are complete: the children and the grandchildren are fetched
       // together (one 8-byte and one 16-byte load), which halves the chain of dependent loads
+      // ... and three levels per trip higher up in the heap
+      while (8 * c + 7 <= mx) {
+        const uint2 pr = *reinterpret_cast<const uint2 *>(&a[2 * c]);
+        const uint4 qd = *reinterpret_cast<const uint4 *>(&a[4 * c]);
+        const uint4 o0 = *reinterpret_cast<const uint4 *>(&a[8 * c]);
+        const uint4 o1 = *reinterpret_cast<const uint4 *>(&a[8 * c + 4]);
+        const bool r1 = KEY(pr.x) < KEY(pr.y);
+        const i32 s1 = 2 * c + (r1 ? 1 : 0);
+        const u32 g0 = r1 ? qd.z : qd.x, g1 = r1 ? qd.w : qd.y;
+        const bool r2 = KEY(g0) < KEY(g1);
+        const i32 s2 = 2 * s1 + (r2 ? 1 : 0);
+        const u32 ox = r1 ? o1.x : o0.x, oy = r1 ? o1.y : o0.y, oz = r1 ? o1.z : o0.z, ow = r1 ? o1.w : o0.w;
+        const u32 h0 = r2 ? oz : ox, h1 = r2 ? ow : oy;
+        const bool r3 = KEY(h0) < KEY(h1);
+        a[c] = r1 ? pr.y : pr.x;
+        a[s1] = r2 ? g1 : g0;
+        a[s2] = r3 ? h1 : h0;
+        c = 2 * s2 + (r3 ? 1 : 0);
+      }
       while (4 * c + 3 <= mx) {
         const uint2 pr = *reinterpret_cast<const uint2 *>(&a[2 * c]);
         const uint4 qd = *reinterpret_cast<const uint4 *>(&a[4 * c]);
