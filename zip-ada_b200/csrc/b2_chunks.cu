@@ -291,8 +291,19 @@ k_cut_chain(const u8 *__restrict__ in, u64 n, i64 size_hint, int level, i64 win_
           const u64 Ge1 = excl_e + warp_tile(in, n, carry_r, te, 0, e1, excl_e, 0);
           const u64 Gt = Ge1 + (need - A);
           // first tile whose inclusive prefix reaches Gt
-          u64 lo = te, hi = ntiles;                          // answer in [lo, hi]; hi = ntiles means none
-          while (lo < hi) { const u64 mid = (lo + hi) >> 1; if (tincl[mid] >= Gt) hi = mid; else lo = mid + 1; }
+          // (32 probes per trip, one per lane; tiles at or beyond the end of the window need not be looked at)
+          u64 lo = te, hi = ntiles;                          // answer in [lo, hi]; hi = "none below"
+          { const u64 wend = end_max / CT_TILE + 1; if (wend < hi) hi = wend; }
+          while (lo < hi) {
+            const u64 span = hi - lo, step = (span + 31) / 32;
+            const u64 upto = (u64)(l + 1) * step;
+            const u64 pr = lo + (upto < span ? upto : span) - 1;      // non-decreasing in the lane, the last ones = hi - 1
+            const u32 m = __ballot_sync(0xffffffffu, tincl[pr] >= Gt);
+            if (m == 0) { lo = hi; break; }
+            const int k = __ffs(m) - 1;
+            hi = __shfl_sync(0xffffffffu, pr, k);
+            lo = lo + (u64)k * step;
+          }
           if (lo < ntiles && lo * CT_TILE < end_max) {
             const u64 excl = lo ? tincl[lo - 1] : 0;
             const u64 p = warp_tile(in, n, carry_r, lo, 1, 0, excl, Gt);
