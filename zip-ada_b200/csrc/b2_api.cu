@@ -120,6 +120,8 @@ struct Workspace {
 struct b2_encoder {
   int level = 9, device = 0;
   cudaStream_t st = nullptr;            // stream of the stream-level work (cut, segment, copies, footer)
+  cudaStream_t st2 = nullptr;           // segmentation following the chunk chain
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int timing = 0;                       // 0 off, 1 scatter + call events, 2 also per-stage timers (adds syncs, no pipelining)
   // constants
   DevBuf<B2CrcTables> d_ct;
@@ -410,6 +412,7 @@ int encode_streams(b2_encoder *e, const u8 *d_in, std::vector<StreamDesc> &strea
   const i64 full_cap = (i64)level * 100000;
   // ---- A1 chunk cutting --------------------------------------------------------------------------
   std::vector<u32> chunk_stream;          // stream of every chunk
+  bool followed = false;                  // the segmentation already ran, following the chunk chain
   {
     StageTimer tm(e, st, e->ev, &e->stats.stage_ms[0]);
     // a stream whose RLE1 output cannot reach the smallest possible capacity is a single chunk
@@ -429,8 +432,24 @@ int encode_streams(b2_encoder *e, const u8 *d_in, std::vector<StreamDesc> &strea
         B2_TRY(e->d_cut_first.ensure(ct)); B2_TRY(e->d_cut_last.ensure(ct)); B2_TRY(e->d_cut_tsum.ensure(ct));
         B2_TRY(e->d_cut_carry.ensure(ct)); B2_TRY(e->d_cut_tincl.ensure(ct));
         B2CutWork cw{e->d_cut_first.p, e->d_cut_last.p, e->d_cut_tsum.p, e->d_cut_carry.p, e->d_cut_tincl.p};
-        B2_TRY(b2k_cut(st, d_in + S.off, S.n, S.hint, level, win_lo, win_hi, e->d_chunks.p, e->d_scalars.p, max_chunks, &cw));
+        // A single large stream: the segmentation of a chunk starts as soon as the chain has cut it
+        // (k_segment on a second stream follows the chain's progress counter) instead of after the
+        // whole chain, which is one warp walking from chunk to chunk.
+        const bool follow = level == 9 && streams.size() == 1 && e->timing < 2;
+        if (follow) {
+          B2_TRY(e->d_seg.ensure((size_t)max_chunks * 2 * B2_MAX_SEG));
+          B2_TRY(e->d_nseg.ensure((size_t)max_chunks * 2));
+        }
+        B2_TRY(b2k_cut(st, d_in + S.off, S.n, S.hint, level, win_lo, win_hi, e->d_chunks.p, e->d_scalars.p, max_chunks, &cw,
+                       follow ? e->d_scalars.p + 12 : nullptr, follow ? e->ev_fork : nullptr));
         e->launches_other += 5;
+        if (follow) {
+          B2_CUDA_CHECK(cudaStreamWaitEvent(e->st2, e->ev_fork, 0));
+          B2_TRY(b2k_segment(e->st2, d_in + S.off, e->d_chunks.p, max_chunks, e->d_T.p, e->d_seg.p, e->d_nseg.p, e->d_scalars.p + 12));
+          B2_CUDA_CHECK(cudaEventRecord(e->ev_join, e->st2));
+          e->launches_other += 1;
+          followed = true;
+        }
         u32 nc = 0;
         B2_CUDA_CHECK(cudaMemcpyAsync(&nc, e->d_scalars.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
         B2_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -451,12 +470,17 @@ int encode_streams(b2_encoder *e, const u8 *d_in, std::vector<StreamDesc> &strea
   // ---- A3 segmentation of every chunk --------------------------------------------------------------
   {
     StageTimer tm(e, st, e->ev, &e->stats.stage_ms[0]);
+    if (followed) {
+      B2_CUDA_CHECK(cudaStreamWaitEvent(st, e->ev_join, 0));      // k_segment has read the chunk table: it may be rewritten now
+    }
     B2_TRY(e->d_chunks.ensure(n_chunks));
     B2_CUDA_CHECK(cudaMemcpyAsync(e->d_chunks.p, e->chunks.data(), n_chunks * sizeof(B2Chunk), cudaMemcpyHostToDevice, st));
     if (level == 9) {
-      B2_TRY(e->d_seg.ensure((size_t)n_chunks * 2 * B2_MAX_SEG));
-      B2_TRY(e->d_nseg.ensure((size_t)n_chunks * 2));
-      B2_TRY(b2k_segment(st, d_in, e->d_chunks.p, n_chunks, e->d_T.p, e->d_seg.p, e->d_nseg.p));
+      if (!followed) {
+        B2_TRY(e->d_seg.ensure((size_t)n_chunks * 2 * B2_MAX_SEG));
+        B2_TRY(e->d_nseg.ensure((size_t)n_chunks * 2));
+        B2_TRY(b2k_segment(st, d_in, e->d_chunks.p, n_chunks, e->d_T.p, e->d_seg.p, e->d_nseg.p, nullptr));
+      }
       e->nseg.resize((size_t)n_chunks * 2);
       B2_CUDA_CHECK(cudaMemcpyAsync(e->nseg.data(), e->d_nseg.p, e->nseg.size() * sizeof(u32), cudaMemcpyDeviceToHost, st));
       B2_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -470,7 +494,7 @@ int encode_streams(b2_encoder *e, const u8 *d_in, std::vector<StreamDesc> &strea
           B2_CUDA_CHECK(cudaMemcpyAsync(e->seg[k].data(), e->d_seg.p + (size_t)k * B2_MAX_SEG, ns * sizeof(u32), cudaMemcpyDeviceToHost, st));
         }
       }
-      e->launches_other += 1;
+      if (!followed) e->launches_other += 1;
     }
     B2_CUDA_CHECK(cudaStreamSynchronize(st));
   }
@@ -703,6 +727,9 @@ int b2_create(int level, int device, b2_encoder **out) {
   if (const char *s = getenv("B2GPU_BATCH_JOBS")) { long long v = atoll(s); if (v >= 8) e->batch_jobs_max = (size_t)v; }
   if (const char *s = getenv("B2GPU_PIPELINE")) { int v = atoi(s); if (v >= 1 && v <= 8) e->n_workspaces = v; }
   B2_CUDA_CHECK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
+  B2_CUDA_CHECK(cudaStreamCreateWithFlags(&e->st2, cudaStreamNonBlocking));
+  B2_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+  B2_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
   B2_CUDA_CHECK(cudaEventCreate(&e->ev[0])); B2_CUDA_CHECK(cudaEventCreate(&e->ev[1]));
   B2_CUDA_CHECK(cudaEventCreate(&e->ev_call[0])); B2_CUDA_CHECK(cudaEventCreate(&e->ev_call[1]));
   for (int i = 0; i < e->n_workspaces; i++) {
@@ -744,6 +771,9 @@ void b2_destroy(b2_encoder *e) {
   if (e->ev[1]) cudaEventDestroy(e->ev[1]);
   if (e->ev_call[0]) cudaEventDestroy(e->ev_call[0]);
   if (e->ev_call[1]) cudaEventDestroy(e->ev_call[1]);
+  if (e->st2) { cudaStreamSynchronize(e->st2); cudaStreamDestroy(e->st2); }
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  if (e->ev_join) cudaEventDestroy(e->ev_join);
   if (e->st) cudaStreamDestroy(e->st);
   delete e;
 }

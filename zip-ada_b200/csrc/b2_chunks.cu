@@ -240,7 +240,9 @@ __device__ u64 warp_tile(const u8 *__restrict__ in, u64 n, const u64 *__restrict
 __global__ void __launch_bounds__(32)
 k_cut_chain(const u8 *__restrict__ in, u64 n, i64 size_hint, int level, i64 win_lo, i64 win_hi,
             const u32 *__restrict__ firstchg, const u64 *__restrict__ carry_r, const u64 *__restrict__ tincl, u64 ntiles,
-            B2Chunk *chunks, u32 *n_chunks, u32 max_chunks) {
+            B2Chunk *chunks, u32 *n_chunks, u32 max_chunks, u32 *progress) {
+  // progress[0] = chunks published so far, progress[1] = 1 when the chain is complete: k_segment may be
+  // following on another stream and starts on a chunk as soon as it is there
   const u32 l = lane_id();
   u64 pos = 0;
   u32 nc = 0;
@@ -314,15 +316,19 @@ k_cut_chain(const u8 *__restrict__ in, u64 n, i64 size_hint, int level, i64 win_
     }
     if (l == 0 && nc < max_chunks) { chunks[nc].start = pos; chunks[nc].len = (u32)len; chunks[nc].cap = (u32)cap; chunks[nc].pad = 0; chunks[nc].pad2 = 0; }
     nc++;
+    if (l == 0 && progress) { __threadfence(); *(volatile u32 *)progress = nc < max_chunks ? nc : max_chunks; }
     pos += len;
     if (pos >= n) break;                                     // exit when not More_Bytes (:1428)
     if (len == 0) break;
   }
-  if (l == 0) *n_chunks = nc;
+  if (l == 0) {
+    *n_chunks = nc;
+    if (progress) { __threadfence(); ((volatile u32 *)progress)[1] = 1u; }
+  }
 }
 
 int b2k_cut(cudaStream_t st, const u8 *d_in, u64 n, i64 size_hint, int level, i64 win_lo, i64 win_hi,
-            B2Chunk *d_chunks, u32 *d_n_chunks, u32 max_chunks, B2CutWork *w) {
+            B2Chunk *d_chunks, u32 *d_n_chunks, u32 max_chunks, B2CutWork *w, u32 *d_progress, cudaEvent_t ev_chain_starts) {
   const u64 ntiles = (n + CT_TILE - 1) / CT_TILE;
   if (ntiles) {
     k_cut_a<<<(u32)ntiles, CT_THREADS, 0, st>>>(d_in, n, w->firstchg, w->lastchg);
@@ -330,8 +336,10 @@ int b2k_cut(cudaStream_t st, const u8 *d_in, u64 n, i64 size_hint, int level, i6
     k_cut_b<<<(u32)ntiles, CT_THREADS, 0, st>>>(d_in, n, w->carry_r, w->tsum);
     k_cut_s2<<<1, 1024, 0, st>>>(w->tsum, ntiles, w->tincl);
   }
+  if (d_progress) B2_CUDA_CHECK(cudaMemsetAsync(d_progress, 0, 2 * sizeof(u32), st));
+  if (ev_chain_starts) B2_CUDA_CHECK(cudaEventRecord(ev_chain_starts, st));
   k_cut_chain<<<1, 32, 0, st>>>(d_in, n, size_hint, level, win_lo, win_hi, w->firstchg, w->carry_r, w->tincl, ntiles,
-                                d_chunks, d_n_chunks, max_chunks);
+                                d_chunks, d_n_chunks, max_chunks, d_progress);
   B2_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -31,10 +31,10 @@ struct B2SortStats {
 // b2_chunks.cu  (per 2048-byte tile work arrays of the chunk cutter)
 struct B2CutWork { u32 *firstchg, *lastchg, *tsum; u64 *carry_r, *tincl; };
 int b2k_cut(cudaStream_t st, const u8 *d_in, u64 n, i64 size_hint, int level, i64 win_lo, i64 win_hi,
-            B2Chunk *d_chunks, u32 *d_n_chunks, u32 max_chunks, B2CutWork *w);
+            B2Chunk *d_chunks, u32 *d_n_chunks, u32 max_chunks, B2CutWork *w, u32 *d_progress, cudaEvent_t ev_chain_starts);
 // b2_segment.cu
 int b2k_segment(cudaStream_t st, const u8 *d_in, const B2Chunk *d_chunks, u32 n_chunks, const double *d_T,
-                u32 *d_seg, u32 *d_nseg);
+                u32 *d_seg, u32 *d_nseg, const u32 *d_progress);
 // b2_rle1.cu
 void b2k_make_crc_tables(B2CrcTables *t);
 int b2k_rle1(cudaStream_t st, const u8 *d_in, B2Job *d_jobs, u32 n_jobs, u8 *d_text, const B2CrcTables *d_ct);

@@ -179,11 +179,33 @@ template <int N> __device__ __forceinline__ void seg_scan(SegSmem &S, double E, 
 
 __global__ void __launch_bounds__(SG_THREADS, 3)
 k_segment(const u8 *__restrict__ in, const B2Chunk *__restrict__ chunks, u32 n_chunks,
-          const double *__restrict__ T, u32 *__restrict__ seg, u32 *__restrict__ nseg) {
+          const double *__restrict__ T, u32 *__restrict__ seg, u32 *__restrict__ nseg, const u32 *progress) {
   __shared__ SegSmem S;
   const u32 c = blockIdx.x;
   if (c >= n_chunks) return;
   const u32 tid = threadIdx.x, l = lane_id(), w = warp_id();
+  if (progress) {
+    // following the chunk chain (k_cut_chain on another stream): wait until my chunk is there.  CTAs
+    // are dispatched in chunk order, so the resident ones are always the next chunks to appear; the
+    // CTAs of the unused tail of the table leave when the chain reports the end.
+    if (tid == 0) {
+      u32 state = 2;                                    // 0 no such chunk, 1 ready, 2 gave up
+      for (u32 spins = 0; spins < 8000000u; spins++) {
+        const u32 done = ((const volatile u32 *)progress)[1];
+        const u32 ready = ((const volatile u32 *)progress)[0];
+        if (ready > c) { state = 1; break; }
+        if (done) { state = 0; break; }
+        __nanosleep(400);
+      }
+      S.first[0] = state;
+      if (state == 2) { nseg[2 * c] = 0xFFFFFFFFu; nseg[2 * c + 1] = 0xFFFFFFFFu; }   // reported as an overflow by the host
+    }
+    __syncthreads();
+    const u32 state = S.first[0];
+    __syncthreads();
+    if (state != 1) return;
+    __threadfence();
+  }
   const u32 lt = (1u << l) - 1u;
   const u8 *buf = in + chunks[c].start;
   const i32 len = (i32)chunks[c].len;
@@ -396,9 +418,9 @@ k_segment(const u8 *__restrict__ in, const B2Chunk *__restrict__ chunks, u32 n_c
 }
 
 int b2k_segment(cudaStream_t st, const u8 *d_in, const B2Chunk *d_chunks, u32 n_chunks, const double *d_T,
-                u32 *d_seg, u32 *d_nseg) {
+                u32 *d_seg, u32 *d_nseg, const u32 *d_progress) {
   if (n_chunks == 0) return 0;
-  k_segment<<<n_chunks, SG_THREADS, 0, st>>>(d_in, d_chunks, n_chunks, d_T, d_seg, d_nseg);
+  k_segment<<<n_chunks, SG_THREADS, 0, st>>>(d_in, d_chunks, n_chunks, d_T, d_seg, d_nseg, d_progress);
   B2_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
