@@ -19,6 +19,8 @@
 #include <condition_variable>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
+#include <chrono>
 #include <map>
 #include <mutex>
 #include <string>
@@ -406,6 +408,7 @@ struct StreamDesc {
 int encode_streams(b2_encoder *e, const u8 *d_in, std::vector<StreamDesc> &streams) {
   cudaStream_t st = e->st;
   const int level = e->level;
+  B2_CUDA_CHECK(cudaStreamSynchronize(e->st2));     // nothing of an earlier (failed) call may still be following a chain
   e->trace.clear(); e->chunks.clear(); e->nseg.clear(); e->seg.clear();
   i64 win_lo, win_hi;
   balance_window(level, win_lo, win_hi);
@@ -439,6 +442,7 @@ int encode_streams(b2_encoder *e, const u8 *d_in, std::vector<StreamDesc> &strea
         if (follow) {
           B2_TRY(e->d_seg.ensure((size_t)max_chunks * 2 * B2_MAX_SEG));
           B2_TRY(e->d_nseg.ensure((size_t)max_chunks * 2));
+          B2_CUDA_CHECK(cudaMemsetAsync(e->d_nseg.p, 0xFE, (size_t)max_chunks * 2 * sizeof(u32), st));   // "not there yet"
         }
         B2_TRY(b2k_cut(st, d_in + S.off, S.n, S.hint, level, win_lo, win_hi, e->d_chunks.p, e->d_scalars.p, max_chunks, &cw,
                        follow ? e->d_scalars.p + 12 : nullptr, follow ? e->ev_fork : nullptr));
@@ -470,34 +474,52 @@ int encode_streams(b2_encoder *e, const u8 *d_in, std::vector<StreamDesc> &strea
   // ---- A3 segmentation of every chunk --------------------------------------------------------------
   {
     StageTimer tm(e, st, e->ev, &e->stats.stage_ms[0]);
-    if (followed) {
-      B2_CUDA_CHECK(cudaStreamWaitEvent(st, e->ev_join, 0));      // k_segment has read the chunk table: it may be rewritten now
+    if (!followed) {
+      B2_TRY(e->d_chunks.ensure(n_chunks));
+      B2_CUDA_CHECK(cudaMemcpyAsync(e->d_chunks.p, e->chunks.data(), n_chunks * sizeof(B2Chunk), cudaMemcpyHostToDevice, st));
     }
-    B2_TRY(e->d_chunks.ensure(n_chunks));
-    B2_CUDA_CHECK(cudaMemcpyAsync(e->d_chunks.p, e->chunks.data(), n_chunks * sizeof(B2Chunk), cudaMemcpyHostToDevice, st));
     if (level == 9) {
+      e->nseg.assign((size_t)n_chunks * 2, 0);
+      e->seg.assign((size_t)n_chunks * 2, std::vector<u32>());
       if (!followed) {
         B2_TRY(e->d_seg.ensure((size_t)n_chunks * 2 * B2_MAX_SEG));
         B2_TRY(e->d_nseg.ensure((size_t)n_chunks * 2));
         B2_TRY(b2k_segment(st, d_in, e->d_chunks.p, n_chunks, e->d_T.p, e->d_seg.p, e->d_nseg.p, nullptr));
+        e->launches_other += 1;
       }
-      e->nseg.resize((size_t)n_chunks * 2);
-      B2_CUDA_CHECK(cudaMemcpyAsync(e->nseg.data(), e->d_nseg.p, e->nseg.size() * sizeof(u32), cudaMemcpyDeviceToHost, st));
-      B2_CUDA_CHECK(cudaStreamSynchronize(st));
-      // only chunks with a real segmentation need their cut lists (a trivial one is just [len])
-      e->seg.assign((size_t)n_chunks * 2, std::vector<u32>());
-      for (u32 k = 0; k < 2 * n_chunks; k++) {
-        const u32 ns = e->nseg[k];
-        if (ns > B2_MAX_SEG) B2_FAIL(B2_ERR_INTERNAL, "segment table overflow");
-        if (ns > 1) {
-          e->seg[k].resize(ns);
-          B2_CUDA_CHECK(cudaMemcpyAsync(e->seg[k].data(), e->d_seg.p + (size_t)k * B2_MAX_SEG, ns * sizeof(u32), cudaMemcpyDeviceToHost, st));
-        }
-      }
-      if (!followed) e->launches_other += 1;
     }
     B2_CUDA_CHECK(cudaStreamSynchronize(st));
   }
+  // Cut lists of the chunks below `upto`, brought to the host.  When the segmentation is still following
+  // the chunk chain on the other stream, this waits for exactly those chunks, so that the first batches
+  // start while later chunks are still being segmented.
+  u32 seg_have = 0;
+  auto fetch_seg = [&](u32 upto) -> int {
+    if (level != 9 || upto <= seg_have) return 0;
+    upto = std::min(n_chunks, std::max(upto, seg_have + 64));
+    for (u32 tries = 0;; tries++) {
+      B2_CUDA_CHECK(cudaMemcpyAsync(e->nseg.data() + 2 * (size_t)seg_have, e->d_nseg.p + 2 * (size_t)seg_have,
+                                    2 * (size_t)(upto - seg_have) * sizeof(u32), cudaMemcpyDeviceToHost, st));
+      B2_CUDA_CHECK(cudaStreamSynchronize(st));
+      bool all = true;
+      for (u32 k = 2 * seg_have; k < 2 * upto; k++) if (e->nseg[k] == 0xFEFEFEFEu) { all = false; break; }
+      if (all) break;
+      if (!followed || tries > 2000000u) B2_FAIL(B2_ERR_INTERNAL, "segmentation results missing");
+      std::this_thread::sleep_for(std::chrono::microseconds(50));
+    }
+    // only chunks with a real segmentation need their cut lists (a trivial one is just [len])
+    for (u32 k = 2 * seg_have; k < 2 * upto; k++) {
+      const u32 ns = e->nseg[k];
+      if (ns > B2_MAX_SEG) B2_FAIL(B2_ERR_INTERNAL, "segment table overflow");
+      if (ns > 1) {
+        e->seg[k].resize(ns);
+        B2_CUDA_CHECK(cudaMemcpyAsync(e->seg[k].data(), e->d_seg.p + (size_t)k * B2_MAX_SEG, ns * sizeof(u32), cudaMemcpyDeviceToHost, st));
+      }
+    }
+    B2_CUDA_CHECK(cudaStreamSynchronize(st));
+    seg_have = upto;
+    return 0;
+  };
   // ---- output regions ------------------------------------------------------------------------------
   u64 out_total = 0;
   for (auto &S : streams) {
@@ -506,38 +528,19 @@ int encode_streams(b2_encoder *e, const u8 *d_in, std::vector<StreamDesc> &strea
   }
   B2_TRY(e->d_out.ensure(out_total / 4 + 16));
   B2_CUDA_CHECK(cudaMemsetAsync(e->d_out.p, 0, (out_total / 4 + 8) * sizeof(u32), st));
-  // ---- plan: batches of whole chunks ---------------------------------------------------------
-  std::vector<ChunkPlan> plans(n_chunks);
-  std::vector<Batch> batches;
-  {
-    Batch cur; cur.c0 = 0;
-    u64 positions = 0;
-    std::vector<B2Job> add;
-    for (u32 c = 0; c < n_chunks; c++) {
-      ChunkPlan &P = plans[c];
-      P.start = e->chunks[c].start; P.len = e->chunks[c].len; P.cap = e->chunks[c].cap;
-      P.n_seg[0] = P.n_seg[1] = 0;
-      u64 addpos = 0;
-      B2_TRY(plan_chunk(e, c, P, add, cur.jobs.size(), addpos));
-      if (!cur.jobs.empty() && (positions + addpos > e->batch_positions || cur.jobs.size() + add.size() > e->batch_jobs_max)) {
-        cur.c1 = c;
-        batches.push_back(std::move(cur));
-        cur = Batch(); cur.c0 = c; positions = 0;
-        B2_TRY(plan_chunk(e, c, P, add, 0, addpos));      // job ids restart in the new batch
-      }
-      cur.jobs.insert(cur.jobs.end(), add.begin(), add.end());
-      positions += addpos;
-    }
-    cur.c1 = n_chunks;
-    if (n_chunks) batches.push_back(std::move(cur));
-  }
   B2_CUDA_CHECK(cudaStreamSynchronize(st));           // output zeroed before any concat
+  // ---- batches of whole chunks: planned by this thread, run by the workers as they appear -----------
+  std::vector<ChunkPlan> plans(n_chunks);
+  std::deque<Batch> batches;                          // grows while the workers run (references stay valid)
+  std::mutex bmu;
+  std::condition_variable bcv;
+  bool planned_all = false;                           // guarded by bmu
   // ---- pipelined batches ---------------------------------------------------------------------
   // serial state carried from chunk to chunk inside a stream (:1305-1345)
   std::vector<B2StreamEnd> ends(streams.size());
   for (size_t si = 0; si < streams.size(); si++) { ends[si].out_off = streams[si].out_off; ends[si].end_bit = 32; ends[si].crc = 0; ends[si].pad = 0; }
   u64 out_words_needed = 0;
-  const int W = (e->timing >= 2) ? 1 : std::max(1, std::min<int>((int)e->ws.size(), (int)batches.size()));
+  const int W = (e->timing >= 2) ? 1 : std::max<int>(1, (int)e->ws.size());
   for (auto *w : e->ws) {
     memset(&w->sort_stats, 0, sizeof w->sort_stats);
     w->launches = 0; w->blocks = 0; w->block_bytes = 0;
@@ -554,19 +557,25 @@ int encode_streams(b2_encoder *e, const u8 *d_in, std::vector<StreamDesc> &strea
     Workspace *w = e->ws[wi];
     for (;;) {
       const u32 b = next.fetch_add(1);
-      if (b >= batches.size()) break;
+      Batch *B = nullptr;
+      {
+        std::unique_lock<std::mutex> lk(bmu);
+        bcv.wait(lk, [&] { return b < batches.size() || planned_all; });
+        if (b < batches.size()) B = &batches[b];
+      }
+      if (!B) break;
       int rc = 0;
       {
         std::lock_guard<std::mutex> lk(mu);
         if (err) rc = err;
       }
-      if (!rc) rc = run_batch(e, w, d_in, batches[b].jobs);
+      if (!rc) rc = run_batch(e, w, d_in, B->jobs);
       std::unique_lock<std::mutex> lk(mu);
       cv.wait(lk, [&] { return turn == b; });
       if (!rc && !err) {
         // winners of the chunks of this batch, in order
         std::vector<B2ConcatItem> items;
-        for (u32 c = batches[b].c0; c < batches[b].c1; c++) {
+        for (u32 c = B->c0; c < B->c1; c++) {
           ChunkPlan &P = plans[c];
           B2StreamEnd &E = ends[chunk_stream[c]];
           b2_chunk_trace tr; memset(&tr, 0, sizeof tr);
@@ -608,12 +617,45 @@ int encode_streams(b2_encoder *e, const u8 *d_in, std::vector<StreamDesc> &strea
       cv.notify_all();
     }
   };
-  if (W == 1) worker(0);
-  else {
-    std::vector<std::thread> th;
-    for (int i = 0; i < W; i++) th.emplace_back(worker, i);
-    for (auto &t : th) t.join();
+  std::vector<std::thread> th;
+  for (int i = 0; i < W; i++) th.emplace_back(worker, i);
+  int plan_rc = 0;
+  std::string plan_msg;
+  {
+    auto publish = [&](Batch &&bt) {
+      { std::lock_guard<std::mutex> lk(bmu); batches.push_back(std::move(bt)); }
+      bcv.notify_all();
+    };
+    Batch cur; cur.c0 = 0;
+    u64 positions = 0;
+    std::vector<B2Job> add;
+    for (u32 c = 0; c < n_chunks && !plan_rc; c++) {
+      ChunkPlan &P = plans[c];
+      P.start = e->chunks[c].start; P.len = e->chunks[c].len; P.cap = e->chunks[c].cap;
+      P.n_seg[0] = P.n_seg[1] = 0;
+      u64 addpos = 0;
+      if ((plan_rc = fetch_seg(c + 1))) break;                 // may wait for the segmentation of this chunk
+      if ((plan_rc = plan_chunk(e, c, P, add, cur.jobs.size(), addpos))) break;
+      if (!cur.jobs.empty() && (positions + addpos > e->batch_positions || cur.jobs.size() + add.size() > e->batch_jobs_max)) {
+        cur.c1 = c;
+        publish(std::move(cur));
+        cur = Batch(); cur.c0 = c; positions = 0;
+        if ((plan_rc = plan_chunk(e, c, P, add, 0, addpos))) break;      // job ids restart in the new batch
+      }
+      cur.jobs.insert(cur.jobs.end(), add.begin(), add.end());
+      positions += addpos;
+    }
+    if (!plan_rc && n_chunks) { cur.c1 = n_chunks; publish(std::move(cur)); }
+    if (plan_rc) {
+      plan_msg = g_last_error;
+      std::lock_guard<std::mutex> lk(mu);
+      if (!err) { err = plan_rc; err_msg = plan_msg; }
+    }
+    { std::lock_guard<std::mutex> lk(bmu); planned_all = true; }
+    bcv.notify_all();
   }
+  for (auto &t : th) t.join();
+  if (followed) B2_CUDA_CHECK(cudaStreamSynchronize(e->st2));
   (void)out_words_needed;
   if (err) { g_last_error = err_msg; return err; }
   // ---- stream headers and footers (:1384-1407) on the device ----------------------------------------

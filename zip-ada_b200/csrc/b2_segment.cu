@@ -412,8 +412,9 @@ k_segment(const u8 *__restrict__ in, const B2Chunk *__restrict__ chunks, u32 n_c
   if (tid == 0) {
     for (int k = 0; k < 2; k++) {
       if (len > 0) { if (cnt[k] < B2_MAX_SEG) out[k][cnt[k]] = (u32)len; cnt[k]++; }   // :102-104
-      nseg[2 * c + k] = cnt[k];
     }
+    __threadfence();                                   // the cut lists are complete before their counts show
+    nseg[2 * c] = cnt[0]; nseg[2 * c + 1] = cnt[1];
   }
 }
 
