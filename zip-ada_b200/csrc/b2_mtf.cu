@@ -261,7 +261,14 @@ k_mtf_seq(const B2SortTile *__restrict__ segs, u32 n_segs, const B2Job *__restri
 __global__ void __launch_bounds__(32 * MS_WARPS)
 k_mtf_seq8(const B2SortTile *__restrict__ segs, u32 n_segs, const B2Job *__restrict__ jobs, const u8 *__restrict__ bwt,
            const u32 *__restrict__ m16, const u32 *__restrict__ m256, u8 *__restrict__ idx_out) {
+  // Per unit: the list at the segment start (bytes in list order), the dense code of every byte (its
+  // rank among the bytes in use) and, from both, the PLACE of every code in the list.  Phase 2 keeps the
+  // places, not the list: lane g of a group holds the places of codes 8g .. 8g+7 as bytes of two
+  // registers.  A byte b with place r is coded as r; then every place below r moves up by one (a per-byte
+  // compare and add on the packed registers) and b's place becomes 0.  No list shifting, no search.
   __shared__ u8 lists[MS_WARPS][4][256];
+  __shared__ u8 ctab[MS_WARPS][4][256];
+  __shared__ __align__(8) u8 place0[MS_WARPS][4][64];
   const u32 l = lane_id(), gl = l & 7u, grp = l >> 3;
   const u32 unit0 = (blockIdx.x * MS_WARPS + warp_id()) * 4;
   if (unit0 >= n_segs) return;
@@ -271,7 +278,17 @@ k_mtf_seq8(const B2SortTile *__restrict__ segs, u32 n_segs, const B2Job *__restr
       const B2SortTile sg = segs[unit0 + u];
       const B2Job &job = jobs[sg.job];
       const u32 off = job.pos_off;
-      mtf_build_list(job, bwt + off, m16 + (size_t)(off >> 4) * 8, m256 + (size_t)(off >> 8) * 8, sg.start, lists[warp_id()][u]);
+      u8 *lst = lists[warp_id()][u], *ct = ctab[warp_id()][u], *pl = place0[warp_id()][u];
+      mtf_build_list(job, bwt + off, m16 + (size_t)(off >> 4) * 8, m256 + (size_t)(off >> 8) * 8, sg.start, lst);
+      u32 pre = 0;                                   // bytes in use below 32 * (my word)
+      for (u32 q = 0; q < 8; q++) {
+        const u32 wv = job.in_use[q];
+        ct[32 * q + l] = (u8)(pre + __popc(wv & ((1u << l) - 1u)));
+        pre += __popc(wv);
+      }
+      pl[l] = 255; pl[32 + l] = 255;                 // codes not in use never move
+      __syncwarp();
+      for (u32 pos = l; pos < job.n_used; pos += 32) pl[ct[lst[pos]]] = (u8)pos;
     }
   }
   __syncwarp();
@@ -281,16 +298,10 @@ k_mtf_seq8(const B2SortTile *__restrict__ segs, u32 n_segs, const B2Job *__restr
   const B2Job &job = jobs[sg.job];
   const u32 n = job.n, off = job.pos_off;
   const u8 *d = bwt + off;
-  const u8 *lst = lists[warp_id()][grp];
+  const u8 *ct = ctab[warp_id()][have ? grp : 0];
   const u32 p0 = sg.start, p1 = have ? min(n, sg.start + B2_MTF_SEG) : sg.start;
-  const u32 n_used = job.n_used;
-  u32 v0 = *reinterpret_cast<const u32 *>(lst + 8 * gl), v1 = *reinterpret_cast<const u32 *>(lst + 8 * gl + 4);
-  u32 live0 = 0, live1 = 0;
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    if (8 * gl + k < n_used) live0 |= 0xFFu << (8 * k);
-    if (8 * gl + 4 + k < n_used) live1 |= 0xFFu << (8 * k);
-  }
+  u32 R0 = *reinterpret_cast<const u32 *>(place0[warp_id()][have ? grp : 0] + 8 * gl);
+  u32 R1 = *reinterpret_cast<const u32 *>(place0[warp_id()][have ? grp : 0] + 8 * gl + 4);
   const u32 gbase = grp << 3;                      // first lane of my group
   u32 prevb = (have && p0 > 0) ? d[p0 - 1] : 256u;
   const u32 nb = (B2_MTF_SEG / 32);
@@ -299,6 +310,8 @@ k_mtf_seq8(const B2SortTile *__restrict__ segs, u32 n_segs, const B2Job *__restr
     if (!__any_sync(0xffffffffu, b0 < p1)) break;
     const u32 pi = b0 + 4 * gl;                    // my four positions
     const u32 word = (b0 < p1) ? *reinterpret_cast<const u32 *>(d + pi) : 0u;   // slots are 256-aligned and padded
+    const u32 cword = (u32)ct[word & 255u] | ((u32)ct[(word >> 8) & 255u] << 8) | ((u32)ct[(word >> 16) & 255u] << 16) |
+                      ((u32)ct[word >> 24] << 24);  // the codes of my four bytes
     // bits of my positions whose byte differs from the byte before it
     u32 before = __shfl_up_sync(0xffffffffu, word >> 24, 1, 8);
     if (gl == 0) before = prevb;
@@ -324,27 +337,17 @@ k_mtf_seq8(const B2SortTile *__restrict__ segs, u32 n_segs, const B2Job *__restr
       const bool act = todo != 0;
       const u32 k = act ? (u32)(__ffs(todo) - 1) : 0u;
       todo &= todo - 1;
-      const u32 wk = __shfl_sync(0xffffffffu, word, gbase + (k >> 2));
-      const u32 b = act ? ((wk >> (8 * (k & 3))) & 255u) : 0x100u;
-      const u32 sp = (b & 255u) * 0x01010101u;
-      const u32 e0 = act ? (__vcmpeq4(v0, sp) & live0) : 0u, e1 = act ? (__vcmpeq4(v1, sp) & live1) : 0u;
-      const u32 hm = (__ballot_sync(0xffffffffu, (e0 | e1) != 0) >> gbase) & 0xFFu;
-      const u32 h = hm ? (u32)(__ffs(hm) - 1) : 0u;            // group-relative lane holding b
-      const u32 kk_mine = e0 ? ((u32)(__ffs(e0) - 1) >> 3) : (e1 ? (4u + ((u32)(__ffs(e1) - 1) >> 3)) : 0u);
-      const u32 kk = __shfl_sync(0xffffffffu, kk_mine, gbase + h);
-      if (act && gl == (k >> 2)) myidx4 |= (8 * h + kk) << (8 * (k & 3));
-      const u32 m0 = kk >= 3 ? 0xFFFFFFFFu : ((1u << (8 * (kk + 1))) - 1u);
-      const u32 m1 = kk < 4 ? 0u : (kk >= 7 ? 0xFFFFFFFFu : ((1u << (8 * (kk - 3))) - 1u));
-      const u32 top = v1 >> 24;
-      u32 carry = __shfl_up_sync(0xffffffffu, top, 1, 8);
-      if (gl == 0) carry = b;
-      const u32 s0 = (v0 << 8) | carry, s1 = (v1 << 8) | (v0 >> 24);
+      const u32 ck = __shfl_sync(0xffffffffu, cword, gbase + (k >> 2));
+      const u32 c = (ck >> (8 * (k & 3))) & 63u;                 // code of the byte at position k (< 64 here)
+      const u32 sh = 8 * (c & 3u);
+      const u32 mine = (((c & 4u) ? R1 : R0) >> sh) & 255u;      // its place, if I am the lane that holds it
+      const u32 r = __shfl_sync(0xffffffffu, mine, gbase + (c >> 3));
       if (act) {
-        if (gl < h) { v0 = s0; v1 = s1; }
-        else if (gl == h) {
-          v0 = (s0 & m0) | (v0 & ~m0);
-          v1 = (s1 & m1) | (v1 & ~m1);
-        }
+        const u32 m = r * 0x01010101u;
+        R0 += __vcmpltu4(R0, m) & 0x01010101u;                   // places below r move up
+        R1 += __vcmpltu4(R1, m) & 0x01010101u;
+        if (gl == (c >> 3)) { if (c & 4u) R1 &= ~(0xFFu << sh); else R0 &= ~(0xFFu << sh); }   // the byte goes to the front
+        if (gl == (k >> 2)) myidx4 |= r << (8 * (k & 3));
       }
     }
     if (b0 < p1) {
