@@ -183,7 +183,11 @@ __device__ void mtf_build_list(const B2Job &job, const u8 *__restrict__ d, const
 __global__ void __launch_bounds__(32 * MS_WARPS)
 k_mtf_seq(const B2SortTile *__restrict__ segs, u32 n_segs, const B2Job *__restrict__ jobs, const u8 *__restrict__ bwt,
           const u32 *__restrict__ m16, const u32 *__restrict__ m256, u8 *__restrict__ idx_out) {
+  // One warp per segment; lane g holds the places of the codes 8g .. 8g+7 in the list as bytes of two
+  // registers (see k_mtf_seq8 for the scheme: no list shifting, no search).
   __shared__ u8 lists[MS_WARPS][256];
+  __shared__ u8 ctab[MS_WARPS][256];
+  __shared__ __align__(8) u8 place0[MS_WARPS][256];
   const u32 unit = blockIdx.x * MS_WARPS + warp_id();
   if (unit >= n_segs) return;
   const u32 l = lane_id();
@@ -191,24 +195,31 @@ k_mtf_seq(const B2SortTile *__restrict__ segs, u32 n_segs, const B2Job *__restri
   const B2Job &job = jobs[sg.job];
   const u32 n = job.n, off = job.pos_off;
   const u8 *d = bwt + off;
-  u8 *lst = lists[warp_id()];
+  u8 *lst = lists[warp_id()], *ct = ctab[warp_id()], *pl = place0[warp_id()];
   const u32 p0 = sg.start, p1 = min(n, sg.start + B2_MTF_SEG);
   const u32 n_used = job.n_used;
   mtf_build_list(job, d, m16 + (size_t)(off >> 4) * 8, m256 + (size_t)(off >> 8) * 8, p0, lst);
+  {
+    u32 pre = 0;                                     // bytes in use below 32 * (my word)
+    for (u32 q = 0; q < 8; q++) {
+      const u32 wv = job.in_use[q];
+      ct[32 * q + l] = (u8)(pre + __popc(wv & ((1u << l) - 1u)));
+      pre += __popc(wv);
+      pl[32 * q + l] = 255;                          // codes not in use never move (a place is at most 255 and
+    }                                                // "< r" with r <= 255 is false for them)
+    __syncwarp();
+    for (u32 pos = l; pos < n_used; pos += 32) pl[ct[lst[pos]]] = (u8)pos;
+  }
   __syncwarp();
   // ---- 2. the segment, in order ------------------------------------------------------------------
-  u32 v0 = *reinterpret_cast<const u32 *>(lst + 8 * l), v1 = *reinterpret_cast<const u32 *>(lst + 8 * l + 4);
-  // places >= n_used hold padding zeros that must not match symbol 0
-  u32 live0 = 0, live1 = 0;
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    if (8 * l + k < n_used) live0 |= 0xFFu << (8 * k);
-    if (8 * l + 4 + k < n_used) live1 |= 0xFFu << (8 * k);
-  }
+  u32 R0 = *reinterpret_cast<const u32 *>(pl + 8 * l), R1 = *reinterpret_cast<const u32 *>(pl + 8 * l + 4);
+  // With 256 bytes in use the place 255 is a real one; slots of unused codes only exist when n_used < 256,
+  // and then no real place reaches 255, so the two never meet.
   u32 prevb = p0 > 0 ? d[p0 - 1] : 256u;
   for (u32 b0 = p0; b0 < p1; b0 += 32) {
     const u32 pi = b0 + l;
     const u32 mybyte = pi < p1 ? d[pi] : 0u;
+    const u32 mycode = ct[mybyte];
     u32 myidx = 0;
     // positions whose byte differs from the one before them; the others continue a run (index 0)
     u32 before = __shfl_up_sync(0xffffffffu, mybyte, 1);
@@ -219,36 +230,15 @@ k_mtf_seq(const B2SortTile *__restrict__ segs, u32 n_segs, const B2Job *__restri
     while (todo) {
       const u32 k = (u32)(__ffs(todo) - 1);
       todo &= todo - 1;
-      const u32 b = __shfl_sync(0xffffffffu, mybyte, k);
-      const u32 sp = b * 0x01010101u;
-      const u32 e0 = __vcmpeq4(v0, sp) & live0, e1 = __vcmpeq4(v1, sp) & live1;
-      const u32 hm = __ballot_sync(0xffffffffu, (e0 | e1) != 0);
-      const u32 h = (u32)(__ffs(hm) - 1);
-      const u32 kk_mine = e0 ? ((u32)(__ffs(e0) - 1) >> 3) : (4u + ((u32)(__ffs(e1) - 1) >> 3));
-      const u32 kk = __shfl_sync(0xffffffffu, kk_mine, h);
-      if (l == k) myidx = 8 * h + kk;
-      // move to front: places below the index shift up by one, b goes to place 0
-      // bytes 0 .. kk of the hit lane take the shifted value, bytes above kk stay
-      const u32 m0 = kk >= 3 ? 0xFFFFFFFFu : ((1u << (8 * (kk + 1))) - 1u);
-      const u32 m1 = kk < 4 ? 0u : (kk >= 7 ? 0xFFFFFFFFu : ((1u << (8 * (kk - 3))) - 1u));
-      if (h == 0) {
-        // common case (index < 8): only lane 0 changes
-        if (l == 0) {
-          const u32 s0 = (v0 << 8) | b, s1 = (v1 << 8) | (v0 >> 24);
-          v0 = (s0 & m0) | (v0 & ~m0);
-          v1 = (s1 & m1) | (v1 & ~m1);
-        }
-      } else {
-        const u32 top = v1 >> 24;
-        u32 carry = __shfl_up_sync(0xffffffffu, top, 1);
-        if (l == 0) carry = b;
-        const u32 s0 = (v0 << 8) | carry, s1 = (v1 << 8) | (v0 >> 24);
-        if (l < h) { v0 = s0; v1 = s1; }
-        else if (l == h) {
-          v0 = (s0 & m0) | (v0 & ~m0);
-          v1 = (s1 & m1) | (v1 & ~m1);
-        }
-      }
+      const u32 c = __shfl_sync(0xffffffffu, mycode, k);
+      const u32 sh = 8 * (c & 3u);
+      const u32 mine = (((c & 4u) ? R1 : R0) >> sh) & 255u;      // its place, if I am the lane that holds it
+      const u32 r = __shfl_sync(0xffffffffu, mine, c >> 3);
+      const u32 m = r * 0x01010101u;
+      R0 += __vcmpltu4(R0, m) & 0x01010101u;                     // places below r move up
+      R1 += __vcmpltu4(R1, m) & 0x01010101u;
+      if (l == (c >> 3)) { if (c & 4u) R1 &= ~(0xFFu << sh); else R0 &= ~(0xFFu << sh); }   // the byte goes to the front
+      if (l == k) myidx = r;
     }
     if (pi < p1) idx_out[off + pi] = (u8)myidx;
   }
