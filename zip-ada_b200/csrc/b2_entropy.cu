@@ -630,10 +630,13 @@ k_ent_sweep(EntArgs a) {
         // cost of coder cl = excess + place, both in 4-bit fields (no carries: <= 7 + 7).  key = (cost << 3)
         // | coder0: the minimum is the cheapest coder, lowest coder on ties (strict "<" scanning cl
         // upward, :691-695).
+        // The six keys are built three at a time as bytes (even coders, odd coders) and reduced with one
+        // per-byte minimum and two scalar ones.
         const u32 sum = c16[k] + posv;
-        u32 key = 0xFFFFFFFFu;
-#pragma unroll
-        for (int cl = 0; cl < 6; cl++) key = min(key, (((sum >> (4 * cl)) & 15u) << 3) | (u32)cl);
+        const u32 ev = ((sum & 0x000F0F0Fu) << 3) | 0x00040200u;            // coders 0, 2, 4
+        const u32 od = (((sum >> 4) & 0x000F0F0Fu) << 3) | 0x00050301u;     // coders 1, 3, 5
+        const u32 m3 = __vminu4(ev, od);
+        const u32 key = min(min(m3 & 255u, (m3 >> 8) & 255u), (m3 >> 16) & 255u);
         const u32 best0 = key & 7u;
         if (active && best0 + 1 != clk) { def++; sel[g0 + k] = (u8)(best0 + 1); }
         // move to front (:707-717): places below the chosen one move down by one, the chosen one becomes 1
