@@ -326,7 +326,7 @@ __global__ void k_scan_heads(const B2SortJob *__restrict__ sj, u32 n_sj, B2Job *
 }
 
 // slot_in == nullptr: round 0, the compact list is the whole block (slot of c is c).
-__global__ void __launch_bounds__(ST_THREADS)
+__global__ void __launch_bounds__(ST_THREADS, 6)
 k_ranks(const B2SortTile *__restrict__ tiles, const B2Job *__restrict__ jobs, const u64 *__restrict__ keys,
         const u32 *__restrict__ vals, const i32 *__restrict__ carry_in, const u32 *__restrict__ tile_cnt,
         const u32 *__restrict__ slot_in, u32 *__restrict__ rank, u32 *__restrict__ sa_full,
