@@ -556,8 +556,21 @@ k_ent_cost(EntArgs a) {
   const u8 *sel = a.sel + (size_t)t * a.total_groups + job.grp_off;
   const u16 *gh = a.ghist + job.mtf_off;
   const u8 *gd = a.gdist + job.grp_off;
-  for (u32 g = threadIdx.x; g < G; g += 256) {
-    const u16 *e = gh + g * B2_GROUP_SIZE;
+  // The sparse histograms of 32 consecutive groups are one contiguous piece of 3200 bytes: every warp
+  // brings its piece to shared memory with coalesced loads, then each lane walks its own row there
+  // (rows are 25 words apart: no bank conflicts).
+  __shared__ u32 rows[8][32 * B2_GROUP_SIZE / 2];
+  const u32 wid = threadIdx.x >> 5, ln = threadIdx.x & 31u;
+  const u32 *gh32 = reinterpret_cast<const u32 *>(gh);       // the arena offset of a block is a multiple of 4 symbols
+  for (u32 gb = 0; gb < G; gb += 256) {
+    const u32 gw = gb + 32 * wid;                             // first group of my warp
+    const u32 nrow = gw < G ? min(32u, G - gw) : 0u;
+    __syncwarp();
+    for (u32 i = ln; i < nrow * (B2_GROUP_SIZE / 2); i += 32) rows[wid][i] = gh32[(size_t)gw * (B2_GROUP_SIZE / 2) + i];
+    __syncwarp();
+    const u32 g = gw + ln;
+    if (g >= G) continue;
+    const u16 *e = reinterpret_cast<const u16 *>(rows[wid]) + ln * B2_GROUP_SIZE;
     const u32 D = gd[g];
     unsigned long long acc = 0;
     for (u32 k = 0; k < D; k++) { const u32 v = e[k]; acc += lenpack[v & 511u] * (unsigned long long)(v >> 9); }
