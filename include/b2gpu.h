@@ -23,6 +23,13 @@
 extern "C" {
 #endif
 
+/* Only the entry points below are exported by libb2gpu.so. */
+#if defined(__GNUC__)
+#define B2_API __attribute__((visibility("default")))
+#else
+#define B2_API
+#endif
+
 #define B2_OK 0
 #define B2_ERR_ARGUMENT 1
 #define B2_ERR_OUTPUT_TOO_SMALL 2
@@ -45,27 +52,27 @@ typedef struct b2_encoder b2_encoder;
 /* Creates an encoder bound to CUDA device `device` (0-based).  `level` is one of B2_BLOCK_*.
  * Replaces: the per-call heap allocations of Encode (bzip2-encoding.adb:162, :263, :272, :372,
  * :1157) — the handle owns all device workspaces and reuses them across calls. */
-int b2_create(int level, int device, b2_encoder **out);
+B2_API int b2_create(int level, int device, b2_encoder **out);
 
 /* Releases everything the handle owns.  Mirrors the exception-path clean-up of
  * bzip2-encoding.adb:1128-1133, :1351-1357, :1377-1381: the Ada body calls it from a handler. */
-void b2_destroy(b2_encoder *enc);
+B2_API void b2_destroy(b2_encoder *enc);
 
 /* Upper bound of the encoded size for `n` input bytes (for sizing `out`). */
-uint64_t b2_bound(uint64_t n);
+B2_API uint64_t b2_bound(uint64_t n);
 
 /* Whole-stream encode, host buffers: produces exactly the bytes that
  * `Encode (option, size_hint)` sends through Write_Byte for the bytes that Read_Byte/More_Bytes
  * deliver (bzip2-encoding.adb:1413-1431): "BZh<level>", blocks, footer.
  * `size_hint` is the reference's size_hint (B2_UNKNOWN_SIZE = -1): it changes the cutting of the
  * last two chunks (bzip2-encoding.adb:1416-1424).  Copies in -> device and device -> out. */
-int b2_encode_stream(b2_encoder *enc, const uint8_t *in, uint64_t n, int64_t size_hint,
+B2_API int b2_encode_stream(b2_encoder *enc, const uint8_t *in, uint64_t n, int64_t size_hint,
                      uint8_t *out, uint64_t out_cap, uint64_t *out_len);
 
 /* Same, with input and output already in device memory of the handle's device (no PCIe traffic;
  * used to measure the kernels alone).  `d_in` needs 64 readable bytes of slack after `n`;
  * `d_out` must be 4-byte aligned. */
-int b2_encode_stream_device(b2_encoder *enc, const uint8_t *d_in, uint64_t n, int64_t size_hint,
+B2_API int b2_encode_stream_device(b2_encoder *enc, const uint8_t *d_in, uint64_t n, int64_t size_hint,
                             uint8_t *d_out, uint64_t out_cap, uint64_t *out_len);
 
 /* Many independent streams in one call (archive entries: every entry of a Zip archive written with
@@ -75,7 +82,7 @@ int b2_encode_stream_device(b2_encoder *enc, const uint8_t *d_in, uint64_t n, in
  * NULL = unknown_size for all).  The streams are written back to back, each 8-byte aligned, into
  * `out`; out_offsets[i] / out_lens[i] locate stream i.  Chunks of all entries share the device
  * batches, so 100 000 small entries are as efficient as one large stream. */
-int b2_encode_batch(b2_encoder *enc, uint32_t n_entries, const uint8_t *in, const uint64_t *in_offsets,
+B2_API int b2_encode_batch(b2_encoder *enc, uint32_t n_entries, const uint8_t *in, const uint64_t *in_offsets,
                     const uint64_t *sizes, const int64_t *size_hints, uint8_t *out, uint64_t out_cap,
                     uint64_t *out_offsets, uint64_t *out_lens);
 
@@ -110,17 +117,17 @@ typedef struct b2_zip_entry_info {
   uint64_t compressed_size;
   uint64_t local_header_offset;
 } b2_zip_entry_info;
-uint64_t b2_zip_bound(uint32_t n_entries, uint64_t total_name_bytes, uint64_t total_input_bytes);
-int b2_zip_create(b2_encoder *enc, uint32_t n_entries, const uint8_t *in, const uint64_t *in_offsets,
+B2_API uint64_t b2_zip_bound(uint32_t n_entries, uint64_t total_name_bytes, uint64_t total_input_bytes);
+B2_API int b2_zip_create(b2_encoder *enc, uint32_t n_entries, const uint8_t *in, const uint64_t *in_offsets,
                   const uint64_t *sizes, const char *names, const uint32_t *name_offsets,
                   const uint32_t *dos_times, const uint32_t *flags, int duplicates,
                   uint8_t *out, uint64_t out_cap, uint64_t *out_len, b2_zip_entry_info *info);
 
 /* Zip CRC-32 of a host buffer, computed on the device (zip-crc_crypto.adb:31-61: Init, Update, Final). */
-int b2_zip_crc32(b2_encoder *enc, const uint8_t *in, uint64_t n, uint32_t *crc);
+B2_API int b2_zip_crc32(b2_encoder *enc, const uint8_t *in, uint64_t n, uint32_t *crc);
 
 /* Last error message of the calling thread (never NULL). */
-const char *b2_last_error(void);
+B2_API const char *b2_last_error(void);
 
 /* ---------------------------------------------------------------------------------------------
  * Measurement taps (bench.py).  Times are CUDA-event times on the handle's stream. */
@@ -143,9 +150,9 @@ typedef struct b2_stats {
 
 /* level 0: off; 1: events around every encode call and every radix scatter launch (no extra
  * synchronisation); 2: also per-stage timers (adds stream synchronisations, diagnostic only). */
-int b2_set_timing(b2_encoder *enc, int level);
-int b2_get_stats(b2_encoder *enc, b2_stats *out);
-int b2_reset_stats(b2_encoder *enc);
+B2_API int b2_set_timing(b2_encoder *enc, int level);
+B2_API int b2_get_stats(b2_encoder *enc, b2_stats *out);
+B2_API int b2_reset_stats(b2_encoder *enc);
 
 /* ---------------------------------------------------------------------------------------------
  * Parity taps (tests only): the intermediates the reference prints at verbosity `detailed` /
@@ -158,7 +165,7 @@ typedef struct b2_block_info {
 /* One Encode_Block (bzip2-encoding.adb:148) on the device.  Any output pointer may be NULL.
  * rle_out/bwt_out: >= len*5/4+64 bytes; mtf_out: >= len*5/4+64 uint16; sel_out: >= 18002;
  * lens_out: 6*258 bytes; bits_out: the block's bitstream from bit 0. */
-int b2_dbg_block(b2_encoder *enc, const uint8_t *raw, uint32_t len,
+B2_API int b2_dbg_block(b2_encoder *enc, const uint8_t *raw, uint32_t len,
                  uint8_t *rle_out, uint8_t *bwt_out, uint16_t *mtf_out, uint8_t *sel_out,
                  uint8_t *lens_out, uint8_t *bits_out, uint64_t bits_cap, b2_block_info *info);
 
@@ -172,10 +179,10 @@ typedef struct b2_chunk_trace {
 } b2_chunk_trace;
 
 /* Trace of the last b2_encode_stream* call: one record per chunk. */
-int b2_get_trace(b2_encoder *enc, b2_chunk_trace *out, uint64_t cap, uint64_t *n);
+B2_API int b2_get_trace(b2_encoder *enc, b2_chunk_trace *out, uint64_t cap, uint64_t *n);
 
 /* Segment_by_Entropy cut list of one chunk of the last call (profile 0 = segmented_1, 1 = segmented_2). */
-int b2_get_segments(b2_encoder *enc, uint64_t chunk, int profile, uint32_t *cuts, uint32_t cap, uint32_t *n);
+B2_API int b2_get_segments(b2_encoder *enc, uint64_t chunk, int profile, uint32_t *cuts, uint32_t cap, uint32_t *n);
 
 #ifdef __cplusplus
 }

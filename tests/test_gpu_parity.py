@@ -114,3 +114,28 @@ def test_other_levels(b2mod, level):
         out = e.encode(data, data.size).tobytes()
     assert out == orc.encode_stream(data, level, data.size)
     assert bz2.decompress(out) == data.tobytes()
+
+
+@pytest.mark.parametrize("nsym", [1, 2, 3, 5, 9, 17, 33, 64, 65, 129, 255, 256])
+def test_block_alphabet_sizes(enc9, nsym):
+    """Every width of the packed round-0 sort keys (1 .. 8 bits per character) and both move-to-front kernels
+    (<= 64 distinct bytes: four segments per warp; more: one): no long runs, so RLE1 adds no count bytes."""
+    rng = np.random.default_rng(900 + nsym)
+    alphabet = rng.permutation(256)[:nsym].astype(np.uint8)
+    if nsym == 1:
+        data = np.full(3000, alphabet[0], np.uint8)          # a single byte value: runs only (count bytes join the alphabet)
+    else:
+        idx = rng.integers(0, nsym, 40_000)
+        idx[1:][idx[1:] == idx[:-1]] = (idx[1:][idx[1:] == idx[:-1]] + 1) % nsym     # avoid runs of four
+        data = alphabet[idx]
+    _cmp_block(enc9, data, "alphabet%d" % nsym)
+
+
+def test_batch_of_mixed_alphabets_equals_single_calls(enc9):
+    """The key width of a batch is set by its largest alphabet; results must not depend on the company."""
+    rng = np.random.default_rng(77)
+    entries = [datagen.text(60_000, 5), rng.integers(0, 2, 50_000).astype(np.uint8), datagen.random_bytes(30_000, 6),
+               np.frombuffer(b"abc" * 9000, np.uint8), datagen.sparse_binary(70_000, 8)]
+    outs = enc9.encode_batch(entries, "size")
+    for e, o in zip(entries, outs):
+        assert o == orc.encode_stream(e, 9, e.size)
