@@ -43,6 +43,7 @@ def main():
     a = ap.parse_args()
     golden = json.load(open(os.path.join(ROOT, "tests", "golden", "oracle_vectors.json")))
     bad = 0
+    compared = 0
     with tempfile.TemporaryDirectory() as tmp:
         for name, fn in make_inputs.CASES.items():
             data, level, hint = fn()
@@ -68,8 +69,12 @@ def main():
                     continue
             ok = hashlib.sha256(got).hexdigest() == golden[name]["sha256"]
             bad += not ok
+            compared += 1
             print("%-28s %s  (%d bytes, oracle %d)" % (name, "IDENTICAL" if ok else "DIFFERENT", len(got), golden[name]["len"]))
-    print("oracle pinned" if bad == 0 else "%d case(s) differ: see SURVEY.md 8c for the two places that depend on the GNAT runtime" % bad)
+    if compared == 0:
+        print("nothing compared: give --zipada and / or --bzip2-enc")
+        return 2
+    print("oracle pinned on %d case(s)" % compared if bad == 0 else "%d case(s) differ: see SURVEY.md 8c for the two places that depend on the GNAT runtime" % bad)
     return 1 if bad else 0
 
 
