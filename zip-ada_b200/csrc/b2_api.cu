@@ -153,7 +153,7 @@ struct b2_encoder {
   std::vector<b2_chunk_trace> trace;
   b2_stats stats;
   B2SortStats sort_stats;
-  size_t batch_positions = 512u << 20;  // positions per batch (env B2GPU_BATCH_POSITIONS); big batches amortise the latency-bound kernels
+  size_t batch_positions = 1536ull << 20;  // positions per batch (env B2GPU_BATCH_POSITIONS); big batches amortise the latency-bound kernels (about 45 B of device memory per position)
   size_t batch_jobs_max = 32768;        // blocks per batch    (env B2GPU_BATCH_JOBS)
   int n_workspaces = 1;                 // batches in flight   (env B2GPU_PIPELINE)
   u64 launches_other = 0;
