@@ -154,7 +154,7 @@ struct b2_encoder {
   b2_stats stats;
   B2SortStats sort_stats;
   size_t batch_positions = 1536ull << 20;  // positions per batch (env B2GPU_BATCH_POSITIONS); big batches amortise the latency-bound kernels (about 45 B of device memory per position)
-  size_t batch_jobs_max = 32768;        // blocks per batch    (env B2GPU_BATCH_JOBS)
+  size_t batch_jobs_max = 65535;        // blocks per batch    (env B2GPU_BATCH_JOBS)
   int n_workspaces = 1;                 // batches in flight   (env B2GPU_PIPELINE)
   u64 launches_other = 0;
   cudaEvent_t ev[2] = {nullptr, nullptr};
@@ -766,7 +766,7 @@ int b2_create(int level, int device, b2_encoder **out) {
   memset(&e->stats, 0, sizeof e->stats);
   memset(&e->sort_stats, 0, sizeof e->sort_stats);
   if (const char *s = getenv("B2GPU_BATCH_POSITIONS")) { long long v = atoll(s); if (v >= (1 << 20)) e->batch_positions = (size_t)v; }
-  if (const char *s = getenv("B2GPU_BATCH_JOBS")) { long long v = atoll(s); if (v >= 8) e->batch_jobs_max = (size_t)v; }
+  if (const char *s = getenv("B2GPU_BATCH_JOBS")) { long long v = atoll(s); if (v >= 8) e->batch_jobs_max = (size_t)std::min<long long>(v, 65535); }   // grid.y of the per-(triple, block) kernels
   if (const char *s = getenv("B2GPU_PIPELINE")) { int v = atoi(s); if (v >= 1 && v <= 8) e->n_workspaces = v; }
   B2_CUDA_CHECK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
   B2_CUDA_CHECK(cudaStreamCreateWithFlags(&e->st2, cudaStreamNonBlocking));
