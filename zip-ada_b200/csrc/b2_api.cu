@@ -6,9 +6,13 @@
 // blocks ("jobs") that are encoded in batches on the device.  The only serial cross-chunk data are
 // scalars — incoming bit offset, winner, combined CRC — replayed here in O(#chunks).
 //
-// Batches are pipelined: each of W workspaces owns a CUDA stream and a host worker thread, so the
-// latency-bound kernels of one batch (ranking heap sorts, selector sweeps, scans) overlap with the
-// bandwidth-bound kernels (radix passes) of another.  Winners are resolved strictly in chunk order.
+// Flow of one call: chunk cutting (tile scans + one warp walking the chunk chain) -> entropy
+// segmentation (for a single large stream on a second CUDA stream, following the chain chunk by chunk)
+// -> the calling thread plans batches of whole chunks as their cut lists arrive and hands them to the
+// worker thread(s); each of W workspaces (default 1) owns a CUDA stream and a worker that runs
+// RLE1 -> BWT sort -> MTF/RLE2 -> entropy search -> bit packing for its batch and then resolves the
+// winners of its chunks strictly in chunk order (shift-concatenation into the output stream).
+// b2_zip_create adds the archive side around the same machinery (Zip CRC-32, headers, Store fallback).
 #include "b2_common.cuh"
 #include "b2_kernels.h"
 #include "../../include/b2gpu.h"

@@ -4,21 +4,24 @@
 // an O(N) comparator that is a total order (:229-255), so the sorted matrix, its last column and
 // the origin pointer are unique functions of the block; any sort is admissible.
 //
-// Here: cyclic prefix doubling with filtering.  Round 0 sorts every rotation by its first 8 bytes
-// (64-bit key, 8 LSD radix passes of 8 bits).  A rank is the row index ("slot") of the first row of
-// a class, so equal prefixes share a rank.  After every round the rows that are alone in their class
-// are final; only the others ("active" rows) are compacted and re-sorted in round r >= 1 by the
-// 40-bit key (rank[i] << 20 | rank[(i+h) mod n]) with 5 passes, h = 8, 16, ..., and written back to
-// the slots they came from (a class occupies a contiguous range of slots, and the key's high part
-// keeps classes in place).  A block is finished when no row is active or when the compared prefix
-// covers the whole rotation (periodic blocks: the classes are then sets of EQUAL rotations; their
-// last-column bytes coincide and the origin pointer is the first row of the class of rotation 0,
-// because the reference orders equal rotations by offset and rotation 0 has offset 0, :254,
-// :276-279).  All blocks of a batch are sorted together: every radix pass is segmented by block
-// through a tile table, so no block id is needed in the key.
+// Here: cyclic prefix doubling with filtering.  Round 0 sorts every rotation by its first 8 bytes,
+// each byte replaced by its rank among the bytes in use and packed with b = ceil (log2 (largest
+// alphabet of the batch)) bits: b LSD radix passes of 8 bits (5 for plain text, 8 for binary data).  A
+// rank is the row index ("slot") of the first row of a class, so equal prefixes share a rank.  After
+// every round the rows that are alone in their class are final; only the others ("active" rows) are
+// compacted and re-sorted in round r >= 1 by the 40-bit key (rank[i] << 20 | rank[(i+h) mod n]) with 5
+// passes, h = 8, 16, ..., and written back to the slots they came from (a class occupies a contiguous
+// range of slots, and the key's high part keeps classes in place).  A block is finished when no row is
+// active or when the compared prefix covers the whole rotation (periodic blocks: the classes are then
+// sets of EQUAL rotations; their last-column bytes coincide and the origin pointer is the first row of
+// the class of rotation 0, because the reference orders equal rotations by offset and rotation 0 has
+// offset 0, :254, :276-279).  All blocks of a batch are sorted together: every radix pass is segmented
+// by block through a tile table, so no block id is needed in the key.
 //
-// Radix pass = histogram (8 B/elt read) + per-block scan (tiny) + scatter (12 B/elt read, 12 B/elt
-// write, staged through shared memory so the writes leave as runs).
+// Radix pass = ONE kernel (k_scatter): 12 B/row read, 12 B/row written, staged through shared memory so
+// that the writes leave as runs.  The digit totals of all passes of a round come from one read of the
+// keys (k_hist_all: LSD passes only permute the rows of a block), the per-tile offsets from a decoupled
+// look-back inside the scatter (see k_scatter).
 #include "b2_common.cuh"
 #include "b2_kernels.h"
 
