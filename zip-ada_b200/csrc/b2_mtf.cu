@@ -81,9 +81,10 @@ k_mtf_masks(const B2SortTile *__restrict__ tiles, const B2Job *__restrict__ jobs
 //     symbols appear in the order of their last occurrence, which IS the list order; whole
 //     16- / 256-position segments that hold no symbol not yet seen are skipped through their masks;
 //     symbols never seen keep the initial increasing order (:374-376) behind the seen ones.
-//  2. The segment is then processed in order with the list spread over the warp (lane l holds
-//     places 8l .. 8l+7): find by byte compare + ballot, move to front by a byte shift with the
-//     carry passed between neighbouring lanes (:384-396).
+//  2. The segment is then processed in order.  Not the list is kept but its inverse, the PLACE of every
+//     byte (as a dense code) in the list, eight places per lane as bytes of two registers: a byte with
+//     place r is coded as r, every place below r moves up by one (a per-byte compare-and-add on the
+//     packed registers), its own place becomes 0 (:384-396 without the search and without the shift).
 // ---------------------------------------------------------------------------------------------
 #define MS_WARPS 4
 
