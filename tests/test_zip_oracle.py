@@ -85,3 +85,18 @@ def test_zip64_end_records_when_65535_entries():
     assert len(z.infolist()) == n and z.infolist()[-1].filename == "e65534"
     arc2, _ = orc.zip_create([("e%05d" % i, b"") for i in range(1000)], 9)
     assert arc2[-42:-38] != b"PK\x06\x07"
+
+
+def test_pin_script_reads_an_entry_payload():
+    """tools/pin_against_reference.py extracts the raw payload of a one-entry archive (as zipada would write it)."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location(
+        "pin", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "pin_against_reference.py"))
+    pin = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(pin)
+    data = datagen.text(50_000, 12).tobytes()
+    arc, methods = orc.zip_create([("in.bin", data)], 9)
+    method, payload = pin.payload_of_single_entry(arc)
+    assert method == 12 == methods[0]
+    assert payload == orc.encode_stream(data, 9, len(data))
