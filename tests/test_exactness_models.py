@@ -1,0 +1,193 @@
+"""CPU models of the three restructurings whose exactness the CUDA kernels rely on, checked against the
+literal sequential algorithms in pure Python (no GPU, no oracle):
+
+ * k_segment: the sequential FP64 running sum of Segment_by_Entropy (data_segmentation.adb:75-90) replayed
+   as a composition of integer maps "k -> k + a[k mod 4]" over two binades (zip-ada_b200/csrc/b2_segment.cu);
+ * k_mtf_seq / k_mtf_seq8: move-to-front kept as the PLACE of every symbol instead of the list
+   (zip-ada_b200/csrc/b2_mtf.cu; bzip2-encoding.adb:384-396);
+ * k_ent_pm: the forward package-merge may stop as soon as a list repeats the one below
+   (zip-ada_b200/csrc/b2_entropy.cu; huffman-encoding-length_limited_coding.adb:131-163).
+"""
+import math
+import random
+from fractions import Fraction
+
+
+# ---------------------------------------------------------------------------------------------------
+# 1. FP64 replay
+# ---------------------------------------------------------------------------------------------------
+def term_map(d, B, coarse):
+    """The map of fl (k u' + d) on k, u' = 2^(B-52), when the result lies on the grid u' (coarse False)
+    or 2 u' (coarse True): four increments indexed by k mod 4 (mirror of pf_term in b2_segment.cu)."""
+    x = Fraction(d) * Fraction(2) ** (52 - B)          # exact: d is a double, the scale a power of two
+    X = math.floor(x)
+    fr = x - X
+    a = [0, 0, 0, 0]
+    if not coarse:
+        m = X + (1 if fr > Fraction(1, 2) else 0)
+        tie = fr == Fraction(1, 2)
+        for r in range(4):
+            a[r] = m + (1 if (tie and ((r + m) & 1)) else 0)
+    else:
+        for b in range(2):
+            Y = X + b
+            odd = Y & 1
+            m = (Y >> 1) + (1 if (odd and fr > 0) else 0)
+            tie = bool(odd) and fr == 0
+            for qp in range(2):
+                a[2 * qp + b] = 2 * (m + (1 if (tie and ((qp + m) & 1)) else 0)) - b
+    return a
+
+
+def compose(f, g):                                      # first f, then g (pf_compose)
+    return [f[i] + g[(i + f[i]) & 3] for i in range(4)]
+
+
+def t_table():
+    inv = 1.0 / 16000.0
+    return [0.0] + [-(c * inv) * math.log(c * inv) for c in range(1, 16002)]
+
+
+def _replay_case(rng, E0, n_terms, T):
+    """Serial chain of IEEE adds against the composed maps; returns the number of adds checked."""
+    eb = math.frexp(E0)[1] - 1                          # E0 in [2^eb, 2^(eb+1))
+    B = eb - 1 if E0 < 1.5 * 2.0 ** eb else eb          # two binades [2^B, 2^(B+2)) as in the kernel
+    u = 2.0 ** (B - 52)
+    split = 2.0 ** (B + 1)
+    k = int(Fraction(E0) / Fraction(u))
+    assert float(k) * u == E0
+    e = E0
+    total = [0, 0, 0, 0]
+    k0 = k
+    checked = 0
+    for _ in range(n_terms):
+        c = rng.randrange(1, 16000)
+        for d in (-T[c], T[c + 1]):                     # "remove the old element, add the new one" (:75-83)
+            e2 = e + d                                  # IEEE double add, round to nearest even
+            if not (2.0 ** B <= e2 < 2.0 ** (B + 2)):
+                return checked                          # the kernel restarts here; nothing to compare
+            f = term_map(d, B, e2 >= split)
+            k = k + f[k & 3]
+            assert Fraction(k) * Fraction(u) == Fraction(e2), (E0, d, e, e2, k)
+            total = compose(total, f)
+            assert k0 + total[k0 & 3] == k              # the composed map gives the same sum
+            e = e2
+            checked += 1
+    return checked
+
+
+def test_fp64_sum_replayed_by_integer_maps():
+    rng = random.Random(20261017)
+    T = t_table()
+    checked = 0
+    # sums inside a binade, just above / just below a power of two (intermediate sums cross it), ties
+    for E0 in (2.9, 3.000000000000001, 1.02, 2.0000000001, 3.9999, 4.3, 5.545, 1.999, 0.51, 0.26, 7.6):
+        for _ in range(6):
+            checked += _replay_case(rng, E0 * (1 + rng.random() * 1e-9), 400, T)
+    assert checked > 20_000
+
+
+def test_ties_go_to_the_even_neighbour_in_both_grids():
+    # d = half a grid step: the result depends on the parity of k (fine grid) or of k / 2 (coarse grid)
+    B = 0
+    u = 2.0 ** (B - 52)
+    for k in (2 ** 52 + 4, 2 ** 52 + 5, 2 ** 52 + 6, 2 ** 52 + 7):
+        e = float(k) * u
+        f = term_map(u / 2, B, False)
+        assert Fraction(k + f[k & 3]) * Fraction(u) == Fraction(e + u / 2)
+    for k in (2 ** 53 + 4, 2 ** 53 + 6, 2 ** 53 + 8, 2 ** 53 + 10):
+        e = float(k) * u
+        for d in (u, 3 * u, -u, 0.5 * u, 1.5 * u):
+            f = term_map(d, B, True)
+            assert Fraction(k + f[k & 3]) * Fraction(u) == Fraction(e + d), (k, d)
+
+
+def test_map_composition_is_associative():
+    rng = random.Random(7)
+    T = t_table()
+    maps = [term_map(rng.choice((-1, 1)) * T[rng.randrange(1, 16000)], 1, rng.random() < 0.5) for _ in range(64)]
+    left = [0, 0, 0, 0]
+    for m in maps:
+        left = compose(left, m)
+    halves = [[0, 0, 0, 0], [0, 0, 0, 0]]
+    for i, m in enumerate(maps):
+        halves[i >= 32] = compose(halves[i >= 32], m)
+    assert compose(halves[0], halves[1]) == left
+
+
+# ---------------------------------------------------------------------------------------------------
+# 2. move-to-front by places
+# ---------------------------------------------------------------------------------------------------
+def test_mtf_places_equal_the_shifted_list():
+    rng = random.Random(11)
+    for n_used in (1, 2, 7, 64, 65, 256):
+        symbols = rng.sample(range(256), n_used)
+        lst = sorted(symbols)                            # the list starts in increasing order (:374-376)
+        code = {b: i for i, b in enumerate(sorted(symbols))}
+        place = [255] * 256
+        for pos, b in enumerate(lst):
+            place[code[b]] = pos
+        data = [rng.choice(symbols[:max(1, n_used // 3)]) if rng.random() < 0.7 else rng.choice(symbols) for _ in range(5000)]
+        for b in data:
+            r_list = lst.index(b)                        # the reference: linear search, shift (:384-396)
+            lst.insert(0, lst.pop(r_list))
+            c = code[b]
+            r = place[c]
+            for j in range(256):                         # the kernels: per-byte compare-and-add on packed places
+                if place[j] < r:
+                    place[j] += 1
+            place[c] = 0
+            assert r == r_list
+        assert [place[code[b]] for b in lst] == list(range(n_used))
+
+
+# ---------------------------------------------------------------------------------------------------
+# 3. forward package-merge with early stop
+# ---------------------------------------------------------------------------------------------------
+def package_merge_lengths(weights, max_bits, early_stop):
+    leaves = sorted(weights)
+    n = len(leaves)
+    need = 2 * n - 2
+    lists = [(list(leaves), [False] * n)]               # (weights, is_package)
+    for lev in range(1, max_bits):
+        prev = lists[-1][0]
+        pk = [prev[2 * b] + prev[2 * b + 1] for b in range(len(prev) // 2)]
+        cur, flag, i, j = [], [], 0, 0
+        while (i < n or j < len(pk)) and len(cur) < need:
+            if j < len(pk) and (i >= n or pk[j] <= leaves[i]):      # a package goes before a leaf of equal weight
+                cur.append(pk[j]); flag.append(True); j += 1
+            else:
+                cur.append(leaves[i]); flag.append(False); i += 1
+        lists.append((cur, flag))
+        if early_stop and cur == prev:
+            while len(lists) < max_bits:
+                lists.append((cur, flag))                # every list above repeats this one
+            break
+    lens = [0] * n
+    k = need
+    for lev in range(max_bits - 1, -1, -1):
+        flag = lists[lev][1]
+        p = sum(flag[:k])
+        for a in range(k - p):
+            lens[a] += 1
+        k = 2 * p
+    return lens
+
+
+def test_package_merge_may_stop_when_a_list_repeats():
+    rng = random.Random(5)
+    for _ in range(300):
+        n = rng.choice((2, 3, 5, 17, 40, 90, 258))
+        kind = rng.random()
+        if kind < 0.3:
+            w = [1] * n                                              # Avoid_Zeros on an empty cluster
+        elif kind < 0.6:
+            w = [max(1, int(1000 * rng.random() ** 6)) for _ in range(n)]
+        else:
+            w = [rng.randrange(1, 50) for _ in range(n)]
+        for max_bits in (15, 16, 17):
+            if (1 << max_bits) < n:
+                continue
+            full = package_merge_lengths(w, max_bits, False)
+            assert package_merge_lengths(w, max_bits, True) == full
+            assert sum(Fraction(1, 2 ** l) for l in full) <= 1 and max(full) <= max_bits
