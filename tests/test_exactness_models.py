@@ -191,3 +191,21 @@ def test_package_merge_may_stop_when_a_list_repeats():
             full = package_merge_lengths(w, max_bits, False)
             assert package_merge_lengths(w, max_bits, True) == full
             assert sum(Fraction(1, 2 ** l) for l in full) <= 1 and max(full) <= max_bits
+
+
+# ---------------------------------------------------------------------------------------------------
+# 4. selector sweep: cost excesses clipped at 7
+# ---------------------------------------------------------------------------------------------------
+def test_clipped_excess_picks_the_same_coder():
+    """k_ent_cost keeps, per group, the bits of every coder above the cheapest one clipped at 7 (4-bit fields);
+    the sweep adds the coder's place 1..6 in the selector list and takes the strict minimum, lowest coder on ties
+    (bzip2-encoding.adb:683-695).  A coder 7 or more bits above the cheapest can never win."""
+    rng = random.Random(3)
+    for _ in range(20000):
+        ec = rng.randrange(2, 7)
+        bits = [rng.randrange(0, 400) if rng.random() < 0.5 else rng.randrange(100, 120) for _ in range(ec)]
+        places = rng.sample(range(1, ec + 1), ec)
+        exact = min(range(ec), key=lambda c: (bits[c] + places[c], c))
+        mn = min(bits)
+        clipped = min(range(ec), key=lambda c: (min(bits[c] - mn, 7) + places[c], c))
+        assert exact == clipped
