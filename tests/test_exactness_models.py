@@ -209,3 +209,39 @@ def test_clipped_excess_picks_the_same_coder():
         mn = min(bits)
         clipped = min(range(ec), key=lambda c: (min(bits[c] - mn, 7) + places[c], c))
         assert exact == clipped
+
+
+# ---------------------------------------------------------------------------------------------------
+# 5. chunk chain: 32 probes per trip
+# ---------------------------------------------------------------------------------------------------
+def search32(tincl, lo, hi, target):
+    """The warp-wide search of k_cut_chain (b2_chunks.cu): first index in [lo, hi) whose inclusive prefix
+    reaches `target`, or hi; lane l probes the end of the l-th of 32 sub-ranges."""
+    while lo < hi:
+        span = hi - lo
+        step = (span + 31) // 32
+        probes = [lo + min((l + 1) * step, span) - 1 for l in range(32)]
+        hits = [tincl[p] >= target for p in probes]
+        if not any(hits):
+            lo = hi
+            break
+        k = hits.index(True)
+        hi = probes[k]
+        lo = lo + k * step
+    return lo
+
+
+def test_search32_is_a_lower_bound():
+    import bisect
+    rng = random.Random(9)
+    for _ in range(400):
+        n = rng.randrange(1, 5000)
+        inc, run = [], 0
+        for _ in range(n):
+            run += rng.choice((0, 0, 1, 5, 2048, 2560))
+            inc.append(run)
+        lo = rng.randrange(0, n)
+        hi = rng.randrange(lo, n + 1)
+        for target in (0, 1, inc[lo], inc[min(n - 1, (lo + hi) // 2)] + rng.choice((0, 1)), inc[-1] + 7):
+            want = lo + bisect.bisect_left(inc[lo:hi], target)
+            assert search32(inc, lo, hi, target) == want
