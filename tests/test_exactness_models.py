@@ -245,3 +245,44 @@ def test_search32_is_a_lower_bound():
         for target in (0, 1, inc[lo], inc[min(n - 1, (lo + hi) // 2)] + rng.choice((0, 1)), inc[-1] + 7):
             want = lo + bisect.bisect_left(inc[lo:hi], target)
             assert search32(inc, lo, hi, target) == want
+
+
+# ---------------------------------------------------------------------------------------------------
+# 6. radix scatter: dispatch order of the tiles and the look-back chain
+# ---------------------------------------------------------------------------------------------------
+def tiles_rr(ntiles_per_block, group):
+    """Mirror of build_tiles_rr (b2_bwt.cu): blocks in groups; inside a group tile k of every block, then
+    tile k + 1 of every block; every tile remembers the place of the tile before it in its block."""
+    rr, last = [], [None] * len(ntiles_per_block)
+    for g0 in range(0, len(ntiles_per_block), group):
+        blocks = range(g0, min(len(ntiles_per_block), g0 + group))
+        for k in range(max(ntiles_per_block[j] for j in blocks)):
+            for j in blocks:
+                if ntiles_per_block[j] > k:
+                    rr.append((j, k, last[j]))
+                    last[j] = len(rr) - 1
+    return rr
+
+
+def test_scatter_dispatch_order_and_lookback_offsets():
+    rng = random.Random(13)
+    for group in (1, 4, 128):
+        nt = [rng.randrange(1, 12) for _ in range(rng.randrange(1, 300))]
+        rr = tiles_rr(nt, group)
+        assert len(rr) == sum(nt)
+        seen = {}
+        for pos, (j, k, prev) in enumerate(rr):
+            assert k == seen.get(j, 0)                      # the tiles of a block come in order
+            seen[j] = k + 1
+            assert (prev is None) == (k == 0)
+            if prev is not None:
+                assert prev < pos and rr[prev][:2] == (j, k - 1)   # the predecessor was dispatched earlier: no deadlock
+        # a tile's offset for a digit = digit base of the block + counts of the digit in the block's earlier tiles,
+        # obtained by walking the chain until an inclusive state is met
+        counts = [[rng.randrange(0, 9) for _ in range(4)] for _ in rr]       # 4 digits are enough here
+        inclusive = [None] * len(rr)
+        for pos, (j, k, prev) in enumerate(rr):                              # dispatch order = completion order here
+            excl = [0] * 4 if prev is None else inclusive[prev]
+            inclusive[pos] = [e + c for e, c in zip(excl, counts[pos])]
+            want = [sum(counts[p][d] for p, (jj, kk, _) in enumerate(rr) if jj == j and kk < k) for d in range(4)]
+            assert excl == want
