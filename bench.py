@@ -1,18 +1,30 @@
 #!/usr/bin/env python
 """bench.py — BZip2 encode throughput of the b2gpu path (BASELINE.json metric).
 
-  python bench.py --gpus N --steps K --warmup W            our CUDA path
-  python bench.py --impl reference --gpus N ...            the reference's CPU algorithm (oracle port) on host cores
+  python bench.py --gpus N --steps K --warmup W [--config text|mixed|entries|zipf]     our CUDA path
+  python bench.py --impl reference --gpus N ...      the reference's CPU algorithm (oracle port) on the host cores
 
-A "step" is one pass of the hot path over one synthetic stream: `Encode (block_900k, size_hint =>
-size)` of a --size-mb MiB English-like text (BASELINE.json configs[1]: 1 GB text, 900 KB blocks, 1xB200).
-`value` = uncompressed MB/s with the input resident in HBM; `e2e` = the same through
-b2_encode_stream with HOST buffers (pinned), host<->device copies inside the timed region.
-Under torchrun every rank encodes its own stream on its own GPU (weak scaling, no collective:
-streams / chunks are independent); time = max over ranks.
+A "step" is one pass of the hot path over one synthetic input (tests/corpus.py, seeded, integer arithmetic:
+the same bytes from numpy and from torch on the GPU):
+  text    (default; BASELINE.json configs[1])  ONE stream of N GiB of order-3 Markov text,
+          `Encode (block_900k, size_hint => size)`.  N = 1: b2_encode_stream(_device) on one handle.  N > 1
+          (torchrun, one rank per GPU): the SAME call sharded over the ranks — every rank owns a contiguous
+          byte range of the stream (b2_shard_*, zip-ada_b200/sharding.py); two scalar exchanges, no bulk data
+          between GPUs; 1 GiB per GPU (weak scaling), the output is one .bz2 stream
+  mixed   (configs[2]) ONE 4 GiB stream of 16 MiB stripes {Markov text, random, sparse}, the same stream at
+          every N (strong scaling)
+  entries (configs[4]) archive of 100 000 entries of 1-64 KiB through b2_zip_create; under torchrun the entries
+          are dealt to the ranks (longest first) and every rank writes the archive of its share
+  zipf    round 1's friendlier text (Zipf pseudo-words over 30 symbols), kept for comparison
+`value` = uncompressed MB/s with the input resident in HBM; `e2e` = the same call with HOST buffers (pinned),
+host<->device copies inside the timed region.  Time = wall clock between barriers, max over ranks.
+The output of the timed steps is hashed (SHA-256) and compared with the oracle's golden
+(tests/golden/stream_sha.json, tools/make_golden_sha.py) and decoded with libbz2, outside the timed region.
 """
 import argparse
+import bz2
 import ctypes as C
+import hashlib
 import importlib
 import json
 import os
@@ -28,45 +40,9 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import numpy as np
 
-
-def gen_text_torch(nbytes, seed, device):
-    """Zipf pseudo-word text (same model as tests/datagen.text), generated on the GPU."""
-    import torch
-    import datagen
-    tab, lens = datagen._vocab(np.random.default_rng(12345))
-    nwords = tab.shape[0]
-    ranks = np.arange(1, nwords + 1, dtype=np.float64)
-    p = 1.0 / ranks ** 1.07
-    cdf = torch.tensor(np.cumsum(p / p.sum()), dtype=torch.float64, device=device)
-    tab_t = torch.tensor(tab, device=device)
-    lens_t = torch.tensor(lens.astype(np.int64), device=device)
-    g = torch.Generator(device=device)
-    g.manual_seed(seed)
-    out = torch.empty(nbytes + 256, dtype=torch.uint8, device=device)
-    out[nbytes:] = 0
-    total = 0
-    while total < nbytes:
-        k = int(min(8_000_000, (nbytes - total) // 5 + 4096))
-        ids = torch.searchsorted(cdf, torch.rand(k, generator=g, device=device, dtype=torch.float64)).clamp_(0, nwords - 1)
-        l = lens_t[ids]
-        r = torch.rand(k, generator=g, device=device)
-        sep = torch.full((k,), 32, dtype=torch.uint8, device=device)
-        sep[r < 0.08] = ord(",")
-        sep[r < 0.045] = ord(".")
-        sep[r < 0.012] = 10
-        rows = torch.zeros((k, 18), dtype=torch.uint8, device=device)
-        rows[:, :16] = tab_t[ids]
-        ar = torch.arange(k, device=device)
-        rows[ar, l] = sep
-        extra = (sep == ord(",")) | (sep == ord("."))
-        rows[ar[extra], l[extra] + 1] = 32
-        flat = rows.reshape(-1)
-        flat = flat[flat != 0]
-        m = min(flat.numel(), nbytes - total)
-        out[total:total + m] = flat[:m]
-        total += m
-        del rows, flat, ids
-    return out
+MiB = 1 << 20
+GiB = 1 << 30
+SEEDS = {"markov": 0x5EED0001, "mixed": 0x5EED0004}
 
 
 class ClockSampler:
@@ -125,36 +101,122 @@ def hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic():
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture, if any."""
-    p = os.path.join(ROOT, "profiles", "scatter_traffic.json")
-    if os.path.exists(p):
-        try:
-            return json.load(open(p))
-        except Exception:
-            return None
-    return None
+def golden(key):
+    p = os.path.join(ROOT, "tests", "golden", "stream_sha.json")
+    try:
+        return json.load(open(p)).get(key)
+    except Exception:
+        return None
 
 
-def cpu_port_sample(sample, threads):
-    """The oracle (CPU port of the reference algorithm) on `threads` host threads, each encoding its
-    own piece of `sample` as a stream.  Returns (MB/s, seconds)."""
+# ---- CPU legs: the oracle (CPU port of the reference's algorithm); the only place bench.py touches oracle/ ----
+def cpu_oracle(sample, threads, hint=None, bwt_mode=0):
+    """The oracle on one stream with its chunks spread over `threads` host threads (1 = the sequential
+    restatement).  Returns (MB/s, seconds, bytes)."""
     import oracle_lib as orc
     orc.lib()
-    pieces = np.array_split(sample, threads)
-    res = [None] * threads
+    t0 = time.perf_counter()
+    out = orc.encode_stream(sample, 9, sample.size if hint is None else hint, bwt_mode, threads=threads if threads > 1 else 0)
+    dt = time.perf_counter() - t0
+    return sample.size / 1e6 / dt, dt, out
+
+
+def cpu_streams(pieces):
+    """One independent stream per host thread ('one process per core')."""
+    import oracle_lib as orc
+    orc.lib()
+    res = [None] * len(pieces)
 
     def work(i):
-        res[i] = orc.encode_stream(pieces[i], 9, pieces[i].size)   # ctypes releases the GIL
+        res[i] = orc.encode_stream(pieces[i], 9, pieces[i].size)      # ctypes releases the GIL
 
     t0 = time.perf_counter()
-    ths = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(len(pieces))]
     for t in ths:
         t.start()
     for t in ths:
         t.join()
     dt = time.perf_counter() - t0
-    return sample.size / 1e6 / dt, dt, res
+    return sum(p.size for p in pieces) / 1e6 / dt, dt
+
+
+def workload_desc(cfg, n, world):
+    if cfg == "text":
+        return "ONE stream of %d MiB of order-3 Markov text (SURVEY 8d generator, seed 5eed0001), BZip2_3 / block_900k, size_hint = size%s" % (
+            n // MiB, "" if world == 1 else ", sharded over %d ranks by byte range (b2_shard_*)" % world)
+    if cfg == "mixed":
+        return "ONE stream of %d MiB, 16 MiB stripes cycling {Markov text, random bytes, sparse binary} (seed 5eed0004), BZip2_3, size_hint = size%s" % (
+            n // MiB, "" if world == 1 else ", sharded over %d ranks by byte range" % world)
+    if cfg == "zipf":
+        return "%d MiB of Zipf pseudo-word text over 30 symbols (round 1's workload), BZip2_3, size_hint = size" % (n // MiB)
+    return cfg
+
+
+def reference_arm(args, rank, world):
+    """--impl reference: the reference is Ada and there is no Ada compiler in this image, so the arm
+    is the oracle port of its algorithm on the host cores: every step encodes a bounded prefix of the arm's
+    workload as ONE stream, its chunks spread over all host threads."""
+    if rank != 0:
+        return
+    import corpus
+    cfg = args.config
+    threads = os.cpu_count() or 1
+    name = {"text": "markov", "mixed": "mixed", "zipf": "markov", "entries": "markov"}[cfg]
+    seed = SEEDS[name]
+    n_full = stream_size(args, world)
+    total_steps = args.warmup + args.steps
+    budget_s = 150.0
+    # calibrate on one chunk-sized piece, then size the per-step sample for the time budget
+    probe = corpus.workload(name, 2 * MiB, seed)
+    r1, dt1, _ = cpu_oracle(probe, 1)
+    per_step = max(8.0, budget_s / max(1, total_steps))
+    sample_n = int(min(n_full, max(4 * MiB, r1 * 1e6 * per_step * threads * 0.8)))
+    sample_n = max(threads * 2 * MiB, sample_n) if n_full >= threads * 2 * MiB else n_full
+    sample = corpus.workload(name, n_full, seed, hi=sample_n)
+    vals = []
+    for s in range(total_steps):
+        mbps, dt, _ = cpu_oracle(sample, threads)
+        if s >= args.warmup:
+            vals.append((mbps, dt))
+        if sum(v[1] for v in vals) > 2 * budget_s:
+            break
+    v = statistics.mean(x[0] for x in vals)
+    ms = 1000 * statistics.mean(x[1] for x in vals)
+    # the other CPU modes BASELINE.md lists, each on a small bounded sample
+    modes = {"single_thread_MBps": round(r1, 3), "per_thread_MBps_in_this_run": round(v / threads, 3)}
+    try:
+        four, _, _ = cpu_oracle(sample[:8 * MiB], 4)
+        modes["one_stream_4_threads_MBps"] = round(four, 3)           # the reference's own parallelism: 4 tasks per chunk (:1226-1303)
+        pcs, _ = cpu_streams([np.ascontiguousarray(x) for x in np.array_split(sample[:threads * 2 * MiB], threads)])
+        modes["one_stream_per_thread_MBps"] = round(pcs, 3)
+        fa, _, _ = cpu_oracle(sample[:256 * 1024], 1, bwt_mode=1)
+        modes["faithful_heap_sort_bwt_single_thread_MBps_256KiB"] = round(fa, 4)   # the reference's own sort (heap sort, O(N) comparator)
+        t0 = time.perf_counter()
+        subprocess.run(["bzip2", "-9", "-c"], input=sample[:16 * MiB].tobytes(), stdout=subprocess.DEVNULL, check=True)
+        modes["usr_bin_bzip2_9_single_thread_MBps (unrelated yardstick, not the reference)"] = round(16 * MiB / 1e6 / (time.perf_counter() - t0), 2)
+    except Exception as ex:
+        modes["error"] = str(ex)
+    sample_desc = ("first %d bytes of the arm's stream (%s) encoded as ONE stream with size_hint = its size, chunks of 900 000 "
+                   "post-RLE1 bytes spread over %d host threads; oracle = C++ port of the reference (fast prefix-doubling BWT, "
+                   "so faster than the reference's heap sort)" % (sample.size, name, threads))
+    config = {"workload": workload_desc(cfg, n_full, world), "stream_bytes": n_full, "reference_arm_sample_bytes": int(sample.size)}
+    print(json.dumps({"impl": "reference", "metric": "bzip2_encode_MBps_900k", "value": round(v, 3), "unit": "MB/s", "n_gpus": args.gpus,
+                      "steps": len(vals), "warmup": args.warmup, "ms_per_step": round(ms, 1), "higher_is_better": True,
+                      "scaling": scaling_of(cfg), "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
+                      "cpu_baseline": {"value": round(v, 3), "unit": "MB/s", "cores": threads, "kind": "port", "sample": sample_desc, "modes": modes},
+                      "e2e": {"value": round(v, 3), "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def scaling_of(cfg):
+    return "strong" if cfg == "mixed" else "weak"
+
+
+def stream_size(args, world):
+    if args.size_mb:
+        return args.size_mb * MiB
+    if args.config == "mixed":
+        return 4 * GiB
+    return world * GiB
 
 
 def main():
@@ -163,60 +225,28 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--size-mb", type=int, default=1024, help="MiB of synthetic text per stream (per GPU)")
+    ap.add_argument("--config", default="text", choices=["text", "mixed", "entries", "zipf"])
+    ap.add_argument("--size-mb", type=int, default=0, help="stream size in MiB (default: 1024 per GPU for text, 4096 for mixed)")
+    ap.add_argument("--entries", type=int, default=100000)
     ap.add_argument("--cpu-sample-mb", type=float, default=4.0)
+    ap.add_argument("--no-decode", action="store_true", help="skip the libbz2 round trip of the output")
     ap.add_argument("--stage-times", action="store_true", help="one extra diagnostic step with per-stage timers")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    n = args.size_mb << 20
-    workload = "%d MiB synthetic English-like text (Zipf pseudo-words), BZip2_3 / block_900k, size_hint = size" % args.size_mb
-    config = {"workload": workload, "stream_bytes_per_gpu": n, "streams": world,
-              "l2": "inputs (>= 1 GiB per step) and sort state are far larger than the 126 MB L2; no flush needed"}
-
     if args.impl == "reference":
-        # The reference is Ada; no Ada compiler exists in this image, so the reference arm is the oracle
-        # port of its algorithm, on all host threads, each step a bounded sample.
-        if rank != 0:
-            return
-        import datagen
-        threads = os.cpu_count() or 1
-        per_thread = int(1.0 * (1 << 20))
-        vals = []
-        for s in range(args.warmup + args.steps):
-            sample = datagen.text(per_thread * threads, 0x5EED0001 + s)
-            mbps, dt, _ = cpu_port_sample(sample, threads)
-            if s >= args.warmup:
-                vals.append((mbps, dt))
-            if s >= args.warmup and sum(v[1] for v in vals) > 240:
-                break
-        v = statistics.mean(x[0] for x in vals)
-        ms = 1000 * statistics.mean(x[1] for x in vals)
-        sample_desc = "%d pieces of %d bytes of the same text model, one stream per host thread" % (threads, per_thread)
-        print(json.dumps({"impl": "reference", "metric": "bzip2_encode_MBps_900k", "value": v, "unit": "MB/s", "n_gpus": args.gpus,
-                          "steps": len(vals), "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-                          "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
-                          "cpu_baseline": {"value": v, "unit": "MB/s", "cores": threads, "kind": "port", "sample": sample_desc},
-                          "e2e": {"value": v, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
-        return
+        return reference_arm(args, rank, world)
 
     import torch
     import torch.distributed as dist
+    import corpus
     b2 = importlib.import_module("zip-ada_b200")
+    sharding = importlib.import_module("zip-ada_b200.sharding")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    d_in = gen_text_torch(n, 0x5EED0001 + rank, dev)
-    cap = int(b2.lib().b2_bound(n)) + 1024 * (n // 40000 + 16)
-    d_out = torch.empty(cap, dtype=torch.uint8, device=dev)
-    h_in = torch.empty(n, dtype=torch.uint8, pin_memory=True)
-    h_in.copy_(d_in[:n])
-    h_out = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
-    torch.cuda.synchronize()
-    enc = b2.Encoder(b2.block_900k, local_rank)
-    enc.set_timing(1)
 
     def barrier():
         torch.cuda.synchronize()
@@ -231,84 +261,285 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- device-resident ("value") -------------------------------------------------------------
-    out_len = 0
+    def sumrank(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    enc = b2.Encoder(b2.block_900k, local_rank)
+    enc.set_timing(1)
+    if args.config == "entries":
+        return run_entries(args, rank, local_rank, world, dev, enc, b2, sharding, barrier, maxrank, sumrank)
+
+    # ---- one stream ------------------------------------------------------------------------------------------
+    cfg = args.config
+    n = stream_size(args, world)
+    if cfg == "zipf":
+        import datagen
+        name, seed = "zipf", 0x5EED0001
+        assert world == 1, "the zipf workload is single-GPU only"
+        host_data = datagen.text(n, seed)
+        d_in = torch.zeros(n + 256, dtype=torch.uint8, device=dev)
+        d_in[:n] = torch.from_numpy(host_data).to(dev)
+        bounds, span = [0, n], (0, n)
+    else:
+        name = {"text": "markov", "mixed": "mixed"}[cfg]
+        seed = SEEDS[name]
+        if world == 1:
+            bounds, span = [0, n], (0, n)
+        else:
+            bounds, spans = sharding.plan(n, world, 9, b2.lib())
+            span = spans[rank]
+        lo, hi = span
+        d_in = torch.zeros(hi - lo + 256, dtype=torch.uint8, device=dev)
+        d_in[:hi - lo] = corpus.workload(name, n, seed, torch, dev, lo=lo, hi=hi)
+    lo, hi = span
+    n_local = hi - lo
+    cap = int(b2.lib().b2_bound(n_local)) + 1024 * (n_local // 40000 + 16)
+    d_out = torch.empty(cap, dtype=torch.uint8, device=dev)
+    h_in = torch.empty(n_local, dtype=torch.uint8, pin_memory=True)
+    h_in.copy_(d_in[:n_local])
+    h_out = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
+    torch.cuda.synchronize()
+    comm = sharding.TorchComm(dist, rank, world, dev) if world > 1 else None
+
+    def step(device_resident):
+        """One Encode of the whole stream; returns this rank's piece (byte offset, length) and the stream length."""
+        if world == 1:
+            if device_resident:
+                ln = enc.encode_device_ptr(d_in.data_ptr(), n, n, d_out.data_ptr(), cap)
+            else:
+                ln = enc.encode_ptr(h_in.data_ptr(), n, n, h_out.data_ptr(), cap)
+            return 0, ln, ln
+        r = sharding.encode_sharded(enc, comm, d_in.data_ptr() if device_resident else h_in.data_ptr(), device_resident, n, n, bounds, span,
+                                    d_out.data_ptr() if device_resident else h_out.data_ptr(), device_resident, cap)
+        return r["byte_offset"], r["length"], r["total_length"]
+
+    # ---- device-resident ("value") -------------------------------------------------------------------------
     for _ in range(args.warmup):
-        out_len = enc.encode_device_ptr(d_in.data_ptr(), n, n, d_out.data_ptr(), cap)
+        piece = step(True)
     barrier()
     enc.reset_stats()
     sampler = ClockSampler(local_rank)
     sampler.start()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        out_len = enc.encode_device_ptr(d_in.data_ptr(), n, n, d_out.data_ptr(), cap)
+        piece = step(True)
     barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
     st = enc.stats()
-    dev_ms = st.call_ms                    # CUDA events, first to last operation of every call
-    t_dev = maxrank(dev_ms / 1000.0)
     t_wall = maxrank(wall)
-    value = world * n * args.steps / 1e6 / t_wall
-    dev_bytes = bytes(d_out[:out_len].cpu().numpy().tobytes()) if rank == 0 else b""
-    # ---- end to end through the C ABI with host buffers ------------------------------------------
-    e_len = enc.encode_ptr(h_in.data_ptr(), n, n, h_out.data_ptr(), cap)
+    t_dev = maxrank(st.call_ms / 1000.0)
+    value = n * args.steps / 1e6 / t_wall
+    dev_piece = d_out[:piece[1]].cpu().numpy().copy()
+    # ---- end to end through the C ABI with host buffers ----------------------------------------------------
+    e_piece = step(False)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        e_len = enc.encode_ptr(h_in.data_ptr(), n, n, h_out.data_ptr(), cap)
+        e_piece = step(False)
     barrier()
     e_wall = maxrank(time.perf_counter() - t0)
-    e2e = world * n * args.steps / 1e6 / e_wall
+    e2e = n * args.steps / 1e6 / e_wall
+    host_piece = h_out[:e_piece[1]].numpy()
+    same_paths = bool(piece == e_piece and np.array_equal(dev_piece, host_piece))
+    # ---- statistics over all ranks ----------------------------------------------------------------------------
+    tot = {k: sumrank(float(getattr(st, k))) for k in ("scatter_elems", "scatter_ms", "scatter_launches", "sort_elems_round0", "sort_elems_later",
+                                                      "sort_ms", "kernel_launches", "blocks", "chunks", "block_bytes", "input_bytes")}
+    max_sort_ms = maxrank(st.sort_ms)
+    sort_rounds = int(st.sort_rounds)
+    h2d = sumrank(float(n_local))
+    d2h = sumrank(float(e_piece[1]))
     stage_ms = None
-    if args.stage_times:
+    if args.stage_times and world == 1:
         enc.reset_stats(); enc.set_timing(2)
-        enc.encode_device_ptr(d_in.data_ptr(), n, n, d_out.data_ptr(), cap)
+        step(True)
         s2 = enc.stats()
         stage_ms = dict(zip(["cut_segment", "rle1", "bwt_sort", "mtf_rle2", "entropy_search", "pack", "concat", "copies"],
                             [round(x, 2) for x in s2.stage_ms]))
         stage_ms["scatter_ms"] = round(s2.scatter_ms, 2)
         enc.set_timing(1)
+    # ---- the stream the timed steps wrote: assemble on rank 0 (outside the timed region), hash, decode -----------
+    total_len = piece[2]
+    if world > 1:
+        meta = torch.tensor([piece[0], piece[1]], dtype=torch.int64, device=dev)
+        metas = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(metas, meta)
+        metas = [[int(x) for x in m.tolist()] for m in metas]
+        if rank == 0:
+            pieces = [(metas[0][0], dev_piece)]
+            for r in range(1, world):
+                buf = torch.empty(max(1, metas[r][1]), dtype=torch.uint8, device=dev)
+                dist.recv(buf, r)
+                pieces.append((metas[r][0], buf[:metas[r][1]].cpu().numpy()))
+            stream = b2.assemble_pieces(pieces, total_len)
+        else:
+            buf = d_out[:max(1, piece[1])].contiguous()
+            dist.send(buf, 0)
+    else:
+        stream = dev_piece
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        dist.destroy_process_group()
         return
-    same = dev_bytes == h_out[:e_len].numpy().tobytes()
-    # ---- roofline of the dominant kernel (radix scatter of the BWT sort) ---------------------------
+    sha = hashlib.sha256(stream.tobytes()).hexdigest()
+    gkey = "%s:%d:%x:9" % (name, n, seed)
+    g = golden(gkey)
+    parity = {"device_path_equals_host_path": same_paths, "output_sha256": sha, "golden_key": gkey,
+              "golden_sha256": g["sha256"] if g else None,
+              "timed_output_equals_oracle_golden": (bool(g["sha256"] == sha and g["bytes"] == int(total_len)) if g else None)}
+    decode_thread = None
+    if not args.no_decode and n <= 2 * GiB:
+        def decode():
+            t0 = time.perf_counter()
+            try:
+                dec = bz2.decompress(stream.tobytes())
+                if cfg == "zipf":
+                    ok = dec == host_data.tobytes()
+                elif world == 1:
+                    ok = dec == h_in.numpy().tobytes()
+                else:
+                    ok = hashlib.sha256(dec).hexdigest() == (g["input_sha256"] if g else None) and len(dec) == n
+                parity["libbz2_decodes_timed_output_to_input"] = bool(ok)
+            except Exception as ex:
+                parity["libbz2_decodes_timed_output_to_input"] = "error: %s" % ex
+            parity["decode_seconds"] = round(time.perf_counter() - t0, 1)
+        decode_thread = threading.Thread(target=decode)
+        decode_thread.start()
+    else:
+        parity["libbz2_decodes_timed_output_to_input"] = "skipped (output of %d MiB input: SHA-256 against the oracle golden only)" % (n // MiB)
+    # ---- roofline -------------------------------------------------------------------------------------------------
     peak, peak_src = hbm_peak()
-    alg_bytes = 24.0 * st.scatter_elems          # 8 B key + 4 B index, read once + written once
-    achieved = alg_bytes / (st.scatter_ms / 1000.0) / 1e9 if st.scatter_ms > 0 else 0.0
-    tr = ncu_traffic()
+    alg_bytes = 24.0 * tot["scatter_elems"]          # 8 B key + 4 B index, read once + written once
+    achieved = alg_bytes / (tot["scatter_ms"] / 1000.0) / 1e9 if tot["scatter_ms"] > 0 else 0.0
+    # SURVEY 8(d) stage figure: (24 p + 12) n per round, summed = 24 * (rows moved by all passes) + 12 * (rows entering all rounds)
+    stage_bytes = 24.0 * tot["scatter_elems"] + 12.0 * (tot["sort_elems_round0"] + tot["sort_elems_later"])
+    stage_gbs = stage_bytes / (tot["sort_ms"] / 1000.0) / 1e9 if tot["sort_ms"] > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": "k_scatter (one LSD radix pass of the BWT rotation sort: ranking, decoupled look-back and scatter in one kernel)",
                 "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "peak_source": peak_src, "traffic": tr.get("dram_bytes_per_launch") if tr else None,
-                "algorithmic_bytes_per_launch": alg_bytes / max(1, st.scatter_launches),
-                "launches": int(st.scatter_launches), "avg_launch_ms": st.scatter_ms / max(1, st.scatter_launches),
-                "share_of_step": round(st.scatter_ms / max(1e-9, dev_ms), 4),
-                "sort_elems_round0": int(st.sort_elems_round0 // args.steps), "sort_elems_later": int(st.sort_elems_later // args.steps),
-                "sort_rounds": int(st.sort_rounds // args.steps)}
-    # ---- CPU baseline: oracle port, 1 thread, bounded sample of the same workload -------------------
-    sample_n = int(args.cpu_sample_mb * (1 << 20))
+                "peak_source": peak_src, "traffic": None,
+                "traffic_note": "not measured in this run; the ncu --set full capture of the kernel is under profiles/",
+                "algorithmic_bytes_per_launch": alg_bytes / max(1, tot["scatter_launches"]),
+                "launches": int(tot["scatter_launches"]), "avg_launch_ms": tot["scatter_ms"] / max(1, tot["scatter_launches"]),
+                "share_of_step": round(st.scatter_ms / max(1e-9, st.call_ms), 4),
+                "sort_stage": {"algorithmic_bytes": stage_bytes, "ms": round(tot["sort_ms"], 2), "achieved": round(stage_gbs, 1),
+                               "frac": round(stage_gbs / peak, 4), "share_of_step": round(max_sort_ms / max(1e-9, 1000 * t_dev), 4),
+                               "formula": "sum over rounds of (24 p + 12) n = 24 x rows moved by all radix passes + 12 x rows entering all rounds, over the CUDA-event time of the whole sort stage"},
+                "sort_elems_round0": int(tot["sort_elems_round0"] // args.steps), "sort_elems_later": int(tot["sort_elems_later"] // args.steps),
+                "rows_moved_by_passes": int(tot["scatter_elems"] // args.steps), "sort_rounds_rank0": sort_rounds // args.steps}
+    # ---- CPU baseline: oracle port, 1 thread, bounded sample of the same workload ---------------------------------------
+    sample_n = int(min(n_local, args.cpu_sample_mb * MiB))
     sample = h_in[:sample_n].numpy()
-    mbps, dt, res = cpu_port_sample(sample, 1)
-    gpu_sample = enc.encode(sample, sample.size).tobytes()
-    parity_sample = gpu_sample == res[0]
+    mbps, dt, ref_out = cpu_oracle(sample, 1)
+    with b2.Encoder(b2.block_900k, local_rank) as enc2:
+        gpu_sample = enc2.encode(sample, sample.size).tobytes()
+    parity["sample_equals_oracle"] = bool(gpu_sample == ref_out)
+    if decode_thread:
+        decode_thread.join()
     line = {"metric": "bzip2_encode_MBps_900k", "value": round(value, 2), "unit": "MB/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": round(1000 * t_wall / args.steps, 2), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
+            "warmup": args.warmup, "ms_per_step": round(1000 * t_wall / args.steps, 2), "higher_is_better": True, "scaling": scaling_of(cfg),
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": workload_desc(cfg, n, world), "stream_bytes": n, "streams": 1, "ranks": world,
+                       "bytes_per_rank": [b - a for a, b in zip(bounds, bounds[1:])],
+                       "l2": "inputs (>= 0.5 GiB per GPU and step) and sort state are far larger than the 126 MB L2; no flush needed"},
             "device_event_ms_per_step": round(1000 * t_dev / args.steps, 2),
-            "e2e": {"value": round(e2e, 2), "unit": "MB/s", "h2d_bytes_per_step": n, "d2h_bytes_per_step": int(e_len)},
-            "gpu_launches": int(st.kernel_launches),
+            "e2e": {"value": round(e2e, 2), "unit": "MB/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(tot["kernel_launches"]),
             "roofline": roofline,
             "cpu_baseline": {"value": round(mbps, 3), "unit": "MB/s", "cores": 1, "kind": "port",
-                             "sample": "first %.1f MiB of the same stream, oracle (CPU port of the reference algorithm), %.1f s" % (args.cpu_sample_mb, dt)},
+                             "sample": "first %.1f MiB of the same stream, oracle (CPU port of the reference algorithm, sequential), %.1f s" % (sample_n / MiB, dt)},
             "clocks": clocks,
-            "compressed_bytes": int(out_len), "ratio": round(out_len / n, 4),
-            "blocks_per_step": int(st.blocks // args.steps), "chunks_per_step": int(st.chunks // args.steps),
-            "sorted_bytes_per_input_byte": round(st.block_bytes / max(1, st.input_bytes), 3),
-            "parity": {"device_path_equals_host_path": bool(same), "sample_equals_oracle": bool(parity_sample)}}
+            "compressed_bytes": int(total_len), "ratio": round(total_len / n, 4),
+            "blocks_per_step": int(tot["blocks"] // args.steps), "chunks_per_step": int(tot["chunks"] // args.steps),
+            "sorted_bytes_per_input_byte": round(tot["block_bytes"] / max(1, tot["input_bytes"]), 3),
+            "parity": parity}
     if stage_ms:
         line["stage_ms"] = stage_ms
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_entries(args, rank, local_rank, world, dev, enc, b2, sharding, barrier, maxrank, sumrank):
+    """configs[4]: zip_with_many_files-style archive (test/zip_with_many_files.adb:64-71) through b2_zip_create."""
+    import torch
+    import torch.distributed as dist
+    import zipfile
+    import io
+    import corpus
+    n_entries = args.entries
+    flat, offs, sizes, kinds = corpus.entries(n_entries)
+    mine = sharding.assign_entries([int(s) for s in sizes], world)[rank]
+    # this rank's entries, packed
+    m_sizes = sizes[mine]
+    m_offs = np.zeros(len(mine), np.uint64)
+    pos = 0
+    for k, i in enumerate(mine):
+        m_offs[k] = pos
+        pos += (int(sizes[i]) + 15) & ~15
+    m_flat = np.zeros(max(pos, 1), np.uint8)
+    for k, i in enumerate(mine):
+        m_flat[int(m_offs[k]):int(m_offs[k]) + int(sizes[i])] = flat[int(offs[i]):int(offs[i]) + int(sizes[i])]
+    names_list = [("entry_%06d.dat" % i).encode() for i in mine]
+    name_offs = np.zeros(len(mine) + 1, np.uint32)
+    name_offs[1:] = np.cumsum([len(x) for x in names_list])
+    names = b"".join(names_list)
+    h_flat = torch.from_numpy(m_flat).pin_memory()
+    hf = h_flat.numpy()
+    nbytes = int(m_sizes.sum())
+    for _ in range(max(1, args.warmup)):
+        arch, info = enc.zip_create_flat(hf, m_offs, m_sizes, names, name_offs, want_info=True)
+    barrier()
+    enc.reset_stats()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        arch, info = enc.zip_create_flat(hf, m_offs, m_sizes, names, name_offs, want_info=True)
+    barrier()
+    wall = maxrank(time.perf_counter() - t0)
+    clocks = sampler.stop()
+    st = enc.stats()
+    total_bytes = sumrank(float(nbytes))
+    stored = sumrank(float(sum(1 for x in info if x.zip_type == 0)))
+    launches = sumrank(float(st.kernel_launches))
+    arch_bytes = sumrank(float(arch.size))
+    # every rank checks its own archive with an independent reader
+    z = zipfile.ZipFile(io.BytesIO(arch.tobytes()))
+    ok = z.testzip() is None and len(z.namelist()) == len(mine)
+    k = len(mine) // 2
+    ok = ok and z.read(names_list[k].decode()) == flat[int(offs[mine[k]]):int(offs[mine[k]]) + int(sizes[mine[k]])].tobytes()
+    all_ok = sumrank(1.0 if ok else 0.0) == world
+    if rank != 0:
+        dist.destroy_process_group()
+        return
+    mbps = total_bytes * args.steps / 1e6 / wall
+    # CPU baseline: the oracle's Zip.Create restatement on a bounded sample of the same entries, 1 thread
+    import oracle_lib as orc
+    ns = min(150, len(mine))
+    ents = [("entry_%06d.dat" % i, flat[int(offs[i]):int(offs[i]) + int(sizes[i])]) for i in mine[:ns]]
+    t0 = time.perf_counter()
+    ref_arch, _ = orc.zip_create(ents, 9)
+    dt = time.perf_counter() - t0
+    sample_bytes = sum(e[1].size for e in ents)
+    gpu_arch = enc.zip_create(ents)
+    line = {"metric": "bzip2_encode_MBps_900k", "value": round(mbps, 2), "unit": "MB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(1000 * wall / args.steps, 2), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic",
+            "config": {"workload": "archive of %d entries of 1-64 KiB (3/4 Markov text, 1/4 random; sizes about log-uniform), Zip.Create + BZip2_3 per entry through b2_zip_create%s"
+                                   % (n_entries, "" if world == 1 else "; entries dealt to %d ranks, one archive volume per rank" % world),
+                       "entries": n_entries, "input_bytes": int(total_bytes)},
+            "entries_per_s": round(n_entries * args.steps / wall, 1), "stored_entries": int(stored), "archive_bytes": int(arch_bytes),
+            "e2e": {"value": round(mbps, 2), "unit": "MB/s", "h2d_bytes_per_step": int(total_bytes), "d2h_bytes_per_step": int(arch_bytes),
+                    "note": "b2_zip_create takes and returns host buffers: the timed call is the end-to-end call"},
+            "gpu_launches": int(launches),
+            "roofline": None,
+            "cpu_baseline": {"value": round(sample_bytes / 1e6 / dt, 3), "unit": "MB/s", "cores": 1, "kind": "port", "entries_per_s": round(ns / dt, 1),
+                             "sample": "first %d entries of rank 0's share through the oracle's Zip.Create restatement, %.1f s" % (ns, dt)},
+            "clocks": clocks,
+            "parity": {"python_zipfile_testzip_all_ranks": bool(all_ok), "sample_archive_equals_oracle": bool(gpu_arch.tobytes() == ref_arch)}}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -86,6 +86,57 @@ B2_API int b2_encode_batch(b2_encoder *enc, uint32_t n_entries, const uint8_t *i
                     const uint64_t *sizes, const int64_t *size_hints, uint8_t *out, uint64_t out_cap,
                     uint64_t *out_offsets, uint64_t *out_lens);
 
+/* ---- One stream over several devices (north star: "the input stream is sharded block-wise
+ * across the 8 GPUs of one box with per-device streams and pinned host buffers, no collective") -------------
+ * The reference's own parallelism is four tasks sharing one chunk (bzip2-encoding.adb:1226-1303); chunks
+ * themselves are independent once their start is known.  A stream is split into contiguous byte ranges, one
+ * per shard (handle = device); a shard owns the chunks that START in its range.  What crosses shards is
+ * scalars only:
+ *   - the cutting is a chain (Data_Acquisition, :1160-1208): shard r learns where its first chunk starts from
+ *     shard r-1 (`entry` / `handoff`);
+ *   - the winner of a chunk depends on the incoming bit offset mod 8 (:1319-1325) and the combined CRC is
+ *     folded block by block (:990): each shard reports, for each of the 8 possible incoming offsets, the bits
+ *     it appends and its CRC fold (b2_shard_link); b2_shard_resolve composes them in shard order.
+ * Call order per shard: b2_shard_open (upload + scans, asynchronous) -> b2_shard_cut (needs the previous
+ * shard's handoff) -> b2_shard_encode -> [exchange links, b2_shard_resolve] -> b2_shard_finish.
+ * b2_encode_stream_multi does all of it for the handles of one process (one host thread per handle); under
+ * one-process-per-GPU launchers the two exchanges are a point-to-point send of 8 bytes and an all-gather of
+ * 128 bytes per rank (bench.py). */
+typedef struct b2_shard_link {
+  uint64_t total_bits[8];   /* bits appended when the shard's first chunk starts at bit offset k mod 8 */
+  uint32_t crc_rot[8];      /* combined CRC: crc_out = rotl (crc_in, crc_rot[k]) xor crc_fold[k] */
+  uint32_t crc_fold[8];
+} b2_shard_link;
+
+/* Bytes a shard needs beyond the end of its range (a chunk is at most 10 x capacity raw bytes, :1156). */
+B2_API uint64_t b2_shard_margin(int level);
+/* Range bounds[r] .. bounds[r+1] of every shard (bounds has n_shards + 1 entries, 4096-byte aligned inside).
+ * Later shards start later (the cutting is serial), so their shares shrink by stagger_permille / 1000 per shard
+ * (-1: default / env B2GPU_SHARD_STAGGER). */
+B2_API int b2_shard_plan(uint64_t n, int n_shards, int level, int stagger_permille, uint64_t *bounds);
+/* `in` (host, or device memory of the handle's device) holds the stream bytes [base, base + n_local): from
+ * the start of the shard's range to min (stream_size, own_end + b2_shard_margin).  own_end = bounds[r + 1]. */
+B2_API int b2_shard_open(b2_encoder *enc, const uint8_t *in, int in_is_device, uint64_t base, uint64_t n_local,
+                         uint64_t stream_size, int64_t size_hint, uint64_t own_end);
+/* entry: stream offset where this shard's first chunk starts (0 for the first shard; the previous shard's
+ * handoff otherwise).  handoff: where the next shard's first chunk starts. */
+B2_API int b2_shard_cut(b2_encoder *enc, uint64_t entry, uint64_t *handoff);
+B2_API int b2_shard_encode(b2_encoder *enc, b2_shard_link *link);
+/* bit_offsets[r] = bit offset in the stream of shard r's first block (bit_offsets[0] = 32, behind "BZh9"),
+ * crcs[r] = combined CRC before it; both arrays have n_shards + 1 entries; the stream has
+ * (bit_offsets[n_shards] + 80 + 7) / 8 bytes. */
+B2_API int b2_shard_resolve(const b2_shard_link *links, int n_shards, uint64_t *bit_offsets, uint32_t *crcs);
+/* Writes the shard's piece of the stream to `out`: stream bytes [*out_byte_offset, + *out_len).  The first and
+ * the last byte may be shared with the neighbouring pieces (each piece holds only its own bits there: OR them);
+ * their values are also returned separately.  The first shard writes the stream header, the last the footer. */
+B2_API int b2_shard_finish(b2_encoder *enc, uint64_t bit_offset, uint32_t crc_in, uint8_t *out, int out_is_device,
+                           uint64_t out_cap, uint64_t *out_byte_offset, uint64_t *out_len, uint8_t *first_byte,
+                           uint8_t *last_byte);
+/* Encode (option, size_hint) of one stream on the devices of `encs` (host buffers; pinned memory makes the
+ * copies asynchronous).  Byte-identical to b2_encode_stream on one handle. */
+B2_API int b2_encode_stream_multi(b2_encoder **encs, int n_encs, const uint8_t *in, uint64_t n, int64_t size_hint,
+                                  uint8_t *out, uint64_t out_cap, uint64_t *out_len);
+
 /* ---- Archive side: batched Zip.Create for BZip2 entries ------------------------------------------
  * One call = Create_Archive, Add_Stream for every entry, Finish (zip-create.adb:194-297, :645-756)
  * with Compress_Method = BZip2_1/2/3 (the level of `enc`), no password.  The bytes written to `out`
@@ -146,6 +197,7 @@ typedef struct b2_stats {
   double scatter_ms;             /* their summed duration (only with b2_set_timing(enc, 1)) */
   double stage_ms[8];            /* cut+segment, rle1, sort, mtf, entropy, pack, concat, copies (timing level 2) */
   double call_ms;                /* CUDA-event time of the encode calls, first to last operation on the stream (timing >= 1) */
+  double sort_ms;                /* CUDA-event time of the BWT sort stage (all its kernels), summed over batches (timing >= 1) */
 } b2_stats;
 
 /* level 0: off; 1: events around every encode call and every radix scatter launch (no extra

@@ -32,6 +32,8 @@
 #include <vector>
 #include <algorithm>
 #include <numeric>
+#include <atomic>
+#include <thread>
 
 typedef uint8_t u8;
 typedef uint16_t u16;
@@ -935,6 +937,44 @@ struct StreamEncoder {
     return (u32)raw_buf_index;
   }
 
+  // The four candidate encodings of one chunk (:1223-1299), each continuing a clone of the running bit
+  // buffer (buffer, bit_index) and of the combined CRC.
+  void Encode_Variants(const u8 *raw, u32 len, u8 in_buffer, int in_bit_index, u32 in_crc,
+                       BitBuffer variant[4], u32 crc_variant[4], u32 n_seg[2]) {
+      for (int t = 0; t < 4; t++) {
+        variant[t].buffer = in_buffer; variant[t].bit_index = in_bit_index;               // :1223
+        variant[t].attach_new();                                                          // :1309-1311
+        crc_variant[t] = in_crc;                                                          // :1224
+      }
+      for (int tactic = 0; tactic < 2; tactic++) {                       // :1238-1254
+        i64 slices = tactic == 0 ? 1 : 4;
+        i64 size = (i64)len / slices;
+        i64 stop = 0, startk;
+        BlockEncoder be(cfg);
+        for (i64 count = 1; count <= slices; count++) {
+          startk = stop + 1;
+          if (count == slices) stop = len; else stop = count * size;
+          be.Encode_Block(raw + (startk - 1), stop - startk + 1, variant[tactic], crc_variant[tactic], nullptr);
+        }
+      }
+      for (int tactic = 2; tactic < 4; tactic++) {                       // :1262-1299
+        std::vector<i32> seg;
+        if (tactic == 2) segment_by_entropy(raw, (i32)len, 0.6f, 4000, 16000, seg);
+        else segment_by_entropy(raw, (i32)len, 0.4f, 8000, 16000, seg);
+        n_seg[tactic - 2] = (u32)seg.size();
+        BlockEncoder be(cfg);
+        if (seg.empty()) {
+          be.Encode_Block(raw, 0, variant[tactic], crc_variant[tactic], nullptr);
+        } else {
+          i64 index_start = 1;
+          for (i32 s : seg) {
+            be.Encode_Block(raw + (index_start - 1), s - index_start + 1, variant[tactic], crc_variant[tactic], nullptr);
+            index_start = (i64)s + 1;
+          }
+        }
+      }
+  }
+
   // :1144-1382
   void Read_and_Split_Block(BitBuffer &main_buf, i32 dyn_block_capacity) {
     u64 start = pos;
@@ -955,39 +995,8 @@ struct StreamEncoder {
       // they only touch private state, so the result is the same)
       BitBuffer variant[4];
       u32 crc_variant[4];
-      for (int t = 0; t < 4; t++) {
-        variant[t].buffer = main_buf.buffer; variant[t].bit_index = main_buf.bit_index;   // :1223
-        variant[t].attach_new();                                                          // :1309-1311
-        crc_variant[t] = combined_crc;                                                    // :1224
-      }
-      u64 bits0 = variant[0].total_bits();
-      for (int tactic = 0; tactic < 2; tactic++) {                       // :1238-1254
-        i64 slices = tactic == 0 ? 1 : 4;
-        i64 size = (i64)len / slices;
-        i64 stop = 0, startk;
-        BlockEncoder be(cfg);
-        for (i64 count = 1; count <= slices; count++) {
-          startk = stop + 1;
-          if (count == slices) stop = len; else stop = count * size;
-          be.Encode_Block(raw + (startk - 1), stop - startk + 1, variant[tactic], crc_variant[tactic], nullptr);
-        }
-      }
-      for (int tactic = 2; tactic < 4; tactic++) {                       // :1262-1299
-        std::vector<i32> seg;
-        if (tactic == 2) segment_by_entropy(raw, (i32)len, 0.6f, 4000, 16000, seg);
-        else segment_by_entropy(raw, (i32)len, 0.4f, 8000, 16000, seg);
-        ct.n_seg[tactic - 2] = (u32)seg.size();
-        BlockEncoder be(cfg);
-        if (seg.empty()) {
-          be.Encode_Block(raw, 0, variant[tactic], crc_variant[tactic], nullptr);
-        } else {
-          i64 index_start = 1;
-          for (i32 s : seg) {
-            be.Encode_Block(raw + (index_start - 1), s - index_start + 1, variant[tactic], crc_variant[tactic], nullptr);
-            index_start = (i64)s + 1;
-          }
-        }
-      }
+      u64 bits0 = (u64)(7 - main_buf.bit_index);
+      Encode_Variants(raw, len, main_buf.buffer, main_buf.bit_index, combined_crc, variant, crc_variant, ct.n_seg);
       int best = 0;                                                      // :1305, 1319-1325
       for (int t = 0; t < 4; t++)
         if (variant[t].dest.size() < variant[best].dest.size()) best = t;
@@ -1000,6 +1009,23 @@ struct StreamEncoder {
       combined_crc = crc_variant[best];                                  // :1345
     }
     if (trace) trace->push_back(ct);
+  }
+
+  // The chunk loop of Encode (:1413-1429) with the cutting only: (start, len, capacity) of every chunk.
+  void Cut_Only(std::vector<ChunkTrace> &chunks, u64 stop = ~0ull, bool at_least_one = true) {
+    volatile float fcap = (float)block_capacity;
+    volatile float flo = fcap * 1.05f;
+    volatile float fhi = fcap * 1.30f;
+    for (;;) {
+      if (pos >= stop && !(at_least_one && chunks.empty())) break;      // (a shard ends with the first chunk of the next one)
+      volatile float frest = (float)stream_rest;
+      const i32 cap = (frest >= flo && frest <= fhi) ? (i32)stream_rest / 2 : block_capacity;
+      ChunkTrace ct{};
+      ct.start = pos; ct.dyn_capacity = (u32)cap;
+      ct.len = Data_Acquisition(cap);
+      chunks.push_back(ct);
+      if (!More_Bytes()) break;
+    }
   }
 
   // :1413-1431
@@ -1078,6 +1104,227 @@ int orc_encode_stream(const u8 *in, u64 n, int level, i64 size_hint, int bwt_mod
   if (out) memcpy(out, o.data(), o.size());
   return 0;
 }
+
+// The same stream with the chunks encoded on `threads` host threads (golden scripts and CPU baselines
+// over large inputs).  A candidate's bits do not depend on the incoming bit offset — only the winner test
+// does (it compares flushed bytes, :1319-1325) — and the combined CRC is folded by c -> rotl (c, 1) xor
+// block_crc (:990), which is affine: every chunk is encoded from an empty bit buffer and a zero CRC, then
+// one serial pass picks the winners in order, appends their bits at the running offset and composes the
+// folds.  tests/test_oracle.py checks it against orc_encode_stream.
+int orc_encode_stream_mt(const u8 *in, u64 n, int level, i64 size_hint, int bwt_mode, int threads,
+                         u8 *out, u64 out_cap, u64 *out_len,
+                         orc_chunk_trace *trace, u64 trace_cap, u64 *n_trace) {
+  crc_make_table();
+  if (level != 1 && level != 4 && level != 9) return 1;
+  EncoderConfig cfg{level, bwt_mode};
+  std::vector<u8> dummy;
+  std::vector<ChunkTrace> chunks;
+  {
+    StreamEncoder se(cfg, in, n, size_hint, dummy, nullptr);
+    se.Cut_Only(chunks);
+  }
+  const size_t nc = chunks.size();
+  const int nt = level == 9 ? 4 : 1;
+  struct Cand { std::vector<u8> bytes; u64 bits; u32 fold; u32 blocks; };
+  const size_t window = 256;                 // chunks encoded in parallel before the serial pass takes them (bounds memory)
+  std::vector<Cand> cand(window * 4);
+  size_t w0 = 0;
+  std::atomic<size_t> next{0};
+  auto work = [&]() {
+    for (;;) {
+      const size_t c = next.fetch_add(1);
+      if (c >= std::min(nc, w0 + window)) break;
+      StreamEncoder se(cfg, in, n, size_hint, dummy, nullptr);
+      BitBuffer variant[4];
+      u32 crcv[4] = {0, 0, 0, 0};
+      const u8 *raw = in + chunks[c].start;
+      if (level == 9) {
+        se.Encode_Variants(raw, chunks[c].len, 0, 7, 0, variant, crcv, chunks[c].n_seg);
+      } else {
+        variant[0].attach_new();
+        BlockEncoder be(cfg);
+        be.Encode_Block(raw, chunks[c].len, variant[0], crcv[0], nullptr);
+      }
+      for (int t = 0; t < nt; t++) {
+        Cand &cd = cand[(c - w0) * 4 + t];
+        cd.bits = variant[t].total_bits();
+        cd.bytes = std::move(variant[t].dest);
+        if (variant[t].bit_index != 7) cd.bytes.push_back(variant[t].buffer);
+        cd.fold = crcv[t];
+        cd.blocks = t == 0 ? 1u : t == 1 ? 4u : std::max<u32>(1u, chunks[c].n_seg[t - 2]);
+      }
+    }
+  };
+  std::vector<u8> o;
+  o.reserve((size_t)(n + n / 50 + 4096));
+  const char magic[4] = {'B', 'Z', 'h', (char)('0' + level)};
+  for (int i = 0; i < 4; i++) o.push_back((u8)magic[i]);
+  u64 total_bits = 32;                       // bits written so far; o holds ceil (total_bits / 8) bytes
+  u32 combined = 0;
+  auto append = [&](const std::vector<u8> &src, u64 nbits) {
+    const u32 sh = (u32)(total_bits & 7);
+    const u64 nbytes = (nbits + 7) >> 3;
+    if (sh == 0) o.insert(o.end(), src.begin(), src.begin() + nbytes);
+    else {
+      for (u64 i = 0; i < nbytes; i++) {
+        o.back() |= (u8)(src[i] >> sh);
+        o.push_back((u8)(src[i] << (8 - sh)));
+      }
+    }
+    total_bits += nbits;
+    o.resize((size_t)((total_bits + 7) >> 3));
+  };
+  for (w0 = 0; w0 < nc; w0 += window) {
+    next = w0;
+    {
+      std::vector<std::thread> th;
+      for (int i = 0; i < std::max(1, threads); i++) th.emplace_back(work);
+      for (auto &t : th) t.join();
+    }
+    for (size_t c = w0; c < std::min(nc, w0 + window); c++) {
+      ChunkTrace &ct = chunks[c];
+      const u64 in_bits = total_bits & 7;
+      int best = 0;
+      for (int t = 0; t < nt; t++) { ct.bits[t] = cand[(c - w0) * 4 + t].bits; ct.bytes[t] = (in_bits + ct.bits[t]) >> 3; }
+      for (int t = 0; t < nt; t++) if (ct.bytes[t] < ct.bytes[best]) best = t;
+      ct.winner = best;
+      Cand &w = cand[(c - w0) * 4 + best];
+      append(w.bytes, w.bits);
+      const u32 k = w.blocks & 31u;
+      combined = (k ? ((combined << k) | (combined >> (32 - k))) : combined) ^ w.fold;
+      for (int t = 0; t < nt; t++) std::vector<u8>().swap(cand[(c - w0) * 4 + t].bytes);
+    }
+  }
+  {
+    static const u8 footer[6] = {0x17, 0x72, 0x45, 0x38, 0x50, 0x90};
+    std::vector<u8> f(footer, footer + 6);
+    for (int k = 3; k >= 0; k--) f.push_back((u8)(combined >> (8 * k)));
+    append(f, 80);
+  }
+  if (out_len) *out_len = o.size();
+  if (n_trace) *n_trace = nc;
+  if (trace) {
+    for (size_t i = 0; i < nc && i < trace_cap; i++) {
+      orc_chunk_trace &t = trace[i];
+      t.start = chunks[i].start; t.len = chunks[i].len; t.dyn_capacity = chunks[i].dyn_capacity; t.winner = chunks[i].winner;
+      t.n_seg1 = chunks[i].n_seg[0]; t.n_seg2 = chunks[i].n_seg[1]; t.pad = 0;
+      for (int k = 0; k < 4; k++) { t.bytes[k] = chunks[i].bytes[k]; t.bits[k] = chunks[i].bits[k]; }
+    }
+  }
+  if (o.size() > out_cap) return 2;
+  if (out) memcpy(out, o.data(), o.size());
+  return 0;
+}
+
+// ---- one shard of a stream (mirror of b2_shard_* in include/b2gpu.h, for the CPU tests of the protocol) ----
+// `in_local` holds the stream bytes [base, base + n_local).  Chunks that start in [entry, own_end) are cut
+// and encoded from an empty bit buffer; link = bits appended and CRC fold for each incoming bit offset mod 8.
+struct orc_shard_link { u64 total_bits[8]; u32 crc_rot[8]; u32 crc_fold[8]; };
+struct OrcShard {
+  struct Cand { std::vector<u8> bytes; u64 bits; u32 fold; u32 blocks; };
+  std::vector<ChunkTrace> chunks;
+  std::vector<Cand> cand;
+  int level, nt;
+  bool first, last;
+};
+static inline u32 rotl32(u32 c, u32 k) { k &= 31u; return k ? ((c << k) | (c >> (32 - k))) : c; }
+
+void *orc_shard_encode(const u8 *in_local, u64 base, u64 n_local, u64 stream_n, int level, i64 size_hint, int bwt_mode,
+                       int threads, u64 entry, u64 own_end, u64 *handoff, orc_shard_link *link) {
+  crc_make_table();
+  EncoderConfig cfg{level, bwt_mode};
+  std::vector<u8> dummy;
+  OrcShard *S = new OrcShard();
+  S->level = level; S->nt = level == 9 ? 4 : 1;
+  S->first = base == 0 && entry == 0; S->last = own_end >= stream_n;
+  const u8 *in = in_local - base;                    // indexed with stream offsets
+  {
+    StreamEncoder se(cfg, in, base + n_local, size_hint, dummy, nullptr);
+    se.pos = entry;
+    se.stream_rest = size_hint < 0 ? -1 : ((i64)entry <= size_hint ? size_hint - (i64)entry : -1);   // :1192-1194
+    se.Cut_Only(S->chunks, S->last ? ~0ull : own_end, S->first && stream_n == 0);
+    if (S->last && entry >= stream_n && !(S->first && stream_n == 0)) S->chunks.clear();
+    *handoff = se.pos;
+  }
+  const size_t nc = S->chunks.size();
+  S->cand.resize(nc * 4);
+  std::atomic<size_t> next{0};
+  auto work = [&]() {
+    for (;;) {
+      const size_t c = next.fetch_add(1);
+      if (c >= nc) break;
+      StreamEncoder se(cfg, in, base + n_local, size_hint, dummy, nullptr);
+      BitBuffer variant[4];
+      u32 crcv[4] = {0, 0, 0, 0};
+      const u8 *raw = in + S->chunks[c].start;
+      if (level == 9) se.Encode_Variants(raw, S->chunks[c].len, 0, 7, 0, variant, crcv, S->chunks[c].n_seg);
+      else { variant[0].attach_new(); BlockEncoder be(cfg); be.Encode_Block(raw, S->chunks[c].len, variant[0], crcv[0], nullptr); }
+      for (int t = 0; t < S->nt; t++) {
+        OrcShard::Cand &cd = S->cand[c * 4 + t];
+        cd.bits = variant[t].total_bits();
+        cd.bytes = std::move(variant[t].dest);
+        if (variant[t].bit_index != 7) cd.bytes.push_back(variant[t].buffer);
+        cd.fold = crcv[t];
+        cd.blocks = t == 0 ? 1u : t == 1 ? 4u : std::max<u32>(1u, S->chunks[c].n_seg[t - 2]);
+      }
+    }
+  };
+  {
+    std::vector<std::thread> th;
+    for (int i = 0; i < std::max(1, threads); i++) th.emplace_back(work);
+    for (auto &t : th) t.join();
+  }
+  for (u32 p0 = 0; p0 < 8; p0++) {
+    u64 total = 0; u32 rot = 0, fold = 0, ph = p0;
+    for (size_t c = 0; c < nc; c++) {
+      int best = 0;
+      for (int t = 0; t < S->nt; t++) if (((ph + S->cand[c * 4 + t].bits) >> 3) < ((ph + S->cand[c * 4 + best].bits) >> 3)) best = t;
+      const OrcShard::Cand &w = S->cand[c * 4 + best];
+      total += w.bits; ph = (u32)((ph + w.bits) & 7);
+      fold = rotl32(fold, w.blocks) ^ w.fold; rot = (rot + w.blocks) & 31u;
+    }
+    link->total_bits[p0] = total; link->crc_rot[p0] = rot; link->crc_fold[p0] = fold;
+  }
+  return S;
+}
+
+int orc_shard_finish(void *h, u64 bit_offset, u32 crc_in, u8 *out, u64 out_cap, u64 *byte_offset, u64 *out_len) {
+  OrcShard *S = (OrcShard *)h;
+  const u64 byte0 = S->first ? 0 : bit_offset >> 3;
+  std::vector<u8> o;
+  u64 total_bits = bit_offset - 8 * byte0;            // bits of the piece in place so far
+  if (S->first) { const char magic[4] = {'B', 'Z', 'h', (char)('0' + S->level)}; for (int i = 0; i < 4; i++) o.push_back((u8)magic[i]); }
+  else if (total_bits) o.push_back(0);
+  auto append = [&](const std::vector<u8> &src, u64 nbits) {
+    const u32 sh = (u32)(total_bits & 7);
+    const u64 nbytes = (nbits + 7) >> 3;
+    if (sh == 0) o.insert(o.end(), src.begin(), src.begin() + nbytes);
+    else for (u64 i = 0; i < nbytes; i++) { o.back() |= (u8)(src[i] >> sh); o.push_back((u8)(src[i] << (8 - sh))); }
+    total_bits += nbits;
+    o.resize((size_t)((total_bits + 7) >> 3));
+  };
+  u32 crc = crc_in;
+  for (size_t c = 0; c < S->chunks.size(); c++) {
+    const u64 in_bits = total_bits & 7;
+    int best = 0;
+    for (int t = 0; t < S->nt; t++) if (((in_bits + S->cand[c * 4 + t].bits) >> 3) < ((in_bits + S->cand[c * 4 + best].bits) >> 3)) best = t;
+    const OrcShard::Cand &w = S->cand[c * 4 + best];
+    append(w.bytes, w.bits);
+    crc = rotl32(crc, w.blocks) ^ w.fold;
+  }
+  if (S->last) {
+    static const u8 footer[6] = {0x17, 0x72, 0x45, 0x38, 0x50, 0x90};
+    std::vector<u8> f(footer, footer + 6);
+    for (int k = 3; k >= 0; k--) f.push_back((u8)(crc >> (8 * k)));
+    append(f, 80);
+  }
+  *byte_offset = byte0; *out_len = o.size();
+  if (o.size() > out_cap) return 2;
+  if (out && !o.empty()) memcpy(out, o.data(), o.size());
+  return 0;
+}
+
+void orc_shard_free(void *h) { delete (OrcShard *)h; }
 
 // One Encode_Block with every intermediate.  Buffers may be NULL.
 // rle_out: >= len*5/4+8; bwt_out same; mtf_out: >= len*5/4+10 u16; sel_out >= 18002;

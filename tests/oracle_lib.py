@@ -44,7 +44,9 @@ def _u8(buf):
     return a
 
 
-def encode_stream(data, level=9, size_hint=-1, bwt_mode=0, want_trace=False):
+def encode_stream(data, level=9, size_hint=-1, bwt_mode=0, want_trace=False, threads=0):
+    """threads = 0: the sequential restatement (orc_encode_stream); > 0: orc_encode_stream_mt, the same stream
+    with the chunks encoded on that many host threads."""
     a = _u8(data)
     n = a.size
     cap = n + n // 2 + 2_000_000
@@ -53,9 +55,14 @@ def encode_stream(data, level=9, size_hint=-1, bwt_mode=0, want_trace=False):
     tcap = n // 50_000 + 16
     trace = (ChunkTrace * tcap)()
     ntr = C.c_uint64(0)
-    rc = lib().orc_encode_stream(a.ctypes.data_as(C.c_void_p), C.c_uint64(n), level, C.c_int64(size_hint), bwt_mode,
-                                 out.ctypes.data_as(C.c_void_p), C.c_uint64(cap), C.byref(out_len),
-                                 trace, C.c_uint64(tcap), C.byref(ntr))
+    if threads > 0:
+        rc = lib().orc_encode_stream_mt(a.ctypes.data_as(C.c_void_p), C.c_uint64(n), level, C.c_int64(size_hint), bwt_mode, int(threads),
+                                        out.ctypes.data_as(C.c_void_p), C.c_uint64(cap), C.byref(out_len),
+                                        trace, C.c_uint64(tcap), C.byref(ntr))
+    else:
+        rc = lib().orc_encode_stream(a.ctypes.data_as(C.c_void_p), C.c_uint64(n), level, C.c_int64(size_hint), bwt_mode,
+                                     out.ctypes.data_as(C.c_void_p), C.c_uint64(cap), C.byref(out_len),
+                                     trace, C.c_uint64(tcap), C.byref(ntr))
     assert rc == 0, rc
     res = out[:out_len.value].tobytes()
     if want_trace:

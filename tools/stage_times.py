@@ -11,21 +11,30 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import datagen
+import corpus
 
 STAGES = ["cut_segment", "rle1", "bwt_sort", "mtf_rle2", "entropy_search", "pack", "concat", "copies"]
 
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--kind", default="text", choices=["text", "random", "sparse", "mixed"])
+    ap.add_argument("--kind", default="text", choices=["text", "random", "sparse", "mixed", "markov", "zipf"])
     ap.add_argument("--size-mb", type=int, default=128)
     ap.add_argument("--level", type=int, default=9)
     ap.add_argument("--no-stage", action="store_true")
+    ap.add_argument("--cpu-gen", action="store_true", help="generate the input with numpy (no torch kernels: for runs under ncu)")
     a = ap.parse_args()
     b2 = importlib.import_module("zip-ada_b200")
     n = a.size_mb << 20
-    data = {"text": datagen.text, "random": datagen.random_bytes, "sparse": datagen.sparse_binary,
-            "mixed": lambda k: datagen.mixed(k, 16 << 20)}[a.kind](n)
+    if a.kind in ("text", "zipf"):
+        data = datagen.text(n)
+    else:
+        seed = {"markov": 0x5EED0001, "mixed": 0x5EED0004, "random": 0x5EED0002, "sparse": 0x5EED0003}[a.kind]
+        if a.cpu_gen:
+            data = corpus.workload(a.kind, n, seed)
+        else:
+            import torch
+            data = corpus.workload(a.kind, n, seed, torch, "cuda").cpu().numpy()
     with b2.Encoder(a.level, 0) as enc:
         enc.encode(data, n)
         enc.reset_stats()

@@ -26,7 +26,7 @@ class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in
                 ("streams", "input_bytes", "chunks", "blocks", "block_bytes", "kernel_launches", "sort_rounds",
                  "sort_elems_round0", "sort_elems_later", "scatter_launches", "scatter_elems")] + \
-               [("scatter_ms", C.c_double), ("stage_ms", C.c_double * 8), ("call_ms", C.c_double)]
+               [("scatter_ms", C.c_double), ("stage_ms", C.c_double * 8), ("call_ms", C.c_double), ("sort_ms", C.c_double)]
 
 
 class ZipEntryInfo(C.Structure):
@@ -40,6 +40,10 @@ class BlockInfo(C.Structure):
                  "sample_width", "cost", "pad")] + [("bits", C.c_uint64)]
 
 
+class ShardLink(C.Structure):
+    _fields_ = [("total_bits", C.c_uint64 * 8), ("crc_rot", C.c_uint32 * 8), ("crc_fold", C.c_uint32 * 8)]
+
+
 class ChunkTrace(C.Structure):
     _fields_ = [("start", C.c_uint64), ("len", C.c_uint32), ("dyn_capacity", C.c_uint32),
                 ("winner", C.c_int32), ("n_seg1", C.c_uint32), ("n_seg2", C.c_uint32), ("pad", C.c_uint32),
@@ -48,7 +52,9 @@ class ChunkTrace(C.Structure):
 
 EXPORTS = ["b2_create", "b2_destroy", "b2_bound", "b2_encode_stream", "b2_encode_stream_device", "b2_encode_batch", "b2_last_error",
            "b2_set_timing", "b2_get_stats", "b2_reset_stats", "b2_dbg_block", "b2_get_trace", "b2_get_segments",
-           "b2_zip_bound", "b2_zip_create", "b2_zip_crc32"]
+           "b2_zip_bound", "b2_zip_create", "b2_zip_crc32",
+           "b2_shard_margin", "b2_shard_plan", "b2_shard_open", "b2_shard_cut", "b2_shard_encode", "b2_shard_resolve",
+           "b2_shard_finish", "b2_encode_stream_multi"]
 
 _lib = None
 
@@ -84,6 +90,17 @@ def lib():
         _lib.b2_dbg_block.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32] + [C.c_void_p] * 6 + [C.c_uint64, C.POINTER(BlockInfo)]
         _lib.b2_get_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
         _lib.b2_get_segments.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
+        _lib.b2_shard_margin.restype = C.c_uint64
+        _lib.b2_shard_margin.argtypes = [C.c_int]
+        _lib.b2_shard_plan.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        _lib.b2_shard_open.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int64, C.c_uint64]
+        _lib.b2_shard_cut.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+        _lib.b2_shard_encode.argtypes = [C.c_void_p, C.POINTER(ShardLink)]
+        _lib.b2_shard_resolve.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        _lib.b2_shard_finish.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_int, C.c_uint64,
+                                         C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint8), C.POINTER(C.c_uint8)]
+        _lib.b2_encode_stream_multi.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_int64, C.c_void_p, C.c_uint64,
+                                                C.POINTER(C.c_uint64)]
     return _lib
 
 
@@ -221,6 +238,27 @@ class Encoder:
         _check(lib().b2_zip_crc32(self._h, a.ctypes.data if a.size else None, a.size, C.byref(c)))
         return int(c.value)
 
+    # -- one stream over several handles (b2_shard_*, include/b2gpu.h) ------------------------------
+    def shard_open(self, in_ptr, in_is_device, base, n_local, stream_size, size_hint, own_end):
+        _check(lib().b2_shard_open(self._h, in_ptr, int(in_is_device), base, n_local, stream_size, int(size_hint), own_end))
+
+    def shard_cut(self, entry):
+        h = C.c_uint64(0)
+        _check(lib().b2_shard_cut(self._h, entry, C.byref(h)))
+        return h.value
+
+    def shard_encode(self):
+        link = ShardLink()
+        _check(lib().b2_shard_encode(self._h, C.byref(link)))
+        return link
+
+    def shard_finish(self, bit_offset, crc_in, out_ptr, out_is_device, out_cap):
+        """Returns (byte offset of the piece in the stream, length, first byte, last byte)."""
+        off, ln, fb, lb = C.c_uint64(0), C.c_uint64(0), C.c_uint8(0), C.c_uint8(0)
+        _check(lib().b2_shard_finish(self._h, bit_offset, crc_in, out_ptr, int(out_is_device), out_cap, C.byref(off), C.byref(ln),
+                                     C.byref(fb), C.byref(lb)))
+        return off.value, ln.value, fb.value, lb.value
+
     # -- generic shape of the reference: Read_Byte / More_Bytes / Write_Byte --------------------
     def encode_callbacks(self, read_byte, more_bytes, write_byte, size_hint=unknown_size):
         buf = bytearray()
@@ -270,3 +308,42 @@ class Encoder:
         return dict(rle=rle[:info.n_rle].copy(), bwt=bwt[:info.n_rle].copy(), mtf=mtf[:info.n_mtf].copy(),
                     sel=sel[:info.n_sel].copy(), lens=lens.reshape(6, 258).copy(),
                     bits=bits[:(info.bits + 7) // 8].copy(), info=info)
+
+
+def shard_plan(n, n_shards, level=block_900k, stagger_permille=-1):
+    b = (C.c_uint64 * (n_shards + 1))()
+    _check(lib().b2_shard_plan(n, n_shards, level, stagger_permille, b))
+    return [int(x) for x in b]
+
+
+def shard_resolve(links):
+    """links: list of ShardLink in shard order -> (bit_offsets, crcs), n_shards + 1 entries each."""
+    n = len(links)
+    arr = (ShardLink * n)(*links)
+    bo = (C.c_uint64 * (n + 1))()
+    cr = (C.c_uint32 * (n + 1))()
+    _check(lib().b2_shard_resolve(arr, n, bo, cr))
+    return [int(x) for x in bo], [int(x) for x in cr]
+
+
+def assemble_pieces(pieces, total_len):
+    """pieces: list of (byte offset, bytes) in shard order; shared boundary bytes are OR-ed."""
+    out = np.zeros(total_len, np.uint8)
+    for off, data in pieces:
+        a = np.frombuffer(bytes(data), np.uint8) if not isinstance(data, np.ndarray) else data
+        if a.size:
+            out[off:off + a.size] |= a
+    return out
+
+
+def encode_multi(encoders, data, size_hint=unknown_size, out=None):
+    """One stream over the devices of several Encoder handles (b2_encode_stream_multi)."""
+    a = _u8(data)
+    n = a.size
+    cap = lib().b2_bound(n) + 1024 * (n // 40000 + 16)
+    if out is None:
+        out = np.empty(cap, dtype=np.uint8)
+    hs = (C.c_void_p * len(encoders))(*[e._h for e in encoders])
+    out_len = C.c_uint64(0)
+    _check(lib().b2_encode_stream_multi(hs, len(encoders), a.ctypes.data, n, int(size_hint), out.ctypes.data, out.size, C.byref(out_len)))
+    return out[:out_len.value]

@@ -74,6 +74,8 @@ struct Batch {
 struct Workspace {
   cudaStream_t st = nullptr;
   cudaEvent_t ev[2] = {nullptr, nullptr};
+  cudaEvent_t ev_sort[2] = {nullptr, nullptr};
+  double sort_ms = 0;
   DevBuf<u32> d_scalars;
   DevBuf<B2Job> d_jobs;
   DevBuf<u8> d_text, d_bwt, d_idx;
@@ -116,6 +118,9 @@ struct Workspace {
     h_unsorted = nullptr; h_unsorted_cap = 0;
     if (ev[0]) cudaEventDestroy(ev[0]);
     if (ev[1]) cudaEventDestroy(ev[1]);
+    if (ev_sort[0]) cudaEventDestroy(ev_sort[0]);
+    if (ev_sort[1]) cudaEventDestroy(ev_sort[1]);
+    ev_sort[0] = ev_sort[1] = nullptr;
     if (st) cudaStreamDestroy(st);
     st = nullptr; ev[0] = ev[1] = nullptr;
   }
@@ -123,8 +128,21 @@ struct Workspace {
 
 }  // namespace
 
+// One stream spread over several handles (b2_shard_*): what this handle keeps between the calls.
+struct ShardCand { u32 arena; u32 blocks; u64 word_off; u64 nbits; u32 fold; u32 kept; };
+struct ShardState {
+  bool open = false, cut = false, encoded = false;
+  const u8 *d_in = nullptr;            // the shard's bytes on the device: stream bytes [base, base + n_local)
+  u64 base = 0, n_local = 0, stream_n = 0, own_end = 0, entry = 0, handoff = 0;
+  i64 hint = -1;
+  std::vector<DevBuf<u32> *> arenas;   // candidate bitstreams that may still win, one arena per batch (kept across calls)
+  std::vector<ShardCand> cands;        // [chunk][tactic]
+  std::vector<int> n_tactics;
+};
+
 struct b2_encoder {
   int level = 9, device = 0;
+  ShardState shard;
   cudaStream_t st = nullptr;            // stream of the stream-level work (cut, segment, copies, footer)
   cudaStream_t st2 = nullptr;           // segmentation following the chunk chain
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -300,7 +318,9 @@ int run_batch(b2_encoder *e, Workspace *w, const u8 *d_in, std::vector<B2Job> &j
       cx.sym_bits = 1;
       while ((1u << cx.sym_bits) < max_used) cx.sym_bits++;
     }
+    if (e->timing >= 1) cudaEventRecord(w->ev_sort[0], st);
     int rc = b2k_bwt_batch(&cx, st, w->d_jobs.p, ids, ns, w->d_text.p, w->d_bwt.p);
+    if (e->timing >= 1) cudaEventRecord(w->ev_sort[1], st);
     w->sort_stats = cx.stats;
     if (rc) return rc;
   }
@@ -345,6 +365,7 @@ int run_batch(b2_encoder *e, Workspace *w, const u8 *d_in, std::vector<B2Job> &j
   }
   B2_CUDA_CHECK(cudaMemcpyAsync(w->batch_jobs.data(), w->d_jobs.p, J * sizeof(B2Job), cudaMemcpyDeviceToHost, st));
   B2_CUDA_CHECK(cudaStreamSynchronize(st));
+  if (e->timing >= 1) { float ms = 0; if (cudaEventElapsedTime(&ms, w->ev_sort[0], w->ev_sort[1]) == cudaSuccess) w->sort_ms += ms; }
   return 0;
 }
 
@@ -409,10 +430,14 @@ struct StreamDesc {
 // Encodes streams[*] (all resident in d_in) into disjoint regions of e->d_out.  Every stream is what
 // one `Encode (option, size_hint)` call writes (bzip2-encoding.adb:1413-1431); chunks of all streams
 // share the batches, so many small entries fill the device as well as one large stream.
+int encode_chunks(b2_encoder *e, const u8 *d_in, std::vector<StreamDesc> &streams, std::vector<u32> &chunk_stream, bool followed,
+                  ShardState *sh);
+
 int encode_streams(b2_encoder *e, const u8 *d_in, std::vector<StreamDesc> &streams) {
   cudaStream_t st = e->st;
   const int level = e->level;
   B2_CUDA_CHECK(cudaStreamSynchronize(e->st2));     // nothing of an earlier (failed) call may still be following a chain
+  e->shard.open = e->shard.cut = e->shard.encoded = false;
   e->trace.clear(); e->chunks.clear(); e->nseg.clear(); e->seg.clear();
   i64 win_lo, win_hi;
   balance_window(level, win_lo, win_hi);
@@ -472,9 +497,20 @@ int encode_streams(b2_encoder *e, const u8 *d_in, std::vector<StreamDesc> &strea
       for (u32 c = 0; c < S.n_chunks; c++) chunk_stream.push_back((u32)si);
     }
   }
+  return encode_chunks(e, d_in, streams, chunk_stream, followed, nullptr);
+}
+
+// Everything after the cutting: e->chunks holds the chunks (offsets into d_in), chunk_stream their streams.
+// sh != nullptr: the chunks are one shard of a stream (b2_shard_encode) — the candidates that can still win are
+// kept for b2_shard_finish instead of being concatenated, and no header / footer is written.
+int encode_chunks(b2_encoder *e, const u8 *d_in, std::vector<StreamDesc> &streams, std::vector<u32> &chunk_stream, bool followed,
+                  ShardState *sh) {
+  cudaStream_t st = e->st;
+  const int level = e->level;
   const u32 n_chunks = (u32)e->chunks.size();
   e->stats.chunks += n_chunks;
   e->trace.resize(n_chunks);
+  if (sh) { sh->cands.assign((size_t)n_chunks * 4, ShardCand{0, 0, 0, 0, 0, 0}); sh->n_tactics.assign(n_chunks, 0); }
   // ---- A3 segmentation of every chunk --------------------------------------------------------------
   {
     StageTimer tm(e, st, e->ev, &e->stats.stage_ms[0]);
@@ -505,8 +541,21 @@ int encode_streams(b2_encoder *e, const u8 *d_in, std::vector<StreamDesc> &strea
       B2_CUDA_CHECK(cudaMemcpyAsync(e->nseg.data() + 2 * (size_t)seg_have, e->d_nseg.p + 2 * (size_t)seg_have,
                                     2 * (size_t)(upto - seg_have) * sizeof(u32), cudaMemcpyDeviceToHost, st));
       B2_CUDA_CHECK(cudaStreamSynchronize(st));
-      bool all = true;
-      for (u32 k = 2 * seg_have; k < 2 * upto; k++) if (e->nseg[k] == 0xFEFEFEFEu) { all = false; break; }
+      bool all = true, gave_up = false;
+      for (u32 k = 2 * seg_have; k < 2 * upto; k++) {
+        if (e->nseg[k] == B2_SEG_PENDING) { all = false; break; }
+        if (e->nseg[k] == B2_SEG_GAVE_UP) gave_up = true;
+      }
+      if (all && gave_up) {
+        // a CTA following the chain never saw its chunk (the chain kernel was not co-scheduled: time-sliced GPU):
+        // segment every chunk again now that the chain is complete
+        B2_CUDA_CHECK(cudaStreamSynchronize(e->st2));
+        B2_CUDA_CHECK(cudaMemcpyAsync(e->d_chunks.p, e->chunks.data(), n_chunks * sizeof(B2Chunk), cudaMemcpyHostToDevice, st));
+        B2_TRY(b2k_segment(st, d_in, e->d_chunks.p, n_chunks, e->d_T.p, e->d_seg.p, e->d_nseg.p, nullptr));
+        e->launches_other += 1;
+        followed = false;
+        continue;
+      }
       if (all) break;
       if (!followed || tries > 2000000u) B2_FAIL(B2_ERR_INTERNAL, "segmentation results missing");
       std::this_thread::sleep_for(std::chrono::microseconds(50));
@@ -530,9 +579,11 @@ int encode_streams(b2_encoder *e, const u8 *d_in, std::vector<StreamDesc> &strea
     S.out_off = out_total;
     out_total += (b2_bound(S.n) + 1024ull * S.n_chunks + 71) & ~7ull;
   }
-  B2_TRY(e->d_out.ensure(out_total / 4 + 16));
-  B2_CUDA_CHECK(cudaMemsetAsync(e->d_out.p, 0, (out_total / 4 + 8) * sizeof(u32), st));
-  B2_CUDA_CHECK(cudaStreamSynchronize(st));           // output zeroed before any concat
+  if (!sh) {
+    B2_TRY(e->d_out.ensure(out_total / 4 + 16));
+    B2_CUDA_CHECK(cudaMemsetAsync(e->d_out.p, 0, (out_total / 4 + 8) * sizeof(u32), st));
+    B2_CUDA_CHECK(cudaStreamSynchronize(st));           // output zeroed before any concat
+  }
   // ---- batches of whole chunks: planned by this thread, run by the workers as they appear -----------
   std::vector<ChunkPlan> plans(n_chunks);
   std::deque<Batch> batches;                          // grows while the workers run (references stay valid)
@@ -547,7 +598,7 @@ int encode_streams(b2_encoder *e, const u8 *d_in, std::vector<StreamDesc> &strea
   const int W = (e->timing >= 2) ? 1 : std::max<int>(1, (int)e->ws.size());
   for (auto *w : e->ws) {
     memset(&w->sort_stats, 0, sizeof w->sort_stats);
-    w->launches = 0; w->blocks = 0; w->block_bytes = 0;
+    w->launches = 0; w->blocks = 0; w->block_bytes = 0; w->sort_ms = 0;
     for (int i = 0; i < 8; i++) w->stage_ms[i] = 0;
   }
   std::atomic<u32> next{0};
@@ -576,7 +627,54 @@ int encode_streams(b2_encoder *e, const u8 *d_in, std::vector<StreamDesc> &strea
       if (!rc) rc = run_batch(e, w, d_in, B->jobs);
       std::unique_lock<std::mutex> lk(mu);
       cv.wait(lk, [&] { return turn == b; });
-      if (!rc && !err) {
+      if (!rc && !err && sh) {
+        // one shard of a stream: the bit offset its first chunk lands on is not known yet.  A candidate can
+        // only win if it is the best for one of the eight incoming offsets (:1319-1325 compares flushed
+        // bytes); those are copied, each from a 64-bit boundary, into an arena that outlives the batch.
+        std::vector<B2ConcatItem> items;
+        u64 cursor = 0;
+        for (u32 c = B->c0; c < B->c1; c++) {
+          ChunkPlan &P = plans[c];
+          u64 bits[4] = {0, 0, 0, 0};
+          for (int t = 0; t < P.n_tactics; t++) for (u32 id : P.tactic_jobs[t]) bits[t] += w->batch_jobs[id].nbits;
+          u32 keep = 0;
+          for (u32 phase = 0; phase < 8; phase++) {
+            int best = 0;
+            for (int t = 0; t < P.n_tactics; t++) if (((phase + bits[t]) >> 3) < ((phase + bits[best]) >> 3)) best = t;
+            keep |= 1u << best;
+          }
+          sh->n_tactics[c] = P.n_tactics;
+          b2_chunk_trace tr; memset(&tr, 0, sizeof tr);
+          tr.start = sh->base + P.start; tr.len = P.len; tr.dyn_capacity = P.cap; tr.n_seg1 = P.n_seg[0]; tr.n_seg2 = P.n_seg[1];
+          tr.winner = -1;
+          for (int t = 0; t < P.n_tactics; t++) {
+            tr.bits[t] = bits[t];
+            ShardCand &cd = sh->cands[(size_t)c * 4 + t];
+            cd.arena = b; cd.nbits = bits[t]; cd.kept = (keep >> t) & 1u; cd.blocks = (u32)P.tactic_jobs[t].size(); cd.fold = 0;
+            for (u32 id : P.tactic_jobs[t]) cd.fold = rotl1(cd.fold) ^ w->batch_jobs[id].crc;      // (:990) from a zero CRC
+            if (!cd.kept) continue;
+            cursor = (cursor + 63) & ~63ull;
+            cd.word_off = cursor >> 5;
+            for (u32 id : P.tactic_jobs[t]) {
+              const B2Job &jb = w->batch_jobs[id];
+              items.push_back(B2ConcatItem{jb.bits_off, jb.nbits, cursor});
+              cursor += jb.nbits;
+            }
+          }
+          e->trace[c] = tr;
+        }
+        while (sh->arenas.size() <= b) sh->arenas.push_back(new DevBuf<u32>());
+        DevBuf<u32> *ar = sh->arenas[b];
+        rc = ar->ensure((cursor >> 5) + 8);
+        if (!rc && cudaMemsetAsync(ar->p, 0, ((cursor >> 5) + 8) * sizeof(u32), w->st) != cudaSuccess) rc = B2_ERR_CUDA;
+        if (!rc) rc = w->d_items.ensure(items.size() + 1);
+        if (!rc && !items.empty() && cudaMemcpyAsync(w->d_items.p, items.data(), items.size() * sizeof(B2ConcatItem), cudaMemcpyHostToDevice, w->st) != cudaSuccess) rc = B2_ERR_CUDA;
+        for (size_t i0 = 0; !rc && i0 < items.size(); i0 += 65535) {
+          rc = b2k_concat(w->st, w->d_items.p + i0, (u32)std::min<size_t>(65535, items.size() - i0), w->d_bits.p, ar->p);
+          w->launches += 1;
+        }
+        if (!rc && cudaStreamSynchronize(w->st) != cudaSuccess) { rc = B2_ERR_CUDA; b2_set_error(__FILE__, __LINE__, cudaGetErrorString(cudaGetLastError())); }
+      } else if (!rc && !err) {
         // winners of the chunks of this batch, in order
         std::vector<B2ConcatItem> items;
         for (u32 c = B->c0; c < B->c1; c++) {
@@ -610,7 +708,8 @@ int encode_streams(b2_encoder *e, const u8 *d_in, std::vector<StreamDesc> &strea
           StageTimer tm(e, w->st, w->ev, &w->stage_ms[6]);
           rc = w->d_items.ensure(items.size());
           if (!rc && cudaMemcpyAsync(w->d_items.p, items.data(), items.size() * sizeof(B2ConcatItem), cudaMemcpyHostToDevice, w->st) != cudaSuccess) rc = B2_ERR_CUDA;
-          if (!rc) rc = b2k_concat(w->st, w->d_items.p, (u32)items.size(), w->d_bits.p, e->d_out.p);
+          for (size_t i0 = 0; !rc && i0 < items.size(); i0 += 65535)
+            rc = b2k_concat(w->st, w->d_items.p + i0, (u32)std::min<size_t>(65535, items.size() - i0), w->d_bits.p, e->d_out.p);
           if (!rc && cudaStreamSynchronize(w->st) != cudaSuccess) { rc = B2_ERR_CUDA; b2_set_error(__FILE__, __LINE__, cudaGetErrorString(cudaGetLastError())); }
           w->launches += 1;
         }
@@ -663,7 +762,7 @@ int encode_streams(b2_encoder *e, const u8 *d_in, std::vector<StreamDesc> &strea
   (void)out_words_needed;
   if (err) { g_last_error = err_msg; return err; }
   // ---- stream headers and footers (:1384-1407) on the device ----------------------------------------
-  {
+  if (!sh) {
     B2_TRY(e->d_ends.ensure(ends.size()));
     B2_CUDA_CHECK(cudaMemcpyAsync(e->d_ends.p, ends.data(), ends.size() * sizeof(B2StreamEnd), cudaMemcpyHostToDevice, st));
     B2_TRY(b2k_stream_ends(st, e->d_ends.p, (u32)ends.size(), level, e->d_out.p));
@@ -681,7 +780,7 @@ int encode_streams(b2_encoder *e, const u8 *d_in, std::vector<StreamDesc> &strea
     e->sort_stats.sorted_elems_later += w->sort_stats.sorted_elems_later;
     e->sort_stats.launches += w->sort_stats.launches;
     e->launches_other += w->launches;
-    e->stats.blocks += w->blocks; e->stats.block_bytes += w->block_bytes;
+    e->stats.blocks += w->blocks; e->stats.block_bytes += w->block_bytes; e->stats.sort_ms += w->sort_ms;
     for (int i = 1; i < 8; i++) e->stats.stage_ms[i] += w->stage_ms[i];
   }
   e->stats.sort_rounds = e->sort_stats.rounds;
@@ -783,6 +882,7 @@ int b2_create(int level, int device, b2_encoder **out) {
     e->ws.push_back(w);
     B2_CUDA_CHECK(cudaStreamCreateWithFlags(&w->st, cudaStreamNonBlocking));
     B2_CUDA_CHECK(cudaEventCreate(&w->ev[0])); B2_CUDA_CHECK(cudaEventCreate(&w->ev[1]));
+    B2_CUDA_CHECK(cudaEventCreate(&w->ev_sort[0])); B2_CUDA_CHECK(cudaEventCreate(&w->ev_sort[1]));
   }
   // constant tables
   B2CrcTables *ct = new B2CrcTables();
@@ -899,6 +999,303 @@ int b2_encode_batch(b2_encoder *e, uint32_t n_entries, const uint8_t *in, const 
   if (e->timing) cudaEventRecord(e->ev_call[1], e->st);
   B2_CUDA_CHECK(cudaStreamSynchronize(e->st));
   if (e->timing) { float ms = 0; cudaEventElapsedTime(&ms, e->ev_call[0], e->ev_call[1]); e->stats.call_ms += ms; }
+  return 0;
+}
+
+// ---- one stream over several handles (devices / processes): SURVEY.md §8e ----------------------------
+// Chunks are independent given where they start; the only data that cross shards are scalars: the start of
+// the next shard's first chunk (the cutting is a chain, bzip2-encoding.adb:1160-1208), and per shard, for
+// each of the 8 possible incoming bit offsets, the bits it appends and how it folds the combined CRC
+// (:990, :1319-1345).  No bulk data moves between devices.
+uint64_t b2_shard_margin(int level) { return 10ull * 100000ull * (u64)level + 4096; }
+
+int b2_shard_plan(uint64_t n, int n_shards, int level, int stagger_permille, uint64_t *bounds) {
+  if (!bounds || n_shards < 1) return B2_ERR_ARGUMENT;
+  (void)level;
+  // Shard r can only start once shard r-1 has cut its chunks, so its share is smaller by the factor
+  // (1 - stagger): all shards then finish together (stagger = encode rate / cutting rate of one device).
+  if (stagger_permille < 0) {
+    stagger_permille = 30;
+    if (const char *sv = getenv("B2GPU_SHARD_STAGGER")) { int v = atoi(sv); if (v >= 0 && v < 500) stagger_permille = v; }
+  }
+  const double q = 1.0 - stagger_permille / 1000.0;
+  double tot = 0, w = 1;
+  for (int r = 0; r < n_shards; r++) { tot += w; w *= q; }
+  double acc = 0; w = 1;
+  bounds[0] = 0;
+  for (int r = 0; r < n_shards; r++) {
+    acc += w; w *= q;
+    u64 b = (u64)((double)n * (acc / tot));
+    b &= ~4095ull;                                    // device pointers of the slices stay aligned for vector loads
+    if (b < bounds[r]) b = bounds[r];
+    bounds[r + 1] = r + 1 == n_shards ? n : std::min<u64>(b, n);
+  }
+  return 0;
+}
+
+int b2_shard_resolve(const b2_shard_link *links, int n_shards, uint64_t *bit_offsets, uint32_t *crcs) {
+  if (!links || !bit_offsets || !crcs || n_shards < 1) return B2_ERR_ARGUMENT;
+  bit_offsets[0] = 32; crcs[0] = 0;                  // behind "BZh<level>" (:1384-1391)
+  for (int r = 0; r < n_shards; r++) {
+    const u32 ph = (u32)(bit_offsets[r] & 7);
+    bit_offsets[r + 1] = bit_offsets[r] + links[r].total_bits[ph];
+    const u32 k = links[r].crc_rot[ph] & 31u, c = crcs[r];
+    crcs[r + 1] = (k ? ((c << k) | (c >> (32 - k))) : c) ^ links[r].crc_fold[ph];
+  }
+  return 0;
+}
+
+int b2_shard_open(b2_encoder *e, const uint8_t *in, int in_is_device, uint64_t base, uint64_t n_local,
+                  uint64_t stream_size, int64_t size_hint, uint64_t own_end) {
+  if (!e || (n_local && !in) || base + n_local > stream_size || own_end > stream_size || own_end < base) B2_FAIL(B2_ERR_ARGUMENT, "bad argument");
+  B2_CUDA_CHECK(cudaSetDevice(e->device));
+  B2_CUDA_CHECK(cudaStreamSynchronize(e->st2));
+  ShardState &sh = e->shard;
+  sh.open = sh.cut = sh.encoded = false;
+  sh.base = base; sh.n_local = n_local; sh.stream_n = stream_size; sh.hint = size_hint; sh.own_end = own_end;
+  if (e->timing) cudaEventRecord(e->ev_call[0], e->st);
+  if (in_is_device) sh.d_in = in;
+  else {
+    B2_TRY(e->d_in.ensure(n_local + 256));
+    if (n_local) B2_CUDA_CHECK(cudaMemcpyAsync(e->d_in.p, in, n_local, cudaMemcpyHostToDevice, e->st));
+    B2_CUDA_CHECK(cudaMemsetAsync(e->d_in.p + n_local, 0, 128, e->st));
+    sh.d_in = e->d_in.p;
+  }
+  // the scans of the cutting do not depend on where the first chunk starts: they run while the shards
+  // before this one are still cutting
+  const size_t ct = (size_t)(n_local / 2048 + 2);
+  B2_TRY(e->d_cut_first.ensure(ct)); B2_TRY(e->d_cut_last.ensure(ct)); B2_TRY(e->d_cut_tsum.ensure(ct));
+  B2_TRY(e->d_cut_carry.ensure(ct)); B2_TRY(e->d_cut_tincl.ensure(ct));
+  B2CutWork cw{e->d_cut_first.p, e->d_cut_last.p, e->d_cut_tsum.p, e->d_cut_carry.p, e->d_cut_tincl.p};
+  B2_TRY(b2k_cut_scans(e->st, sh.d_in, n_local, &cw));
+  e->launches_other += 4;
+  sh.open = true;
+  return 0;
+}
+
+int b2_shard_cut(b2_encoder *e, uint64_t entry, uint64_t *handoff) {
+  if (!e || !handoff) B2_FAIL(B2_ERR_ARGUMENT, "bad argument");
+  ShardState &sh = e->shard;
+  if (!sh.open) B2_FAIL(B2_ERR_ARGUMENT, "b2_shard_cut without b2_shard_open");
+  if (entry < sh.base || entry > sh.base + sh.n_local) B2_FAIL(B2_ERR_ARGUMENT, "entry outside the shard's bytes");
+  B2_CUDA_CHECK(cudaSetDevice(e->device));
+  cudaStream_t st = e->st;
+  const int level = e->level;
+  e->trace.clear(); e->chunks.clear(); e->nseg.clear(); e->seg.clear();
+  i64 win_lo, win_hi;
+  balance_window(level, win_lo, win_hi);
+  const u64 own = sh.own_end > entry ? sh.own_end - entry : 0;
+  const u32 max_chunks = (u32)(own / (40000ull * level) + 16);
+  B2_TRY(e->d_chunks.ensure(max_chunks));
+  B2CutWork cw{e->d_cut_first.p, e->d_cut_last.p, e->d_cut_tsum.p, e->d_cut_carry.p, e->d_cut_tincl.p};
+  const bool follow = level == 9 && e->timing < 2;
+  if (level == 9) {
+    B2_TRY(e->d_seg.ensure((size_t)max_chunks * 2 * B2_MAX_SEG));
+    B2_TRY(e->d_nseg.ensure((size_t)max_chunks * 2));
+    B2_CUDA_CHECK(cudaMemsetAsync(e->d_nseg.p, 0xFE, (size_t)max_chunks * 2 * sizeof(u32), st));
+  }
+  // the last shard walks to the end of the stream; the others stop at the first chunk that belongs to the next one
+  const bool last = sh.own_end >= sh.stream_n;
+  const u64 stop = last ? sh.n_local : sh.own_end - sh.base;
+  B2_TRY(b2k_cut_chain(st, sh.d_in, sh.n_local, sh.hint, level, win_lo, win_hi, e->d_chunks.p, e->d_scalars.p, max_chunks, &cw,
+                       follow ? e->d_scalars.p + 12 : nullptr, follow ? e->ev_fork : nullptr, sh.base, entry - sh.base, stop));
+  e->launches_other += 1;
+  if (follow) {
+    B2_CUDA_CHECK(cudaStreamWaitEvent(e->st2, e->ev_fork, 0));
+    B2_TRY(b2k_segment(e->st2, sh.d_in, e->d_chunks.p, max_chunks, e->d_T.p, e->d_seg.p, e->d_nseg.p, e->d_scalars.p + 12));
+    B2_CUDA_CHECK(cudaEventRecord(e->ev_join, e->st2));
+    e->launches_other += 1;
+  }
+  u32 sc[4] = {0, 0, 0, 0};
+  B2_CUDA_CHECK(cudaMemcpyAsync(sc, e->d_scalars.p, sizeof sc, cudaMemcpyDeviceToHost, st));
+  B2_CUDA_CHECK(cudaStreamSynchronize(st));
+  const u32 nc = sc[0];
+  if (nc > max_chunks) B2_FAIL(B2_ERR_INTERNAL, "chunk table overflow");
+  e->chunks.resize(nc);
+  if (nc) B2_CUDA_CHECK(cudaMemcpy(e->chunks.data(), e->d_chunks.p, nc * sizeof(B2Chunk), cudaMemcpyDeviceToHost));
+  sh.entry = entry;
+  sh.handoff = sh.base + ((u64)sc[2] | ((u64)sc[3] << 32));
+  *handoff = sh.handoff;
+  sh.cut = true;
+  // followed: the segmentation is running behind the chain on the other stream
+  return 0;
+}
+
+int b2_shard_encode(b2_encoder *e, b2_shard_link *link) {
+  if (!e || !link) B2_FAIL(B2_ERR_ARGUMENT, "bad argument");
+  ShardState &sh = e->shard;
+  if (!sh.cut) B2_FAIL(B2_ERR_ARGUMENT, "b2_shard_encode without b2_shard_cut");
+  B2_CUDA_CHECK(cudaSetDevice(e->device));
+  const u32 nc = (u32)e->chunks.size();
+  std::vector<StreamDesc> streams(1);
+  streams[0] = StreamDesc{0, sh.n_local, sh.hint, 0, 0, 0, nc};
+  e->stats.streams++; e->stats.input_bytes += sh.handoff - sh.entry;
+  std::vector<u32> chunk_stream(nc, 0u);
+  const bool followed = e->level == 9 && e->timing < 2;
+  B2_TRY(encode_chunks(e, sh.d_in, streams, chunk_stream, followed, &sh));
+  // what the shard does to the bit offset and to the combined CRC, for every incoming offset mod 8
+  for (u32 phase0 = 0; phase0 < 8; phase0++) {
+    u64 total = 0; u32 rot = 0, fold = 0, ph = phase0;
+    for (u32 c = 0; c < nc; c++) {
+      const ShardCand *cd = &sh.cands[(size_t)c * 4];
+      int best = 0;
+      for (int t = 0; t < sh.n_tactics[c]; t++) if (((ph + cd[t].nbits) >> 3) < ((ph + cd[best].nbits) >> 3)) best = t;
+      total += cd[best].nbits; ph = (u32)((ph + cd[best].nbits) & 7);
+      const u32 k = cd[best].blocks & 31u;
+      fold = (k ? ((fold << k) | (fold >> (32 - k))) : fold) ^ cd[best].fold;
+      rot = (rot + cd[best].blocks) & 31u;
+    }
+    link->total_bits[phase0] = total; link->crc_rot[phase0] = rot; link->crc_fold[phase0] = fold;
+  }
+  sh.encoded = true;
+  return 0;
+}
+
+int b2_shard_finish(b2_encoder *e, uint64_t bit_offset, uint32_t crc_in, uint8_t *out, int out_is_device, uint64_t out_cap,
+                    uint64_t *out_byte_offset, uint64_t *out_len, uint8_t *first_byte, uint8_t *last_byte) {
+  if (!e || !out_len || !out_byte_offset) B2_FAIL(B2_ERR_ARGUMENT, "bad argument");
+  ShardState &sh = e->shard;
+  if (!sh.encoded) B2_FAIL(B2_ERR_ARGUMENT, "b2_shard_finish without b2_shard_encode");
+  B2_CUDA_CHECK(cudaSetDevice(e->device));
+  cudaStream_t st = e->st;
+  const bool first = sh.base == 0 && sh.entry == 0, last = sh.own_end >= sh.stream_n;
+  if (first && bit_offset != 32) B2_FAIL(B2_ERR_ARGUMENT, "the first shard starts behind the 32-bit stream header");
+  const u64 byte0 = first ? 0 : bit_offset >> 3;         // first byte of the stream this shard touches
+  const u64 lbit0 = bit_offset - 8 * byte0;              // its bits start here in its piece
+  const u32 nc = (u32)e->chunks.size();
+  // winners, in order (:1305-1345), now that the incoming offset is known
+  std::vector<std::vector<B2ConcatItem>> items(sh.arenas.size());
+  u64 lbit = lbit0;
+  u32 crc = crc_in;
+  for (u32 c = 0; c < nc; c++) {
+    const ShardCand *cd = &sh.cands[(size_t)c * 4];
+    const u32 in_bits = (u32)(lbit & 7);
+    int best = 0;
+    b2_chunk_trace &tr = e->trace[c];
+    for (int t = 0; t < sh.n_tactics[c]; t++) tr.bytes[t] = (in_bits + cd[t].nbits) >> 3;
+    for (int t = 0; t < sh.n_tactics[c]; t++) if (tr.bytes[t] < tr.bytes[best]) best = t;
+    tr.winner = best;
+    if (!cd[best].kept) B2_FAIL(B2_ERR_INTERNAL, "the winning candidate was not kept");
+    if (cd[best].arena >= items.size()) B2_FAIL(B2_ERR_INTERNAL, "candidate arena missing");
+    items[cd[best].arena].push_back(B2ConcatItem{cd[best].word_off, cd[best].nbits, lbit});
+    lbit += cd[best].nbits;
+    const u32 k = cd[best].blocks & 31u;
+    crc = (k ? ((crc << k) | (crc >> (32 - k))) : crc) ^ cd[best].fold;
+  }
+  const u64 end_bit = lbit + (last ? 80 : 0);
+  const u64 len = (end_bit + 7) >> 3;
+  *out_len = len; *out_byte_offset = byte0;
+  if (len > out_cap) B2_FAIL(B2_ERR_OUTPUT_TOO_SMALL, "output buffer too small");
+  B2_TRY(e->d_out.ensure(len / 4 + 16));
+  B2_CUDA_CHECK(cudaMemsetAsync(e->d_out.p, 0, (len / 4 + 8) * sizeof(u32), st));
+  Workspace *w = e->ws[0];
+  for (size_t a = 0; a < items.size(); a++) {
+    if (items[a].empty()) continue;
+    B2_TRY(w->d_items.ensure(items[a].size()));
+    B2_CUDA_CHECK(cudaMemcpyAsync(w->d_items.p, items[a].data(), items[a].size() * sizeof(B2ConcatItem), cudaMemcpyHostToDevice, st));
+    for (size_t i0 = 0; i0 < items[a].size(); i0 += 65535) {
+      B2_TRY(b2k_concat(st, w->d_items.p + i0, (u32)std::min<size_t>(65535, items[a].size() - i0), sh.arenas[a]->p, e->d_out.p));
+      e->launches_other += 1;
+    }
+    B2_CUDA_CHECK(cudaStreamSynchronize(st));          // d_items is reused by the next arena
+  }
+  if (first || last) {
+    B2StreamEnd E{0, lbit, crc, (first ? 0u : 1u) | (last ? 0u : 2u)};
+    B2_TRY(e->d_ends.ensure(1));
+    B2_CUDA_CHECK(cudaMemcpyAsync(e->d_ends.p, &E, sizeof E, cudaMemcpyHostToDevice, st));
+    B2_TRY(b2k_stream_ends(st, e->d_ends.p, 1, e->level, e->d_out.p));
+    e->launches_other += 1;
+  }
+  if (out && len) B2_CUDA_CHECK(cudaMemcpyAsync(out, e->d_out.p, len, out_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+  u8 fb[2] = {0, 0};
+  if (len) {
+    B2_CUDA_CHECK(cudaMemcpyAsync(&fb[0], e->d_out.p, 1, cudaMemcpyDeviceToHost, st));
+    B2_CUDA_CHECK(cudaMemcpyAsync(&fb[1], (const u8 *)e->d_out.p + (len - 1), 1, cudaMemcpyDeviceToHost, st));
+  }
+  if (e->timing) cudaEventRecord(e->ev_call[1], st);
+  B2_CUDA_CHECK(cudaStreamSynchronize(st));
+  if (first_byte) *first_byte = fb[0];
+  if (last_byte) *last_byte = fb[1];
+  if (e->timing) { float ms = 0; cudaEventElapsedTime(&ms, e->ev_call[0], e->ev_call[1]); e->stats.call_ms += ms; }
+  sh.encoded = false; sh.cut = false; sh.open = false;
+  return 0;
+}
+
+// One stream over the devices of several handles of this process: the north star's block-wise sharding
+// (per-device streams, pinned host buffers, no collective).  One host thread per handle.
+int b2_encode_stream_multi(b2_encoder **encs, int n_encs, const uint8_t *in, uint64_t n, int64_t size_hint,
+                           uint8_t *out, uint64_t out_cap, uint64_t *out_len) {
+  if (!encs || n_encs < 1 || !out_len || (n && !in)) B2_FAIL(B2_ERR_ARGUMENT, "bad argument");
+  for (int i = 0; i < n_encs; i++) if (!encs[i] || encs[i]->level != encs[0]->level) B2_FAIL(B2_ERR_ARGUMENT, "handles must share the block size");
+  const int level = encs[0]->level;
+  u64 min_share = 64ull << 20;
+  if (const char *sv = getenv("B2GPU_SHARD_MIN_BYTES")) { long long v = atoll(sv); if (v >= 65536) min_share = (u64)v; }
+  const int ns = (int)std::max<u64>(1, std::min<u64>((u64)n_encs, n / min_share));
+  if (ns == 1) return b2_encode_stream(encs[0], in, n, size_hint, out, out_cap, out_len);
+  std::vector<u64> bounds(ns + 1);
+  B2_TRY(b2_shard_plan(n, ns, level, -1, bounds.data()));
+  const u64 margin = b2_shard_margin(level);
+  std::vector<b2_shard_link> links(ns);
+  std::vector<u64> entry(ns + 1, 0), bit_off(ns + 1, 0), piece_off(ns, 0), piece_len(ns, 0);
+  std::vector<u32> crcs(ns + 1, 0);
+  std::vector<u8> fb(ns, 0), lb(ns, 0);
+  std::vector<int> rcs(ns, 0);
+  std::vector<std::string> msgs(ns);
+  std::mutex mu;
+  std::condition_variable cv;
+  int cut_done = 0, enc_done = 0;           // shards that have cut / encoded (guarded by mu)
+  bool failed = false, resolved = false;
+  auto run = [&](int r) {
+    b2_encoder *e = encs[r];
+    int rc = 0;
+    auto fail = [&](int code) {
+      rc = code; msgs[r] = g_last_error;
+      { std::lock_guard<std::mutex> lk(mu); failed = true; }
+      cv.notify_all();
+    };
+    const u64 lo = bounds[r], hi = std::min<u64>(n, bounds[r + 1] + (r + 1 < ns ? margin : 0));
+    if ((rc = b2_shard_open(e, in + lo, 0, lo, hi - lo, n, size_hint, bounds[r + 1]))) { fail(rc); rcs[r] = rc; return; }
+    {
+      std::unique_lock<std::mutex> lk(mu);
+      cv.wait(lk, [&] { return cut_done == r || failed; });
+      if (failed) { rcs[r] = B2_ERR_INTERNAL; return; }
+    }
+    u64 ho = 0;
+    if ((rc = b2_shard_cut(e, entry[r], &ho))) { fail(rc); rcs[r] = rc; return; }
+    { std::lock_guard<std::mutex> lk(mu); entry[r + 1] = ho; cut_done = r + 1; }
+    cv.notify_all();
+    if ((rc = b2_shard_encode(e, &links[r]))) { fail(rc); rcs[r] = rc; return; }
+    {
+      std::unique_lock<std::mutex> lk(mu);
+      enc_done++;
+      if (enc_done == ns) {
+        b2_shard_resolve(links.data(), ns, bit_off.data(), crcs.data());
+        resolved = true;
+        cv.notify_all();
+      }
+      cv.wait(lk, [&] { return resolved || failed; });
+      if (failed) { rcs[r] = B2_ERR_INTERNAL; return; }
+    }
+    const u64 total = (bit_off[ns] + 80 + 7) >> 3;
+    if (total > out_cap) { b2_set_error(__FILE__, __LINE__, "output buffer too small"); fail(B2_ERR_OUTPUT_TOO_SMALL); rcs[r] = B2_ERR_OUTPUT_TOO_SMALL; return; }
+    const u64 b0 = r == 0 ? 0 : bit_off[r] >> 3;
+    if ((rc = b2_shard_finish(e, bit_off[r], crcs[r], out + b0, 0, out_cap - b0, &piece_off[r], &piece_len[r], &fb[r], &lb[r]))) { fail(rc); rcs[r] = rc; return; }
+  };
+  std::vector<std::thread> th;
+  for (int r = 0; r < ns; r++) th.emplace_back(run, r);
+  for (auto &t : th) t.join();
+  for (int r = 0; r < ns; r++) if (rcs[r] && !msgs[r].empty()) { g_last_error = msgs[r]; return rcs[r]; }
+  for (int r = 0; r < ns; r++) if (rcs[r]) return rcs[r];
+  // neighbouring pieces share a byte when the boundary is not on a byte: every piece wrote only its own bits
+  // there, whichever copy landed last; the byte is the OR of all contributions
+  std::map<u64, u8> edge;
+  for (int r = 0; r < ns; r++) {
+    if (!piece_len[r]) continue;
+    edge[piece_off[r]] |= fb[r];
+    edge[piece_off[r] + piece_len[r] - 1] |= lb[r];
+  }
+  for (auto &kv : edge) out[kv.first] = kv.second;
+  *out_len = (bit_off[ns] + 80 + 7) >> 3;
   return 0;
 }
 

@@ -22,12 +22,13 @@
 #define CT_TILE 2048
 #define CT_THREADS 128          // 16 bytes per thread
 #define NONE32 0xFFFFFFFFu
+#define B2_TRY_K(x) do { int rc_ = (x); if (rc_) return rc_; } while (0)
 
 __device__ __forceinline__ u32 enc_size(u32 len) { return (len < 4 ? len : 4) + (len >= 4 ? 1 : 0); }
 
 __device__ __forceinline__ void load16(const u8 *__restrict__ in, u64 base, u64 n_alloc, u8 *b) {
   // 16-byte aligned vector load when the whole vector is inside the allocation
-  if (base + 16 <= n_alloc) {
+  if (base + 16 <= n_alloc && ((reinterpret_cast<uintptr_t>(in + base)) & 15u) == 0) {
     const uint4 v = *reinterpret_cast<const uint4 *>(in + base);
     const u32 w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -237,20 +238,26 @@ __device__ u64 warp_tile(const u8 *__restrict__ in, u64 n, const u64 *__restrict
   return res;
 }
 
+// `in` holds the bytes [gbase, gbase + n) of the stream (gbase = 0, and the whole stream, unless the stream is
+// spread over several handles: b2_shard_*).  The walk starts at local position pos0 and ends with the first
+// chunk that starts at or after `stop` (that start is handed to the next shard through n_chunks[1..2]) or
+// with the end of the bytes.
 __global__ void __launch_bounds__(32)
 k_cut_chain(const u8 *__restrict__ in, u64 n, i64 size_hint, int level, i64 win_lo, i64 win_hi,
             const u32 *__restrict__ firstchg, const u64 *__restrict__ carry_r, const u64 *__restrict__ tincl, u64 ntiles,
-            B2Chunk *chunks, u32 *n_chunks, u32 max_chunks, u32 *progress) {
+            B2Chunk *chunks, u32 *n_chunks, u32 max_chunks, u32 *progress, u64 gbase, u64 pos0, u64 stop) {
   // progress[0] = chunks published so far, progress[1] = 1 when the chain is complete: k_segment may be
   // following on another stream and starts on a chunk as soon as it is there
   const u32 l = lane_id();
-  u64 pos = 0;
+  u64 pos = pos0;
   u32 nc = 0;
   for (;;) {
+    if (pos >= stop && !(pos0 == 0 && gbase == 0 && n == 0)) break;   // (an empty stream is still one empty chunk, :1428)
     // stream_rest: size_hint - bytes read, sticking at -1 (= unknown_size) once it gets there
     // (bzip2-encoding.adb:1192-1194); the balancing test :1416-1424 was done in float32 on the host
     // and arrives as the integer window [win_lo, win_hi].
-    const i64 rest = size_hint < 0 ? -1 : ((i64)pos <= size_hint ? size_hint - (i64)pos : -1);
+    const i64 gpos = (i64)(gbase + pos);
+    const i64 rest = size_hint < 0 ? -1 : (gpos <= size_hint ? size_hint - gpos : -1);
     i64 cap = (i64)level * 100000;
     if (rest >= win_lo && rest <= win_hi) cap = rest / 2;
     const u64 avail = n - pos;
@@ -322,24 +329,39 @@ k_cut_chain(const u8 *__restrict__ in, u64 n, i64 size_hint, int level, i64 win_
     if (len == 0) break;
   }
   if (l == 0) {
-    *n_chunks = nc;
+    n_chunks[0] = nc;
+    n_chunks[2] = (u32)pos; n_chunks[3] = (u32)(pos >> 32);     // where the next shard's first chunk starts (local)
     if (progress) { __threadfence(); ((volatile u32 *)progress)[1] = 1u; }
   }
 }
 
-int b2k_cut(cudaStream_t st, const u8 *d_in, u64 n, i64 size_hint, int level, i64 win_lo, i64 win_hi,
-            B2Chunk *d_chunks, u32 *d_n_chunks, u32 max_chunks, B2CutWork *w, u32 *d_progress, cudaEvent_t ev_chain_starts) {
+int b2k_cut_scans(cudaStream_t st, const u8 *d_in, u64 n, B2CutWork *w) {
   const u64 ntiles = (n + CT_TILE - 1) / CT_TILE;
   if (ntiles) {
     k_cut_a<<<(u32)ntiles, CT_THREADS, 0, st>>>(d_in, n, w->firstchg, w->lastchg);
     k_cut_s1<<<1, 1024, 0, st>>>(w->lastchg, ntiles, w->carry_r);
     k_cut_b<<<(u32)ntiles, CT_THREADS, 0, st>>>(d_in, n, w->carry_r, w->tsum);
     k_cut_s2<<<1, 1024, 0, st>>>(w->tsum, ntiles, w->tincl);
+    B2_CUDA_CHECK(cudaGetLastError());
   }
+  return 0;
+}
+
+int b2k_cut_chain(cudaStream_t st, const u8 *d_in, u64 n, i64 size_hint, int level, i64 win_lo, i64 win_hi,
+                  B2Chunk *d_chunks, u32 *d_n_chunks, u32 max_chunks, B2CutWork *w, u32 *d_progress, cudaEvent_t ev_chain_starts,
+                  u64 gbase, u64 pos0, u64 stop) {
+  const u64 ntiles = (n + CT_TILE - 1) / CT_TILE;
   if (d_progress) B2_CUDA_CHECK(cudaMemsetAsync(d_progress, 0, 2 * sizeof(u32), st));
   if (ev_chain_starts) B2_CUDA_CHECK(cudaEventRecord(ev_chain_starts, st));
   k_cut_chain<<<1, 32, 0, st>>>(d_in, n, size_hint, level, win_lo, win_hi, w->firstchg, w->carry_r, w->tincl, ntiles,
-                                d_chunks, d_n_chunks, max_chunks, d_progress);
+                                d_chunks, d_n_chunks, max_chunks, d_progress, gbase, pos0, stop);
   B2_CUDA_CHECK(cudaGetLastError());
   return 0;
+}
+
+int b2k_cut(cudaStream_t st, const u8 *d_in, u64 n, i64 size_hint, int level, i64 win_lo, i64 win_hi,
+            B2Chunk *d_chunks, u32 *d_n_chunks, u32 max_chunks, B2CutWork *w, u32 *d_progress, cudaEvent_t ev_chain_starts) {
+  B2_TRY_K(b2k_cut_scans(st, d_in, n, w));
+  return b2k_cut_chain(st, d_in, n, size_hint, level, win_lo, win_hi, d_chunks, d_n_chunks, max_chunks, w, d_progress, ev_chain_starts,
+                       0, 0, n);
 }

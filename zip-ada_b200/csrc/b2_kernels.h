@@ -32,7 +32,13 @@ struct B2SortStats {
 struct B2CutWork { u32 *firstchg, *lastchg, *tsum; u64 *carry_r, *tincl; };
 int b2k_cut(cudaStream_t st, const u8 *d_in, u64 n, i64 size_hint, int level, i64 win_lo, i64 win_hi,
             B2Chunk *d_chunks, u32 *d_n_chunks, u32 max_chunks, B2CutWork *w, u32 *d_progress, cudaEvent_t ev_chain_starts);
+int b2k_cut_scans(cudaStream_t st, const u8 *d_in, u64 n, B2CutWork *w);
+int b2k_cut_chain(cudaStream_t st, const u8 *d_in, u64 n, i64 size_hint, int level, i64 win_lo, i64 win_hi,
+                  B2Chunk *d_chunks, u32 *d_n_chunks, u32 max_chunks, B2CutWork *w, u32 *d_progress, cudaEvent_t ev_chain_starts,
+                  u64 gbase, u64 pos0, u64 stop);
 // b2_segment.cu
+#define B2_SEG_GAVE_UP 0xFFFFFFFDu     // a CTA following the chunk chain never saw its chunk (time-sliced GPU): segment again afterwards
+#define B2_SEG_PENDING 0xFEFEFEFEu
 int b2k_segment(cudaStream_t st, const u8 *d_in, const B2Chunk *d_chunks, u32 n_chunks, const double *d_T,
                 u32 *d_seg, u32 *d_nseg, const u32 *d_progress);
 // b2_rle1.cu

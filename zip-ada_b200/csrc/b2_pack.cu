@@ -234,7 +234,9 @@ __global__ void k_stream_ends(const B2StreamEnd *__restrict__ ends, u32 n, int l
   if (s >= n) return;
   const B2StreamEnd E = ends[s];
   u32 *w = out + (E.out_off >> 2);                 // regions are 8-byte aligned
-  atomicOr(&w[0], bswap32(0x425A6800u | (u32)('0' + level)));
+  // pad bit 0: no header, bit 1: no footer (a shard of a stream that is not its first / last, b2_shard_finish)
+  if (!(E.pad & 1u)) atomicOr(&w[0], bswap32(0x425A6800u | (u32)('0' + level)));
+  if (E.pad & 2u) return;
   u64 p = E.end_bit;
   put_bits_atomic(w, p, 0x177245u, 24); p += 24;
   put_bits_atomic(w, p, 0x385090u, 24); p += 24;

@@ -178,7 +178,7 @@ template <int N> __device__ __forceinline__ void seg_scan(SegSmem &S, double E, 
 }
 
 __global__ void __launch_bounds__(SG_THREADS, 3)
-k_segment(const u8 *__restrict__ in, const B2Chunk *__restrict__ chunks, u32 n_chunks,
+k_segment(const u8 *__restrict__ in, const B2Chunk *chunks, u32 n_chunks,
           const double *__restrict__ T, u32 *__restrict__ seg, u32 *__restrict__ nseg, const u32 *progress) {
   __shared__ SegSmem S;
   const u32 c = blockIdx.x;
@@ -198,7 +198,7 @@ k_segment(const u8 *__restrict__ in, const B2Chunk *__restrict__ chunks, u32 n_c
         __nanosleep(400);
       }
       S.first[0] = state;
-      if (state == 2) { nseg[2 * c] = 0xFFFFFFFFu; nseg[2 * c + 1] = 0xFFFFFFFFu; }   // reported as an overflow by the host
+      if (state == 2) { nseg[2 * c] = B2_SEG_GAVE_UP; nseg[2 * c + 1] = B2_SEG_GAVE_UP; }   // the host segments again after the chain
     }
     __syncthreads();
     const u32 state = S.first[0];
@@ -207,8 +207,9 @@ k_segment(const u8 *__restrict__ in, const B2Chunk *__restrict__ chunks, u32 n_c
     __threadfence();
   }
   const u32 lt = (1u << l) - 1u;
-  const u8 *buf = in + chunks[c].start;
-  const i32 len = (i32)chunks[c].len;
+  // (the table may be written by the chain kernel while this kernel runs: no read-only cache path)
+  const u8 *buf = in + __ldcg(&chunks[c].start);
+  const i32 len = (i32)__ldcg(&chunks[c].len);
   const double thr[2] = {(double)0.6f, (double)0.4f};    // Float generic formal widened (data_segmentation.ads:43)
   const i32 ithr[2] = {4000, 8000};
   i32 index_mark[2] = {1, 1};
