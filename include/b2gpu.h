@@ -36,6 +36,7 @@ extern "C" {
 #define B2_ERR_ALLOC 3
 #define B2_ERR_CUDA 10
 #define B2_ERR_INTERNAL 11
+#define B2_ERR_ABORTED 12          /* the progress callback asked to stop: Zip.User_abort (zip-compress.ads:149) */
 #define B2_ERR_DUPLICATE_NAME 20   /* Zip.Create.Duplicate_name (zip-create.ads, zip-create.adb:138-147) */
 
 /* Compression_Option (bzip2-encoding.ads:40-43): block_100k / block_400k / block_900k.
@@ -176,6 +177,14 @@ B2_API int b2_zip_create(b2_encoder *enc, uint32_t n_entries, const uint8_t *in,
 
 /* Zip CRC-32 of a host buffer, computed on the device (zip-crc_crypto.adb:31-61: Init, Update, Final). */
 B2_API int b2_zip_crc32(b2_encoder *enc, const uint8_t *in, uint64_t n, uint32_t *crc);
+
+/* Feedback and abort (zip.ads:301-306 Feedback_Proc; zip-compress-bzip2_e.adb:78-96 fires it from Read_Byte and
+ * raises User_abort).  The batched calls read no bytes through callbacks, so the hook moves here: `fn` is called
+ * on the CALLING thread (never from a library thread) after every device batch of b2_encode_stream* /
+ * b2_encode_batch / b2_zip_create with the uncompressed bytes done so far and the total; a non-zero result
+ * stops the remaining batches and the call returns B2_ERR_ABORTED (the Ada body raises User_abort).  NULL = off. */
+typedef int (*b2_progress_fn)(void *user, uint64_t done_bytes, uint64_t total_bytes);
+B2_API int b2_set_progress(b2_encoder *enc, b2_progress_fn fn, void *user);
 
 /* Last error message of the calling thread (never NULL). */
 B2_API const char *b2_last_error(void);

@@ -201,3 +201,34 @@ def test_encode_stream_multi(b2mod, enc9, n_handles, monkeypatch):
             e.close()
     assert out == ref and out2 == ref
     assert bz2.decompress(out) == data.tobytes()
+
+
+# ---- feedback / abort through the batched calls (zip.ads:301-306, zip-compress-bzip2_e.adb:78-96) --------------
+def test_progress_callback_and_abort(b2mod, monkeypatch):
+    monkeypatch.setenv("B2GPU_BATCH_POSITIONS", str(4 << 20))          # several device batches for a small input
+    data = corpus.markov_text(12 * MiB, 0x31)
+    ref = None
+    with b2mod.Encoder(9, 0) as e:
+        calls = []
+        e.set_progress(lambda done, total: calls.append((done, total)) or False)
+        out = e.encode(data, data.size).tobytes()
+        assert len(calls) >= 3 and calls[-1][0] == calls[-1][1] == data.size
+        assert all(a[0] < b[0] for a, b in zip(calls, calls[1:]))
+        e.set_progress(None)
+        ref = e.encode(data, data.size).tobytes()
+        assert out == ref                                              # the callback does not change the stream
+        # User_abort: the second call asks to stop
+        seen = []
+        e.set_progress(lambda done, total: seen.append(done) or len(seen) >= 2)
+        with pytest.raises(b2mod.B2Error) as ei:
+            e.encode(data, data.size)
+        assert "error 12" in str(ei.value) and len(seen) == 2
+        # the handle stays usable; archives report progress too
+        e.set_progress(None)
+        assert e.encode(data, data.size).tobytes() == ref
+        zc = []
+        e.set_progress(lambda done, total: zc.append((done, total)) or False)
+        arch = e.zip_create([("a.txt", data[:3 * MiB]), ("b.bin", datagen.random_bytes(2 * MiB, 5)), ("c.txt", data[3 * MiB:9 * MiB])])
+        assert zc and zc[-1][0] == zc[-1][1] == 3 * MiB + 2 * MiB + 6 * MiB
+        import io, zipfile
+        assert zipfile.ZipFile(io.BytesIO(arch.tobytes())).testzip() is None

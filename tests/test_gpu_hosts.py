@@ -96,3 +96,24 @@ def test_cpp_zip_create_mirror(tmp_path):
     assert arc == orc.zip_create(list(files.items()), 9)[0]
     z = zipfile.ZipFile(io.BytesIO(arc))
     assert z.testzip() is None and z.read("t.txt") == files["t.txt"]
+
+
+def test_cpp_encode_loop_pools_the_handle_and_survives_callback_exceptions(tmp_path):
+    """The Ada body's call sequence (one Encode per archive entry, exceptions out of Write_Byte / Read_Byte in
+    the middle of an entry) through the C++ mirror: one pooled handle serves every entry."""
+    exe = tmp_path / "loop"
+    pkg = os.path.join(ROOT, "zip-ada_b200")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", os.path.join(pkg, "host", "test_encode_loop.cpp"), "-L" + pkg, "-lb2gpu",
+                           "-Wl,-rpath," + pkg, "-o", str(exe)])
+    entries = [datagen.text(200_000, 61), datagen.random_bytes(50_000, 62),      # entry 1: incompressible -> Compression_inefficient
+               datagen.text(100_000, 63),                                       # entry 2: User_abort half way through Read_Byte
+               datagen.mixed(1_200_000, 150_000, 64), datagen.text(3_000, 65)]
+    names = []
+    for k, e in enumerate(entries):
+        p = tmp_path / ("in%d.bin" % k)
+        p.write_bytes(e.tobytes())
+        names.append(str(p))
+    res = subprocess.run([str(exe), str(tmp_path)] + names, check=True, stdout=subprocess.PIPE, text=True).stdout
+    assert res.split() == ["created=1", "ok=3", "inefficient=1", "aborted=1"], res
+    for k in (0, 3, 4):
+        assert (tmp_path / ("%d.bz2" % k)).read_bytes() == orc.encode_stream(entries[k], 9, entries[k].size)

@@ -50,11 +50,13 @@ class ChunkTrace(C.Structure):
                 ("bytes", C.c_uint64 * 4), ("bits", C.c_uint64 * 4)]
 
 
+PROGRESS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint64, C.c_uint64)
+
 EXPORTS = ["b2_create", "b2_destroy", "b2_bound", "b2_encode_stream", "b2_encode_stream_device", "b2_encode_batch", "b2_last_error",
            "b2_set_timing", "b2_get_stats", "b2_reset_stats", "b2_dbg_block", "b2_get_trace", "b2_get_segments",
            "b2_zip_bound", "b2_zip_create", "b2_zip_crc32",
            "b2_shard_margin", "b2_shard_plan", "b2_shard_open", "b2_shard_cut", "b2_shard_encode", "b2_shard_resolve",
-           "b2_shard_finish", "b2_encode_stream_multi"]
+           "b2_shard_finish", "b2_encode_stream_multi", "b2_set_progress"]
 
 _lib = None
 
@@ -90,6 +92,7 @@ def lib():
         _lib.b2_dbg_block.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32] + [C.c_void_p] * 6 + [C.c_uint64, C.POINTER(BlockInfo)]
         _lib.b2_get_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
         _lib.b2_get_segments.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
+        _lib.b2_set_progress.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.b2_shard_margin.restype = C.c_uint64
         _lib.b2_shard_margin.argtypes = [C.c_int]
         _lib.b2_shard_plan.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_void_p]
@@ -266,6 +269,15 @@ class Encoder:
             buf.append(read_byte())
         for b in self.encode(bytes(buf), size_hint).tobytes():
             write_byte(b)
+
+    def set_progress(self, fn):
+        """fn (done_bytes, total_bytes) -> truthy to abort (B2Error with code 12); None switches it off."""
+        if fn is None:
+            self._cb = None
+            _check(lib().b2_set_progress(self._h, None, None))
+            return
+        self._cb = PROGRESS_FN(lambda user, done, total: 1 if fn(done, total) else 0)
+        _check(lib().b2_set_progress(self._h, C.cast(self._cb, C.c_void_p), None))
 
     # -- measurement / parity taps ----------------------------------------------------------------
     def set_timing(self, on):

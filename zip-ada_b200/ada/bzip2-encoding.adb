@@ -4,13 +4,18 @@
 --  formals (Read_Byte, More_Bytes, Write_Byte), same Encode (option, size_hint).  This body only
 --  drains the input callbacks into a buffer, calls the C ABI of include/b2gpu.h, and replays the
 --  result through Write_Byte in order.  Exceptions raised inside the callbacks (User_abort,
---  Compression_inefficient, ...) propagate through Encode; the handle and buffers are released in
---  an exception handler, mirroring the clean-up of the original body
---  (bzip2-encoding.adb:1128-1133, :1351-1357, :1377-1381).
+--  Compression_inefficient, ...) propagate through Encode; the buffers are released and the
+--  handle goes back to the pool in an exception handler, mirroring the clean-up of the original
+--  body (bzip2-encoding.adb:1128-1133, :1351-1357, :1377-1381).
+--
+--  Handles (CUDA streams, tables, device workspaces) are expensive to create, and Zip.Create calls
+--  Encode once per archive entry (zip-create.adb:253-265): they are kept in a protected pool, one
+--  per (block size, concurrent caller).  Several tasks may run Encode at the same time
+--  (doc/zipada.txt:26); each takes its own handle from the pool.
 --
 --  NOTE: there is no Ada compiler in the build image of this repository, so this file has not
 --  been compiled.  It is deliberately small; the C++ mirror host/bzip2_encoding.hpp has the same
---  logic and is what the tests drive.  Link with -lb2gpu.
+--  logic (pool included) and is what the tests drive.  Link with -lb2gpu.
 
 with Ada.Unchecked_Deallocation;
 with Interfaces.C;
@@ -19,6 +24,7 @@ with System;
 package body BZip2.Encoding is
 
   use Interfaces, Interfaces.C;
+  use type System.Address;
 
   subtype Handle is System.Address;
 
@@ -27,6 +33,7 @@ package body BZip2.Encoding is
 
   procedure b2_destroy (enc : Handle);
   pragma Import (C, b2_destroy, "b2_destroy");
+  pragma Unreferenced (b2_destroy);  --  pooled handles live as long as the program
 
   function b2_bound (n : Unsigned_64) return Unsigned_64;
   pragma Import (C, b2_bound, "b2_bound");
@@ -47,6 +54,43 @@ package body BZip2.Encoding is
 
   b2gpu_error : exception;
 
+  Device : constant int := 0;  --  CUDA device of the pooled handles
+
+  --  Idle handles, per block size.  Take returns Null_Address when none is idle.
+  type Handle_List is array (1 .. 64) of Handle;
+  type Pool_Row is record
+    idle  : Handle_List := (others => System.Null_Address);
+    count : Natural := 0;
+  end record;
+  type Pool_Table is array (Compression_Option) of Pool_Row;
+
+  protected Pool is
+    procedure Take (option : Compression_Option; h : out Handle);
+    procedure Give (option : Compression_Option; h : Handle; kept : out Boolean);
+  private
+    rows : Pool_Table;
+  end Pool;
+
+  protected body Pool is
+    procedure Take (option : Compression_Option; h : out Handle) is
+    begin
+      if rows (option).count = 0 then
+        h := System.Null_Address;
+      else
+        h := rows (option).idle (rows (option).count);
+        rows (option).count := rows (option).count - 1;
+      end if;
+    end Take;
+    procedure Give (option : Compression_Option; h : Handle; kept : out Boolean) is
+    begin
+      kept := rows (option).count < rows (option).idle'Last;
+      if kept then
+        rows (option).count := rows (option).count + 1;
+        rows (option).idle (rows (option).count) := h;
+      end if;
+    end Give;
+  end Pool;
+
   procedure Encode
     (option    : Compression_Option := block_900k;
      size_hint : Stream_Size_Type   := unknown_size)
@@ -62,9 +106,12 @@ package body BZip2.Encoding is
     n       : Unsigned_64 := 0;
     out_len : aliased Unsigned_64 := 0;
     grown   : Byte_Array_Access;
+    kept    : Boolean;
+    procedure b2_destroy_now (e : Handle);
+    pragma Import (C, b2_destroy_now, "b2_destroy");
   begin
-    --  1) Drain the input callbacks (they update the Zip CRC-32 and the feedback,
-    --     zip-compress-bzip2_e.adb:70-106, exactly as before).
+    --  1) Drain the input callbacks (they update the Zip CRC-32 and the feedback, and may raise
+    --     User_abort, zip-compress-bzip2_e.adb:70-106, exactly as before).
     while More_Bytes loop
       if n = inp'Last then
         grown := new Byte_Array (1 .. inp'Last * 2);
@@ -75,8 +122,9 @@ package body BZip2.Encoding is
       n := n + 1;
       inp (n) := Read_Byte;
     end loop;
-    --  2) One call to the device encoder (whole stream: header, blocks, footer).
-    if b2_create (level, 0, enc'Access) /= 0 then
+    --  2) One call to the device encoder (whole stream: header, blocks, footer) on a pooled handle.
+    Pool.Take (option, enc);
+    if enc = System.Null_Address and then b2_create (level, Device, enc'Access) /= 0 then
       raise b2gpu_error with "b2_create failed (no CUDA device?) - there is no CPU fallback";
     end if;
     outp := new Byte_Array (1 .. b2_bound (n) + 1024 * (n / 40_000 + 16));
@@ -86,17 +134,25 @@ package body BZip2.Encoding is
     then
       raise b2gpu_error with "b2_encode_stream failed";
     end if;
-    --  3) Replay the result through Write_Byte, in order (may raise Compression_inefficient).
+    Pool.Give (option, enc, kept);
+    if not kept then
+      b2_destroy_now (enc);
+    end if;
+    enc := System.Null_Address;
+    Free (inp);
+    --  3) Replay the result through Write_Byte, in order (may raise Compression_inefficient,
+    --     zip-compress.adb:480-486: the handle is already back in the pool).
     for i in 1 .. out_len loop
       Write_Byte (outp (i));
     end loop;
-    b2_destroy (enc);
-    Free (inp);
     Free (outp);
   exception
     when others =>
-      if System."/=" (enc, System.Null_Address) then
-        b2_destroy (enc);
+      if enc /= System.Null_Address then
+        Pool.Give (option, enc, kept);
+        if not kept then
+          b2_destroy_now (enc);
+        end if;
       end if;
       Free (inp);
       Free (outp);

@@ -143,6 +143,8 @@ struct ShardState {
 struct b2_encoder {
   int level = 9, device = 0;
   ShardState shard;
+  b2_progress_fn progress = nullptr;    // called on the calling thread between batches; non-zero return aborts
+  void *progress_user = nullptr;
   cudaStream_t st = nullptr;            // stream of the stream-level work (cut, segment, copies, footer)
   cudaStream_t st2 = nullptr;           // segmentation following the chunk chain
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -270,6 +272,7 @@ int run_batch(b2_encoder *e, Workspace *w, const u8 *d_in, std::vector<B2Job> &j
   const u32 J = (u32)jobs.size();
   if (J == 0) return 0;
   const u64 T = layout_jobs(jobs, e->level);
+  if (T >= (1ull << 32) - (1ull << 20)) B2_FAIL(B2_ERR_INTERNAL, "batch too large for 32-bit arena offsets (lower B2GPU_BATCH_POSITIONS)");
   B2_TRY(ensure_batch_workspace(w, (size_t)T + 64, J));
   cudaStream_t st = w->st;
   B2_CUDA_CHECK(cudaMemcpyAsync(w->d_jobs.p, jobs.data(), J * sizeof(B2Job), cudaMemcpyHostToDevice, st));
@@ -430,6 +433,36 @@ struct StreamDesc {
 // Encodes streams[*] (all resident in d_in) into disjoint regions of e->d_out.  Every stream is what
 // one `Encode (option, size_hint)` call writes (bzip2-encoding.adb:1413-1431); chunks of all streams
 // share the batches, so many small entries fill the device as well as one large stream.
+void reset_workspace_stats(b2_encoder *e) {
+  for (auto *w : e->ws) {
+    memset(&w->sort_stats, 0, sizeof w->sort_stats);
+    w->launches = 0; w->blocks = 0; w->block_bytes = 0; w->sort_ms = 0;
+    for (int i = 0; i < 8; i++) w->stage_ms[i] = 0;
+  }
+}
+
+void merge_workspace_stats(b2_encoder *e) {
+  for (auto *w : e->ws) {
+    e->sort_stats.scatter_launches += w->sort_stats.scatter_launches;
+    e->sort_stats.scatter_elems += w->sort_stats.scatter_elems;
+    e->sort_stats.scatter_ms += w->sort_stats.scatter_ms;
+    e->sort_stats.rounds += w->sort_stats.rounds;
+    e->sort_stats.sorted_elems_round0 += w->sort_stats.sorted_elems_round0;
+    e->sort_stats.sorted_elems_later += w->sort_stats.sorted_elems_later;
+    e->sort_stats.launches += w->sort_stats.launches;
+    e->launches_other += w->launches;
+    e->stats.blocks += w->blocks; e->stats.block_bytes += w->block_bytes; e->stats.sort_ms += w->sort_ms;
+    for (int i = 1; i < 8; i++) e->stats.stage_ms[i] += w->stage_ms[i];
+  }
+  e->stats.sort_rounds = e->sort_stats.rounds;
+  e->stats.sort_elems_round0 = e->sort_stats.sorted_elems_round0;
+  e->stats.sort_elems_later = e->sort_stats.sorted_elems_later;
+  e->stats.scatter_launches = e->sort_stats.scatter_launches;
+  e->stats.scatter_elems = e->sort_stats.scatter_elems;
+  e->stats.scatter_ms = e->sort_stats.scatter_ms;
+  e->stats.kernel_launches = e->launches_other + e->sort_stats.launches;
+}
+
 int encode_chunks(b2_encoder *e, const u8 *d_in, std::vector<StreamDesc> &streams, std::vector<u32> &chunk_stream, bool followed,
                   ShardState *sh);
 
@@ -596,15 +629,12 @@ int encode_chunks(b2_encoder *e, const u8 *d_in, std::vector<StreamDesc> &stream
   for (size_t si = 0; si < streams.size(); si++) { ends[si].out_off = streams[si].out_off; ends[si].end_bit = 32; ends[si].crc = 0; ends[si].pad = 0; }
   u64 out_words_needed = 0;
   const int W = (e->timing >= 2) ? 1 : std::max<int>(1, (int)e->ws.size());
-  for (auto *w : e->ws) {
-    memset(&w->sort_stats, 0, sizeof w->sort_stats);
-    w->launches = 0; w->blocks = 0; w->block_bytes = 0; w->sort_ms = 0;
-    for (int i = 0; i < 8; i++) w->stage_ms[i] = 0;
-  }
+  reset_workspace_stats(e);
   std::atomic<u32> next{0};
   std::mutex mu;
   std::condition_variable cv;
   u32 turn = 0;                 // next batch to resolve (guarded by mu)
+  u32 planned_total = 0xFFFFFFFFu;   // number of batches, known once the planning is complete (guarded by mu)
   int err = 0;
   std::string err_msg;
   auto worker = [&](int wi) {
@@ -754,8 +784,32 @@ int encode_chunks(b2_encoder *e, const u8 *d_in, std::vector<StreamDesc> &stream
       std::lock_guard<std::mutex> lk(mu);
       if (!err) { err = plan_rc; err_msg = plan_msg; }
     }
-    { std::lock_guard<std::mutex> lk(bmu); planned_all = true; }
+    size_t nb_total = 0;
+    { std::lock_guard<std::mutex> lk(bmu); planned_all = true; nb_total = batches.size(); }
     bcv.notify_all();
+    { std::lock_guard<std::mutex> lk(mu); planned_total = (u32)nb_total; }
+    cv.notify_all();
+  }
+  if (e->progress) {
+    // Feedback / User_abort (zip.ads:301-306, zip-compress-bzip2_e.adb:78-96): the callback runs on the calling
+    // thread (never on a worker) after every batch; a non-zero result stops the remaining batches
+    u64 total_bytes = 0;
+    for (u32 c = 0; c < n_chunks; c++) total_bytes += e->chunks[c].len;
+    std::unique_lock<std::mutex> lk(mu);
+    u32 seen = 0;
+    for (;;) {
+      cv.wait(lk, [&] { return turn > seen || err || (planned_total != 0xFFFFFFFFu && turn >= planned_total); });
+      if (turn > seen) {
+        seen = turn;
+        u64 done_bytes = 0;
+        { std::lock_guard<std::mutex> lb(bmu); for (u32 b = 0; b < seen && b < batches.size(); b++) for (u32 c = batches[b].c0; c < batches[b].c1; c++) done_bytes += e->chunks[c].len; }
+        lk.unlock();
+        const int stop = e->progress(e->progress_user, done_bytes, total_bytes);
+        lk.lock();
+        if (stop && !err) { err = B2_ERR_ABORTED; err_msg = "aborted by the progress callback (User_abort)"; }
+      }
+      if (err || (planned_total != 0xFFFFFFFFu && turn >= planned_total)) break;
+    }
   }
   for (auto &t : th) t.join();
   if (followed) B2_CUDA_CHECK(cudaStreamSynchronize(e->st2));
@@ -770,26 +824,7 @@ int encode_chunks(b2_encoder *e, const u8 *d_in, std::vector<StreamDesc> &stream
     B2_CUDA_CHECK(cudaStreamSynchronize(st));
     for (size_t si = 0; si < streams.size(); si++) streams[si].out_len = (ends[si].end_bit + 80 + 7) >> 3;
   }
-  // ---- merge per-workspace statistics -------------------------------------------------------
-  for (auto *w : e->ws) {
-    e->sort_stats.scatter_launches += w->sort_stats.scatter_launches;
-    e->sort_stats.scatter_elems += w->sort_stats.scatter_elems;
-    e->sort_stats.scatter_ms += w->sort_stats.scatter_ms;
-    e->sort_stats.rounds += w->sort_stats.rounds;
-    e->sort_stats.sorted_elems_round0 += w->sort_stats.sorted_elems_round0;
-    e->sort_stats.sorted_elems_later += w->sort_stats.sorted_elems_later;
-    e->sort_stats.launches += w->sort_stats.launches;
-    e->launches_other += w->launches;
-    e->stats.blocks += w->blocks; e->stats.block_bytes += w->block_bytes; e->stats.sort_ms += w->sort_ms;
-    for (int i = 1; i < 8; i++) e->stats.stage_ms[i] += w->stage_ms[i];
-  }
-  e->stats.sort_rounds = e->sort_stats.rounds;
-  e->stats.sort_elems_round0 = e->sort_stats.sorted_elems_round0;
-  e->stats.sort_elems_later = e->sort_stats.sorted_elems_later;
-  e->stats.scatter_launches = e->sort_stats.scatter_launches;
-  e->stats.scatter_elems = e->sort_stats.scatter_elems;
-  e->stats.scatter_ms = e->sort_stats.scatter_ms;
-  e->stats.kernel_launches = e->launches_other + e->sort_stats.launches;
+  merge_workspace_stats(e);
   return 0;
 }
 
@@ -868,37 +903,42 @@ int b2_create(int level, int device, b2_encoder **out) {
   e->level = level; e->device = device;
   memset(&e->stats, 0, sizeof e->stats);
   memset(&e->sort_stats, 0, sizeof e->sort_stats);
-  if (const char *s = getenv("B2GPU_BATCH_POSITIONS")) { long long v = atoll(s); if (v >= (1 << 20)) e->batch_positions = (size_t)v; }
+  // arena offsets are 32-bit: a batch plus one more chunk's worth of blocks must stay below 2^32 positions
+  if (const char *s = getenv("B2GPU_BATCH_POSITIONS")) { long long v = atoll(s); if (v >= (1 << 20)) e->batch_positions = (size_t)std::min<long long>(v, 3ll << 30); }
   if (const char *s = getenv("B2GPU_BATCH_JOBS")) { long long v = atoll(s); if (v >= 8) e->batch_jobs_max = (size_t)std::min<long long>(v, 65535); }   // grid.y of the per-(triple, block) kernels
   if (const char *s = getenv("B2GPU_PIPELINE")) { int v = atoi(s); if (v >= 1 && v <= 8) e->n_workspaces = v; }
-  B2_CUDA_CHECK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
-  B2_CUDA_CHECK(cudaStreamCreateWithFlags(&e->st2, cudaStreamNonBlocking));
-  B2_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
-  B2_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
-  B2_CUDA_CHECK(cudaEventCreate(&e->ev[0])); B2_CUDA_CHECK(cudaEventCreate(&e->ev[1]));
-  B2_CUDA_CHECK(cudaEventCreate(&e->ev_call[0])); B2_CUDA_CHECK(cudaEventCreate(&e->ev_call[1]));
-  for (int i = 0; i < e->n_workspaces; i++) {
-    Workspace *w = new Workspace();
-    e->ws.push_back(w);
-    B2_CUDA_CHECK(cudaStreamCreateWithFlags(&w->st, cudaStreamNonBlocking));
-    B2_CUDA_CHECK(cudaEventCreate(&w->ev[0])); B2_CUDA_CHECK(cudaEventCreate(&w->ev[1]));
-    B2_CUDA_CHECK(cudaEventCreate(&w->ev_sort[0])); B2_CUDA_CHECK(cudaEventCreate(&w->ev_sort[1]));
-  }
-  // constant tables
-  B2CrcTables *ct = new B2CrcTables();
-  b2k_make_crc_tables(ct);
-  int rc = e->d_ct.ensure(1);
-  if (!rc) { cudaMemcpy(e->d_ct.p, ct, sizeof(B2CrcTables), cudaMemcpyHostToDevice); }
-  delete ct;
-  if (rc) { b2_destroy(e); return rc; }
-  // T[c] = -(p * Log (p)), p = Real (c) * inv_window_size, window 16_000 (data_segmentation.adb:44-50)
-  std::vector<double> T(16002, 0.0);
-  const double inv = 1.0 / 16000.0;
-  for (int c = 1; c <= 16001; c++) { double p = (double)c * inv; T[c] = -(p * std::log(p)); }
-  rc = e->d_T.ensure(T.size());
-  if (!rc) cudaMemcpy(e->d_T.p, T.data(), T.size() * sizeof(double), cudaMemcpyHostToDevice);
-  if (!rc) rc = e->d_scalars.ensure(16);
-  if (rc) { b2_destroy(e); return rc; }
+  auto init = [&]() -> int {
+    B2_CUDA_CHECK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
+    B2_CUDA_CHECK(cudaStreamCreateWithFlags(&e->st2, cudaStreamNonBlocking));
+    B2_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+    B2_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+    B2_CUDA_CHECK(cudaEventCreate(&e->ev[0])); B2_CUDA_CHECK(cudaEventCreate(&e->ev[1]));
+    B2_CUDA_CHECK(cudaEventCreate(&e->ev_call[0])); B2_CUDA_CHECK(cudaEventCreate(&e->ev_call[1]));
+    for (int i = 0; i < e->n_workspaces; i++) {
+      Workspace *w = new Workspace();
+      e->ws.push_back(w);
+      B2_CUDA_CHECK(cudaStreamCreateWithFlags(&w->st, cudaStreamNonBlocking));
+      B2_CUDA_CHECK(cudaEventCreate(&w->ev[0])); B2_CUDA_CHECK(cudaEventCreate(&w->ev[1]));
+      B2_CUDA_CHECK(cudaEventCreate(&w->ev_sort[0])); B2_CUDA_CHECK(cudaEventCreate(&w->ev_sort[1]));
+    }
+    // constant tables
+    {
+      std::vector<B2CrcTables> ct(1);
+      b2k_make_crc_tables(ct.data());
+      B2_TRY(e->d_ct.ensure(1));
+      B2_CUDA_CHECK(cudaMemcpy(e->d_ct.p, ct.data(), sizeof(B2CrcTables), cudaMemcpyHostToDevice));
+    }
+    // T[c] = -(p * Log (p)), p = Real (c) * inv_window_size, window 16_000 (data_segmentation.adb:44-50)
+    std::vector<double> T(16002, 0.0);
+    const double inv = 1.0 / 16000.0;
+    for (int c = 1; c <= 16001; c++) { double p = (double)c * inv; T[c] = -(p * std::log(p)); }
+    B2_TRY(e->d_T.ensure(T.size()));
+    B2_CUDA_CHECK(cudaMemcpy(e->d_T.p, T.data(), T.size() * sizeof(double), cudaMemcpyHostToDevice));
+    B2_TRY(e->d_scalars.ensure(16));
+    return 0;
+  };
+  const int rc = init();
+  if (rc) { const std::string msg = g_last_error; b2_destroy(e); g_last_error = msg; return rc; }
   *out = e;
   return 0;
 }
@@ -1462,8 +1502,14 @@ int b2_reset_stats(b2_encoder *e) {
   return 0;
 }
 
+int b2_set_progress(b2_encoder *e, b2_progress_fn fn, void *user) {
+  if (!e) return B2_ERR_ARGUMENT;
+  e->progress = fn; e->progress_user = user;
+  return 0;
+}
+
 int b2_get_trace(b2_encoder *e, b2_chunk_trace *out, uint64_t cap, uint64_t *n) {
-  if (!e || !n) return B2_ERR_ARGUMENT;
+  if (!e || !n || (cap && !out)) return B2_ERR_ARGUMENT;
   *n = e->trace.size();
   for (size_t i = 0; i < e->trace.size() && i < cap; i++) out[i] = e->trace[i];
   return 0;
@@ -1493,7 +1539,11 @@ int b2_dbg_block(b2_encoder *e, const uint8_t *raw, uint32_t len, uint8_t *rle_o
   std::vector<B2Job> jobs(1);
   memset(&jobs[0], 0, sizeof(B2Job));
   jobs[0].raw_off = 0; jobs[0].raw_len = len;
+  reset_workspace_stats(e);
+  memset(&e->sort_stats, 0, sizeof e->sort_stats);
+  e->launches_other = 0;
   B2_TRY(run_batch(e, w, e->d_in.p, jobs));
+  merge_workspace_stats(e);
   const B2Job &b = w->batch_jobs[0];
   if (rle_out && b.n) B2_CUDA_CHECK(cudaMemcpyAsync(rle_out, w->d_text.p + b.pos_off, b.n, cudaMemcpyDeviceToHost, st));
   if (bwt_out && b.n) B2_CUDA_CHECK(cudaMemcpyAsync(bwt_out, w->d_bwt.p + b.pos_off, b.n, cudaMemcpyDeviceToHost, st));
