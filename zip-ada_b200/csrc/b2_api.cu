@@ -239,7 +239,7 @@ int ensure_batch_workspace(Workspace *w, size_t T, size_t J) {
   B2_TRY(w->d_selpos.ensure(GT));
   B2_TRY(w->d_gpack.ensure(GT * B2_N_TRIPLES + 64)); B2_TRY(w->d_gselcost.ensure(GT * B2_N_TRIPLES + 64));
   B2_TRY(w->d_ehist.ensure(J * B2_N_TRIPLES * B2_MAX_CODERS * 260));
-  B2_TRY(w->d_leaves.ensure((J * B2_N_TRIPLES * B2_MAX_CODERS + 64) * 260)); B2_TRY(w->d_wl.ensure(J * B2_N_TRIPLES * (B2_MAX_CODERS + 1) + J / 64 + 256));
+  B2_TRY(w->d_leaves.ensure((J * B2_N_TRIPLES * B2_MAX_CODERS + 64) * 260)); B2_TRY(w->d_wl.ensure(J * B2_N_TRIPLES * (B2_MAX_CODERS + 3) + J / 32 + 512));
   B2_TRY(w->d_estat.ensure(J * B2_N_TRIPLES * 2)); B2_TRY(w->d_selcost.ensure(J * B2_N_TRIPLES));
   B2_TRY(w->d_lens.ensure(J * B2_N_TRIPLES * B2_MAX_CODERS * B2_MAX_ALPHA));
   B2_TRY(w->d_cost.ensure(J * B2_N_TRIPLES)); B2_TRY(w->d_low.ensure(J * B2_N_TRIPLES));
@@ -287,7 +287,7 @@ int run_batch(b2_encoder *e, Workspace *w, const u8 *d_in, std::vector<B2Job> &j
   // group arena offsets need n (M <= n + 1)
   u32 gpos = 0, max_g = 1;
   std::vector<u32> ids(J), ns(J);
-  std::vector<B2SortTile> mtiles, msegs, msegs_big;
+  std::vector<B2SortTile> mtiles, msegs, msegs_mid, msegs_big;
   for (u32 j = 0; j < J; j++) {
     B2Job &b = w->batch_jobs[j];
     if (b.n > b.cap) B2_FAIL(B2_ERR_INTERNAL, "RLE1 output exceeds its slot");
@@ -298,7 +298,7 @@ int run_batch(b2_encoder *e, Workspace *w, const u8 *d_in, std::vector<B2Job> &j
     b.na = b.n;
     b.tile0 = (u32)mtiles.size();
     for (u32 s = 0; s < b.n; s += B2_MTF_TILE) mtiles.push_back(B2SortTile{j, s});
-    for (u32 s = 0; s < b.n; s += B2_MTF_SEG) (b.n_used <= 64 ? msegs : msegs_big).push_back(B2SortTile{j, s});
+    for (u32 s = 0; s < b.n; s += B2_MTF_SEG) (b.n_used <= 64 ? msegs : b.n_used <= 128 ? msegs_mid : msegs_big).push_back(B2SortTile{j, s});
     w->block_bytes += b.n;
   }
   w->blocks += J;
@@ -331,11 +331,12 @@ int run_batch(b2_encoder *e, Workspace *w, const u8 *d_in, std::vector<B2Job> &j
     StageTimer tm(e, st, w->ev, &w->stage_ms[3]);
     if (!mtiles.empty())
       B2_CUDA_CHECK(cudaMemcpyAsync(w->d_mtiles.p, mtiles.data(), mtiles.size() * sizeof(B2SortTile), cudaMemcpyHostToDevice, st));
-    const u32 n_small = (u32)msegs.size();
+    const u32 n_small = (u32)msegs.size(), n_mid = (u32)msegs_mid.size();
+    msegs.insert(msegs.end(), msegs_mid.begin(), msegs_mid.end());
     msegs.insert(msegs.end(), msegs_big.begin(), msegs_big.end());
     if (!msegs.empty())
       B2_CUDA_CHECK(cudaMemcpyAsync(w->d_msegs.p, msegs.data(), msegs.size() * sizeof(B2SortTile), cudaMemcpyHostToDevice, st));
-    B2_TRY(b2k_mtf(st, w->d_jobs.p, J, w->d_mtiles.p, (u32)mtiles.size(), w->d_msegs.p, n_small, (u32)msegs.size(), w->d_bwt.p, w->d_m16.p,
+    B2_TRY(b2k_mtf(st, w->d_jobs.p, J, w->d_mtiles.p, (u32)mtiles.size(), w->d_msegs.p, n_small, n_mid, (u32)msegs.size(), w->d_bwt.p, w->d_m16.p,
                    w->d_m256.p, w->d_tilemask.p, w->d_idx.p, w->d_mtf.p));
     w->launches += 4;
   }

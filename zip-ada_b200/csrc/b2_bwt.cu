@@ -176,19 +176,30 @@ k_scatter(const B2SortTileRR *__restrict__ tiles, const B2Job *__restrict__ jobs
     S.g_off[tid] = jobhist[((size_t)tl.job * ST_MAXPASS + (u32)(shift >> 3)) * 256 + tid];
     if (tl.prev != 0xFFFFFFFFu) v_early = lb_load(state + (size_t)tl.prev * 256 + tid);   // only trusted when final
   }
-  u64 key[SC_ITEMS];
-  u32 rk[SC_ITEMS];   // rank within (warp, digit) | digit << 16 ; 0xFFFFFFFF = invalid
   const u32 wbase = tl.start + w * SC_WCHUNK;
+  // The ranking only needs the digit: its byte is fetched on its own and the whole key is fetched later, next to
+  // the rotation index, when its place in the staged tile is known - that second read hits the L2.  (Holding
+  // eight 64-bit keys across the ranking made the compiler sink every load next to its use: exposed latency
+  // and spills under the 40-register budget of three resident CTAs.)  The state of the ranking is packed: the
+  // digits of the even rows in DA, of the odd rows in DB - so the first two rows already need all eight loads,
+  // which keeps them together at the top - a validity bit per row, and the rank of a row inside its (warp,
+  // digit), at most 255, as a byte of RK0 / RK1.
+  u32 DA = 0, DB = 0, vm = 0, RK0 = 0, RK1 = 0;
+  {
+    const u8 *kb = reinterpret_cast<const u8 *>(keys_in + off) + (shift >> 3);      // little endian: byte shift / 8 of the key
 #pragma unroll
-  for (int k = 0; k < SC_ITEMS; k++) {
-    u32 i = wbase + k * 32 + l;
-    key[k] = (i < n) ? keys_in[off + i] : 0;
+    for (int k = 0; k < SC_ITEMS; k++) {
+      const u32 i = wbase + k * 32 + l;
+      const bool valid = i < n;
+      const u32 dgk = valid ? (u32)kb[(size_t)i * 8] : 0u;
+      if (k & 1) DB |= dgk << (8 * (k >> 1)); else DA |= dgk << (8 * (k >> 1));
+      vm |= (valid ? 1u : 0u) << k;
+    }
   }
 #pragma unroll
   for (int k = 0; k < SC_ITEMS; k++) {
-    u32 i = wbase + k * 32 + l;
-    bool valid = i < n;
-    u32 d = (u32)(key[k] >> shift) & 255u;
+    const bool valid = (vm >> k) & 1u;
+    const u32 d = (((k & 1) ? DB : DA) >> (8 * (k >> 1))) & 255u;
     // lanes holding the same digit: eight ballots (one per digit bit) cost the same for every digit
     // distribution, whereas match.any slows down with the number of distinct digits in the warp
     u32 peers = __ballot_sync(0xffffffffu, valid);
@@ -198,12 +209,13 @@ k_scatter(const B2SortTileRR *__restrict__ tiles, const B2Job *__restrict__ jobs
       const u32 m = __ballot_sync(0xffffffffu, bit);
       peers &= bit ? m : ~m;
     }
-    u32 r = __popc(peers & lt_mask);
-    u32 base = valid ? S.warp_cnt[w][d] : 0;
+    const u32 r = __popc(peers & lt_mask);
+    const u32 base = valid ? S.warp_cnt[w][d] : 0;
     __syncwarp();
     if (valid && r == 0) S.warp_cnt[w][d] = base + __popc(peers);
     __syncwarp();
-    rk[k] = valid ? ((base + r) | (d << 16)) : 0xFFFFFFFFu;
+    const u32 rank8 = valid ? (base + r) : 0u;              // < 256: a warp holds 256 rows
+    if (k < 4) RK0 |= rank8 << (8 * k); else RK1 |= rank8 << (8 * (k - 4));
   }
   __syncthreads();
   // per digit: exclusive over warps, tile count
@@ -244,19 +256,21 @@ k_scatter(const B2SortTileRR *__restrict__ tiles, const B2Job *__restrict__ jobs
     }
   }
   __syncthreads();
-  // the rotation indices are only needed now: fetching them late keeps the register count low
-  // enough for six resident CTAs per SM, whose phases overlap
+  // keys and rotation indices are only needed now
+  u64 key[SC_ITEMS];
   u32 val[SC_ITEMS];
 #pragma unroll
   for (int k = 0; k < SC_ITEMS; k++) {
-    u32 i = wbase + k * 32 + l;
+    const u32 i = wbase + k * 32 + l;
+    key[k] = (i < n) ? keys_in[off + i] : 0;
     val[k] = (i < n) ? vals_in[off + i] : 0;
   }
 #pragma unroll
   for (int k = 0; k < SC_ITEMS; k++) {
-    if (rk[k] != 0xFFFFFFFFu) {
-      u32 d = rk[k] >> 16;
-      u32 lp = S.tile_start[d] + S.warp_cnt[w][d] + (rk[k] & 0xFFFFu);
+    if ((vm >> k) & 1u) {
+      const u32 d = (((k & 1) ? DB : DA) >> (8 * (k >> 1))) & 255u;
+      const u32 rank8 = ((k < 4 ? RK0 : RK1) >> (8 * (k & 3))) & 255u;
+      const u32 lp = S.tile_start[d] + S.warp_cnt[w][d] + rank8;
       S.keys[lp] = key[k];
       S.vals[lp] = val[k];
     }

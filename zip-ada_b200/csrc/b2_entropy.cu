@@ -196,6 +196,8 @@ struct EntArgs {
   u32 *leaves;                          // interleaved: [(slot / 32)][HSTRIDE][slot % 32], slot = place in the work list
   u32 *wl, *wl_count;                   // work list of this round: q = p * 6 + coder of every coder to (re)build
   u32 *wl_off;                          // [p] first slot of problem p in the work list (k_ent_wl_scan)
+  u32 *chg;                             // [p] bit c: the histogram of coder c changed in this round (bit 31: first round, all coders)
+  u32 *pl, *pl_count;                   // unfinished problems of this round, in (block, triple) order: the sweeps run over this list
   u8 *lens;                             // [p][6][B2_MAX_ALPHA]
   u32 *stat;                            // [p][2]: defectors of the last sweep, finished flag
   u32 *selcost;                         // [p]
@@ -248,6 +250,7 @@ k_ent_init(EntArgs a) {
     const bool always = (b2_choice_mask(a.level, job.n_mtf) >> ec) & 1u;
     a.stat[2 * p] = 1;
     a.stat[2 * p + 1] = always ? 0u : 2u;        // 0 running, 1 finished, 2 not scheduled (gated)
+    a.chg[p] = 0x80000000u;
   }
 }
 
@@ -255,12 +258,12 @@ k_ent_init(EntArgs a) {
 // the list then belong to the same block and share its alphabet size, which the 32 lock-step sorts of a
 // warp need (k_ent_qsort), and finished problems cost nothing.
 #define WL_TILE 2048
-__device__ __forceinline__ u32 wl_items(const EntArgs &a, u32 p) {       // coders problem p adds to the work list
+// coders problem p adds to the work list (low 16 bits) and 1 << 16 if the problem is unfinished: both lists
+// come out of the same scan (a tile of 2048 problems adds at most 12 288 coders)
+__device__ __forceinline__ u32 wl_items(const EntArgs &a, u32 p) {
   const int t = (int)(p % B2_N_TRIPLES);
   if (p >= a.n_jobs * B2_N_TRIPLES || t >= a.n_triples || a.stat[2 * p + 1] != 0) return 0;
-  int ml, sw, ec;
-  b2_triple(a.level, t, ml, sw, ec);
-  return (u32)ec;
+  return (u32)__popc(a.chg[p] & 63u) | 0x10000u;
 }
 __global__ void __launch_bounds__(1024)
 k_ent_wl_sum(EntArgs a, u32 *tile_sum) {
@@ -268,38 +271,39 @@ k_ent_wl_sum(EntArgs a, u32 *tile_sum) {
   const u32 p = blockIdx.x * WL_TILE + 2 * threadIdx.x;
   u32 total;
   block_excl_add(wl_items(a, p) + wl_items(a, p + 1), sm, &total);
-  if (threadIdx.x == 0) tile_sum[blockIdx.x] = total;
+  if (threadIdx.x == 0) { tile_sum[2 * blockIdx.x] = total & 0xFFFFu; tile_sum[2 * blockIdx.x + 1] = total >> 16; }
 }
 __global__ void __launch_bounds__(1024)
 k_ent_wl_scan(EntArgs a, const u32 *tile_sum) {
   __shared__ u32 sm[40];
-  u32 before = 0;
-  for (u32 b = threadIdx.x; b < blockIdx.x; b += 1024) before += tile_sum[b];
-  u32 base;
-  block_excl_add(before, sm, &base);
+  u32 before_c = 0, before_p = 0;
+  for (u32 b = threadIdx.x; b < blockIdx.x; b += 1024) { before_c += tile_sum[2 * b]; before_p += tile_sum[2 * b + 1]; }
+  u32 base_c, base_p;
+  block_excl_add(before_c, sm, &base_c);
+  __syncthreads();
+  block_excl_add(before_p, sm, &base_p);
   __syncthreads();
   const u32 P = a.n_jobs * B2_N_TRIPLES;
   const u32 p = blockIdx.x * WL_TILE + 2 * threadIdx.x;
   const u32 c0 = wl_items(a, p), c1 = wl_items(a, p + 1);
   u32 total;
   const u32 ex = block_excl_add(c0 + c1, sm, &total);
-  if (p < P) a.wl_off[p] = base + ex;
-  if (p + 1 < P) a.wl_off[p + 1] = base + ex + c0;
-  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *a.wl_count = base + total;
+  if (p < P) { a.wl_off[p] = base_c + (ex & 0xFFFFu); if (c0 >> 16) a.pl[base_p + (ex >> 16)] = p; }
+  if (p + 1 < P) { a.wl_off[p + 1] = base_c + ((ex + c0) & 0xFFFFu); if (c1 >> 16) a.pl[base_p + ((ex + c0) >> 16)] = p + 1; }
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) { *a.wl_count = base_c + (total & 0xFFFFu); *a.pl_count = base_p + (total >> 16); }
 }
 
 // Define_Descriptors, first half (:643-652) + Avoid_Zeros (:439-462)
 __global__ void __launch_bounds__(256)
 k_ent_hist(EntArgs a) {
   __shared__ u32 h[B2_MAX_CODERS][HSTRIDE];
+  __shared__ u32 changed;
   const int t = blockIdx.x;
   const u32 jb = blockIdx.y;
   const u32 p = jb * B2_N_TRIPLES + t;
   if (a.stat[2 * p + 1]) return;
   const B2Job &job = a.jobs[jb];
-  const u32 M = job.n_mtf, G = job.n_groups;
-  const int A = (int)job.n_used + 2;
-  const u16 *m = a.mtf + job.mtf_off;
+  const u32 G = job.n_groups;
   int max_len, sw, ec;
   b2_triple(a.level, t, max_len, sw, ec);
   const u8 *sel = a.sel + (size_t)t * a.total_groups + job.grp_off;
@@ -307,9 +311,11 @@ k_ent_hist(EntArgs a) {
   u32 *hg = a.hist + (size_t)p * (B2_MAX_CODERS * HSTRIDE);
   const u32 tid = threadIdx.x;
   for (u32 i = tid; i < (u32)ec * HSTRIDE; i += 256) (&h[0][0])[i] = hg[i];
+  if (tid == 0) changed = 0;
   __syncthreads();
   const u16 *gh = a.ghist + job.mtf_off;
   const u8 *gd = a.gdist + job.grp_off;
+  u32 mych = 0;
   for (u32 g = tid; g < G; g += 256) {
     const u32 c = sel[g], o = selprev[g];
     if (c == o) continue;
@@ -320,26 +326,41 @@ k_ent_hist(EntArgs a) {
       atomicAdd(&h[c - 1][sym], cn);
       if (o) atomicSub(&h[o - 1][sym], cn);
     }
+    mych |= (1u << (c - 1)) | (o ? (1u << (o - 1)) : 0u);
     selprev[g] = (u8)c;
   }
+  mych = __reduce_or_sync(0xffffffffu, mych);
+  if (lane_id() == 0 && mych) atomicOr(&changed, mych);
   __syncthreads();
   for (u32 i = tid; i < (u32)ec * HSTRIDE; i += 256) hg[i] = (&h[0][0])[i];
-  // the coders of this problem join the round's work list (compact: finished problems cost nothing)
-  const u32 slot0 = a.wl_off[p];
+  // Coders whose histogram did not change keep their code lengths (Define_Descriptors is a function of the
+  // histogram, :495-513): only the others join the round's work list.  The first round builds all of them.
+  if (tid == 0) a.chg[p] = (a.chg[p] & 0x80000000u) ? ((1u << ec) - 1u) : changed;
+}
+
+// Avoid_Zeros (:439-462) and the leaves, in alphabet order (:230-235), of every coder on the work list
+__global__ void __launch_bounds__(256)
+k_ent_leaves(EntArgs a) {
+  const int t = blockIdx.x;
+  const u32 jb = blockIdx.y;
+  const u32 p = jb * B2_N_TRIPLES + t;
+  if (a.stat[2 * p + 1]) return;
+  const u32 mask = a.chg[p] & 63u;
   const u32 w = warp_id(), l = lane_id();
-  if ((int)w < ec) {
-    u32 zeroes = 0;
-    for (int s = l; s < A; s += 32) zeroes += (h[w][s] == 0);
+  if (!((mask >> w) & 1u)) return;
+  const int A = (int)a.jobs[jb].n_used + 2;
+  const u32 *h = a.hist + (size_t)p * (B2_MAX_CODERS * HSTRIDE) + (size_t)w * HSTRIDE;
+  const u32 slot = a.wl_off[p] + __popc(mask & ((1u << w) - 1u));
+  u32 zeroes = 0;
+  for (int s = l; s < A; s += 32) zeroes += (h[s] == 0);
 #pragma unroll
-    for (int o = 16; o; o >>= 1) zeroes += __shfl_xor_sync(0xffffffffu, zeroes, o);
-    const u32 slot = slot0 + w;
-    if (l == 0) a.wl[slot] = p * B2_MAX_CODERS + w;
-    for (int s = l; s < A; s += 32) {
-      u32 v = h[w][s];
-      if (zeroes > 0 && zeroes <= 100) v = max(1u, v);
-      else if (zeroes > 100) v = (v == 0) ? 1u : v * 2u;
-      a.leaves[leaf_index(slot, (u32)s)] = (v << 9) | (u32)s;   // alphabet order (:230-235); every count is > 0 here
-    }
+  for (int o = 16; o; o >>= 1) zeroes += __shfl_xor_sync(0xffffffffu, zeroes, o);
+  if (l == 0) a.wl[slot] = p * B2_MAX_CODERS + w;
+  for (int s = l; s < A; s += 32) {
+    u32 v = h[s];
+    if (zeroes > 0 && zeroes <= 100) v = max(1u, v);
+    else if (zeroes > 100) v = (v == 0) ? 1u : v * 2u;
+    a.leaves[leaf_index(slot, (u32)s)] = (v << 9) | (u32)s;     // every count is > 0 here
   }
 }
 
@@ -593,18 +614,22 @@ k_ent_cost(EntArgs a) {
 }
 
 // Simulate_Entropy_Coding_Variants_and_Reclassify (:661-753): serial through the selector MTF list.
-// One warp per block; lane t runs the sweep of triple t.
+// One lane per unfinished (block, triple): 32 neighbours of the round's problem list per warp (they mostly
+// belong to the same block, hence the same number of groups).
 __global__ void __launch_bounds__(32)
 k_ent_sweep(EntArgs a) {
-  const u32 jb = blockIdx.x;
-  const u32 t = threadIdx.x;
+  const u32 slot = blockIdx.x * 32 + threadIdx.x;
+  const u32 count = *a.pl_count;
+  if (blockIdx.x * 32 >= count) return;
+  const bool active = slot < count;
+  const u32 p = a.pl[active ? slot : blockIdx.x * 32];
+  const u32 jb = p / B2_N_TRIPLES, t = p % B2_N_TRIPLES;
   const B2Job &job = a.jobs[jb];
-  const u32 G = job.n_groups;
-  const u32 p = jb * B2_N_TRIPLES + t;
-  const bool active = (int)t < a.n_triples && !a.stat[2 * p + 1];
+  const u32 G = active ? job.n_groups : 0u;
+  const u32 Gmax = __reduce_max_sync(0xffffffffu, G);
   int max_len, sw, ec;
-  b2_triple(a.level, (int)(t < (u32)a.n_triples ? t : 0), max_len, sw, ec);
-  const size_t base = (size_t)(active ? t : 0) * a.total_groups + job.grp_off;
+  b2_triple(a.level, (int)t, max_len, sw, ec);
+  const size_t base = (size_t)t * a.total_groups + job.grp_off;
   const u32 *gc = a.gpack + base;
   u8 *sel = a.sel + base;
   u32 posv = 0;                       // place of coder cl in field cl; coders beyond ec sit at place 7
@@ -618,7 +643,7 @@ k_ent_sweep(EntArgs a) {
 #pragma unroll
     for (int k = 0; k < 16; k++) nx[k] = 0;
     ns[0] = ns[1] = ns[2] = ns[3] = 0;
-    if (active && g0 < G) {
+    if (g0 < G) {
 #pragma unroll
       for (int k = 0; k < 4; k++) {
         const uint4 x = *reinterpret_cast<const uint4 *>(gc + g0 + 4 * k);
@@ -630,7 +655,7 @@ k_ent_sweep(EntArgs a) {
     }
   };
   load16g(0);
-  for (u32 g0 = 0; g0 < G; g0 += 16) {
+  for (u32 g0 = 0; g0 < Gmax; g0 += 16) {
     u32 c16[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) c16[k] = nx[k];
@@ -651,7 +676,7 @@ k_ent_sweep(EntArgs a) {
         const u32 m3 = __vminu4(ev, od);
         const u32 key = min(min(m3 & 255u, (m3 >> 8) & 255u), (m3 >> 16) & 255u);
         const u32 best0 = key & 7u;
-        if (active && best0 + 1 != clk) { def++; sel[g0 + k] = (u8)(best0 + 1); }
+        if (best0 + 1 != clk) { def++; sel[g0 + k] = (u8)(best0 + 1); }
         // move to front (:707-717): places below the chosen one move down by one, the chosen one becomes 1
         const u32 pl = (posv >> (4 * best0)) & 15u;
         posv += (~(posv + (8u - pl) * 0x111111u) & 0x888888u) >> 3;
@@ -818,21 +843,24 @@ int b2k_entropy(cudaStream_t st, B2Job *d_jobs, u32 n_jobs, u32 max_groups_per_j
   k_rank_sort<<<n_jobs * 2, 32, sort_smem, st>>>(d_jobs, d_rank3, d_rank4);
   EntArgs a;
   a.jobs = d_jobs; a.mtf = d_mtf; a.ghist = d_ghist; a.gdist = d_gdist; a.rank3 = d_rank3; a.rank4 = d_rank4; a.sel = d_sel; a.selprev = d_selprev;
-  a.gpack = d_gpack; a.gselcost = d_gselcost; a.hist = d_hist; a.leaves = d_leaves; a.wl = d_wl; a.wl_count = d_activated + 1; a.wl_off = d_wl + (size_t)n_jobs * B2_N_TRIPLES * B2_MAX_CODERS + 32; a.lens = d_lens; a.stat = d_stat; a.selcost = d_selcost;
+  a.gpack = d_gpack; a.gselcost = d_gselcost; a.hist = d_hist; a.leaves = d_leaves; a.wl = d_wl; a.wl_count = d_activated + 1; a.pl_count = d_activated + 2; a.wl_off = d_wl + (size_t)n_jobs * B2_N_TRIPLES * B2_MAX_CODERS + 32;
+  a.chg = a.wl_off + (size_t)n_jobs * B2_N_TRIPLES + 32; a.pl = a.chg + (size_t)n_jobs * B2_N_TRIPLES + 32; a.lens = d_lens; a.stat = d_stat; a.selcost = d_selcost;
   a.cost_all = d_cost; a.low_all = d_low; a.total_groups = total_groups; a.level = level; a.n_triples = n_triples;
   a.n_jobs = n_jobs;
   const dim3 grid(n_triples, n_jobs);
   const u32 nq = n_jobs * B2_N_TRIPLES * B2_MAX_CODERS;
   const u32 wl_tiles = (n_jobs * B2_N_TRIPLES + WL_TILE - 1) / WL_TILE;
-  u32 *wl_tile_sum = a.wl_off + (size_t)n_jobs * B2_N_TRIPLES + 32;
+  u32 *wl_tile_sum = a.pl + (size_t)n_jobs * B2_N_TRIPLES + 32;
+  const u32 np = n_jobs * B2_N_TRIPLES;
   k_ent_init<<<grid, 256, 0, st>>>(a);
   *launches += 4;
   for (int phase = 0; phase < 4; phase++) {
     for (int it = 0; it <= 10; it++) {
       // iterations 1..10 (:793-802); round 10 is the extra Define_Descriptors for triples still moving (:803-807)
+      k_ent_hist<<<grid, 256, 0, st>>>(a);
       k_ent_wl_sum<<<wl_tiles, 1024, 0, st>>>(a, wl_tile_sum);
       k_ent_wl_scan<<<wl_tiles, 1024, 0, st>>>(a, wl_tile_sum);
-      k_ent_hist<<<grid, 256, 0, st>>>(a);
+      k_ent_leaves<<<grid, 256, 0, st>>>(a);
       if (max_alpha > QS_SMALL) {             // small alphabets keep their high occupancy next to large ones
         k_ent_qsort<<<(nq + 31) / 32, 32, ((size_t)QS_SMALL + 16) * 32 * 4, st>>>(a, nq, QS_SMALL, 0, QS_SMALL);
         k_ent_qsort<<<(nq + 31) / 32, 32, qs_smem, st>>>(a, nq, max_alpha, QS_SMALL, HSTRIDE);
@@ -842,8 +870,8 @@ int b2k_entropy(cudaStream_t st, B2Job *d_jobs, u32 n_jobs, u32 max_groups_per_j
       }
       k_ent_pm<<<(nq + PM_WARPS - 1) / PM_WARPS, 32 * PM_WARPS, 0, st>>>(a, nq);
       k_ent_cost<<<grid, 256, 0, st>>>(a);
-      *launches += 6;
-      if (it < 10) { k_ent_sweep<<<n_jobs, 32, 0, st>>>(a); *launches += 1; }
+      *launches += 7;
+      if (it < 10) { k_ent_sweep<<<(np + 31) / 32, 32, 0, st>>>(a); *launches += 1; }
     }
     k_ent_selcost<<<n_jobs, 32, 0, st>>>(a);
     k_ent_final<<<grid, 256, 0, st>>>(a);

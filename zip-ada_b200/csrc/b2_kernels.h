@@ -80,7 +80,7 @@ int b2k_bwt_batch(B2SortCtx *cx, cudaStream_t st, B2Job *d_jobs, const std::vect
 #define B2_SORT_TILE 2048
 #define B2_MTF_SEG 32768
 int b2k_mtf(cudaStream_t st, B2Job *d_jobs, u32 n_jobs, const B2SortTile *d_tiles, u32 n_tiles,
-            const B2SortTile *d_segs, u32 n_segs_small, u32 n_segs, const u8 *d_bwt, u32 *d_m16, u32 *d_m256,
+            const B2SortTile *d_segs, u32 n_segs_small, u32 n_segs_mid, u32 n_segs, const u8 *d_bwt, u32 *d_m16, u32 *d_m256,
             u32 *d_tilemask, u8 *d_idx, u16 *d_mtf);
 // b2_entropy.cu
 int b2k_entropy(cudaStream_t st, B2Job *d_jobs, u32 n_jobs, u32 max_groups_per_job, u32 total_groups,

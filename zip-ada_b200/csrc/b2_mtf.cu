@@ -246,25 +246,30 @@ k_mtf_seq(const B2SortTile *__restrict__ segs, u32 n_segs, const B2Job *__restri
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_mtf_seq8: the same for blocks with at most 64 distinct bytes (text).  The list then fits the
-// registers of 8 lanes, so one warp advances FOUR segments at a time, one per group of 8 lanes.
+// k_mtf_seqg<LG>: the same for blocks with at most 8 * LG distinct bytes (LG = 8: plain text, LG = 16: text
+// with capitals, digits and punctuation).  The list then fits the registers of LG lanes, so one warp advances
+// 32 / LG segments at a time, one per group of LG lanes.
 // ---------------------------------------------------------------------------------------------
+template <int LG>
 __global__ void __launch_bounds__(32 * MS_WARPS)
-k_mtf_seq8(const B2SortTile *__restrict__ segs, u32 n_segs, const B2Job *__restrict__ jobs, const u8 *__restrict__ bwt,
+k_mtf_seqg(const B2SortTile *__restrict__ segs, u32 n_segs, const B2Job *__restrict__ jobs, const u8 *__restrict__ bwt,
            const u32 *__restrict__ m16, const u32 *__restrict__ m256, u8 *__restrict__ idx_out) {
   // Per unit: the list at the segment start (bytes in list order), the dense code of every byte (its
   // rank among the bytes in use) and, from both, the PLACE of every code in the list.  Phase 2 keeps the
   // places, not the list: lane g of a group holds the places of codes 8g .. 8g+7 as bytes of two
   // registers.  A byte b with place r is coded as r; then every place below r moves up by one (a per-byte
   // compare and add on the packed registers) and b's place becomes 0.  No list shifting, no search.
-  __shared__ u8 lists[MS_WARPS][4][256];
-  __shared__ u8 ctab[MS_WARPS][4][256];
-  __shared__ __align__(8) u8 place0[MS_WARPS][4][64];
-  const u32 l = lane_id(), gl = l & 7u, grp = l >> 3;
-  const u32 unit0 = (blockIdx.x * MS_WARPS + warp_id()) * 4;
+  constexpr int NU = 32 / LG;                      // units (segments) per warp
+  constexpr int PPL = 32 / LG;                     // positions per lane and step (32 positions per group and step)
+  constexpr u32 CMASK = 8 * LG - 1;
+  __shared__ u8 lists[MS_WARPS][NU][256];
+  __shared__ u8 ctab[MS_WARPS][NU][256];
+  __shared__ __align__(8) u8 place0[MS_WARPS][NU][8 * LG];
+  const u32 l = lane_id(), gl = l & (LG - 1), grp = l / LG;
+  const u32 unit0 = (blockIdx.x * MS_WARPS + warp_id()) * NU;
   if (unit0 >= n_segs) return;
   // phase 1, one unit after the other with the whole warp
-  for (u32 u = 0; u < 4; u++) {
+  for (u32 u = 0; u < (u32)NU; u++) {
     if (unit0 + u < n_segs) {
       const B2SortTile sg = segs[unit0 + u];
       const B2Job &job = jobs[sg.job];
@@ -277,13 +282,13 @@ k_mtf_seq8(const B2SortTile *__restrict__ segs, u32 n_segs, const B2Job *__restr
         ct[32 * q + l] = (u8)(pre + __popc(wv & ((1u << l) - 1u)));
         pre += __popc(wv);
       }
-      pl[l] = 255; pl[32 + l] = 255;                 // codes not in use never move
+      for (u32 i = l; i < 8 * LG; i += 32) pl[i] = 255;   // codes not in use never move
       __syncwarp();
       for (u32 pos = l; pos < job.n_used; pos += 32) pl[ct[lst[pos]]] = (u8)pos;
     }
   }
   __syncwarp();
-  // phase 2, four units side by side
+  // phase 2, NU units side by side
   const bool have = unit0 + grp < n_segs;
   const B2SortTile sg = segs[have ? unit0 + grp : unit0];
   const B2Job &job = jobs[sg.job];
@@ -293,43 +298,44 @@ k_mtf_seq8(const B2SortTile *__restrict__ segs, u32 n_segs, const B2Job *__restr
   const u32 p0 = sg.start, p1 = have ? min(n, sg.start + B2_MTF_SEG) : sg.start;
   u32 R0 = *reinterpret_cast<const u32 *>(place0[warp_id()][have ? grp : 0] + 8 * gl);
   u32 R1 = *reinterpret_cast<const u32 *>(place0[warp_id()][have ? grp : 0] + 8 * gl + 4);
-  const u32 gbase = grp << 3;                      // first lane of my group
+  const u32 gbase = grp * LG;                      // first lane of my group
   u32 prevb = (have && p0 > 0) ? d[p0 - 1] : 256u;
   const u32 nb = (B2_MTF_SEG / 32);
   for (u32 it = 0; it < nb; it++) {
     const u32 b0 = p0 + it * 32;
     if (!__any_sync(0xffffffffu, b0 < p1)) break;
-    const u32 pi = b0 + 4 * gl;                    // my four positions
-    const u32 word = (b0 < p1) ? *reinterpret_cast<const u32 *>(d + pi) : 0u;   // slots are 256-aligned and padded
-    const u32 cword = (u32)ct[word & 255u] | ((u32)ct[(word >> 8) & 255u] << 8) | ((u32)ct[(word >> 16) & 255u] << 16) |
-                      ((u32)ct[word >> 24] << 24);  // the codes of my four bytes
+    const u32 pi = b0 + PPL * gl;                  // my positions
+    u32 word = 0;                                  // slots are 256-aligned and padded
+    if (b0 < p1) word = PPL == 4 ? *reinterpret_cast<const u32 *>(d + pi) : (u32)*reinterpret_cast<const u16 *>(d + pi);
+    u32 cword = 0;                                 // the codes of my bytes
+#pragma unroll
+    for (int j = 0; j < PPL; j++) cword |= (u32)ct[(word >> (8 * j)) & 255u] << (8 * j);
     // bits of my positions whose byte differs from the byte before it
-    u32 before = __shfl_up_sync(0xffffffffu, word >> 24, 1, 8);
+    u32 before = __shfl_up_sync(0xffffffffu, (word >> (8 * (PPL - 1))) & 255u, 1, LG);
     if (gl == 0) before = prevb;
     const u32 shifted = (word << 8) | (before & 255u);
     u32 nib = 0;
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
+    for (int j = 0; j < PPL; j++) {
       const bool differs = ((word >> (8 * j)) & 255u) != ((shifted >> (8 * j)) & 255u) || (j == 0 && gl == 0 && before > 255u);
       if (differs && pi + j < p1) nib |= 1u << j;
     }
-    u32 todo = nib << (4 * gl);
-    todo |= __shfl_xor_sync(0xffffffffu, todo, 1);
-    todo |= __shfl_xor_sync(0xffffffffu, todo, 2);
-    todo |= __shfl_xor_sync(0xffffffffu, todo, 4);
+    u32 todo = nib << (PPL * gl);
+#pragma unroll
+    for (int o = 1; o < LG; o <<= 1) todo |= __shfl_xor_sync(0xffffffffu, todo, o);
     {
       // (warp-wide shuffle: executed by every lane, also by groups that have run out of work)
       const u32 lastpos = (b0 < p1) ? min(31u, p1 - b0 - 1) : 0u;
-      const u32 lw = __shfl_sync(0xffffffffu, word, gbase + (lastpos >> 2));
-      if (b0 < p1) prevb = (lw >> (8 * (lastpos & 3))) & 255u;
+      const u32 lw = __shfl_sync(0xffffffffu, word, gbase + lastpos / PPL);
+      if (b0 < p1) prevb = (lw >> (8 * (lastpos % PPL))) & 255u;
     }
-    u32 myidx4 = 0;
+    u32 myidx = 0;
     while (__any_sync(0xffffffffu, todo != 0)) {
       const bool act = todo != 0;
       const u32 k = act ? (u32)(__ffs(todo) - 1) : 0u;
       todo &= todo - 1;
-      const u32 ck = __shfl_sync(0xffffffffu, cword, gbase + (k >> 2));
-      const u32 c = (ck >> (8 * (k & 3))) & 63u;                 // code of the byte at position k (< 64 here)
+      const u32 ck = __shfl_sync(0xffffffffu, cword, gbase + k / PPL);
+      const u32 c = (ck >> (8 * (k % PPL))) & CMASK;             // code of the byte at position k (< 8 * LG here)
       const u32 sh = 8 * (c & 3u);
       const u32 mine = (((c & 4u) ? R1 : R0) >> sh) & 255u;      // its place, if I am the lane that holds it
       const u32 r = __shfl_sync(0xffffffffu, mine, gbase + (c >> 3));
@@ -338,12 +344,13 @@ k_mtf_seq8(const B2SortTile *__restrict__ segs, u32 n_segs, const B2Job *__restr
         R0 += __vcmpltu4(R0, m) & 0x01010101u;                   // places below r move up
         R1 += __vcmpltu4(R1, m) & 0x01010101u;
         if (gl == (c >> 3)) { if (c & 4u) R1 &= ~(0xFFu << sh); else R0 &= ~(0xFFu << sh); }   // the byte goes to the front
-        if (gl == (k >> 2)) myidx4 |= r << (8 * (k & 3));
+        if (gl == k / PPL) myidx |= r << (8 * (k % PPL));
       }
     }
     if (b0 < p1) {
-      // four index bytes per lane; positions beyond p1 inside the last word are never read
-      *reinterpret_cast<u32 *>(idx_out + off + pi) = myidx4;
+      // PPL index bytes per lane; positions beyond p1 inside the last word are never read
+      if (PPL == 4) *reinterpret_cast<u32 *>(idx_out + off + pi) = myidx;
+      else *reinterpret_cast<u16 *>(idx_out + off + pi) = (u16)myidx;
     }
   }
 }
@@ -423,15 +430,19 @@ k_rle2(B2Job *jobs, const u8 *__restrict__ idx_in, u16 *__restrict__ mtf) {
 }
 
 int b2k_mtf(cudaStream_t st, B2Job *d_jobs, u32 n_jobs, const B2SortTile *d_tiles, u32 n_tiles,
-            const B2SortTile *d_segs, u32 n_segs_small, u32 n_segs, const u8 *d_bwt, u32 *d_m16, u32 *d_m256,
+            const B2SortTile *d_segs, u32 n_segs_small, u32 n_segs_mid, u32 n_segs, const u8 *d_bwt, u32 *d_m16, u32 *d_m256,
             u32 *d_tilemask, u8 *d_idx, u16 *d_mtf) {
-  // d_segs[0 .. n_segs_small) belong to blocks with <= 64 distinct bytes, the rest to the others
+  // d_segs[0 .. n_segs_small) belong to blocks with <= 64 distinct bytes, the next n_segs_mid to blocks with
+  // <= 128, the rest to the others
   if (n_tiles) {
     k_mtf_masks<<<n_tiles, MI_THREADS, 0, st>>>(d_tiles, d_jobs, d_bwt, d_m16, d_m256, d_tilemask);
     if (n_segs_small)
-      k_mtf_seq8<<<(n_segs_small + 4 * MS_WARPS - 1) / (4 * MS_WARPS), 32 * MS_WARPS, 0, st>>>(d_segs, n_segs_small, d_jobs, d_bwt, d_m16, d_m256, d_idx);
-    if (n_segs > n_segs_small)
-      k_mtf_seq<<<(n_segs - n_segs_small + MS_WARPS - 1) / MS_WARPS, 32 * MS_WARPS, 0, st>>>(d_segs + n_segs_small, n_segs - n_segs_small, d_jobs, d_bwt, d_m16, d_m256, d_idx);
+      k_mtf_seqg<8><<<(n_segs_small + 4 * MS_WARPS - 1) / (4 * MS_WARPS), 32 * MS_WARPS, 0, st>>>(d_segs, n_segs_small, d_jobs, d_bwt, d_m16, d_m256, d_idx);
+    if (n_segs_mid)
+      k_mtf_seqg<16><<<(n_segs_mid + 2 * MS_WARPS - 1) / (2 * MS_WARPS), 32 * MS_WARPS, 0, st>>>(d_segs + n_segs_small, n_segs_mid, d_jobs, d_bwt, d_m16, d_m256, d_idx);
+    const u32 rest = n_segs - n_segs_small - n_segs_mid;
+    if (rest)
+      k_mtf_seq<<<(rest + MS_WARPS - 1) / MS_WARPS, 32 * MS_WARPS, 0, st>>>(d_segs + n_segs_small + n_segs_mid, rest, d_jobs, d_bwt, d_m16, d_m256, d_idx);
   }
   if (n_jobs) k_rle2<<<n_jobs, R2_THREADS, 0, st>>>(d_jobs, d_idx, d_mtf);
   B2_CUDA_CHECK(cudaGetLastError());
