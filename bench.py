@@ -305,6 +305,8 @@ def main():
     torch.cuda.synchronize()
     comm = sharding.TorchComm(dist, rank, world, dev) if world > 1 else None
 
+    phases = []
+
     def step(device_resident):
         """One Encode of the whole stream; returns this rank's piece (byte offset, length) and the stream length."""
         if world == 1:
@@ -315,6 +317,7 @@ def main():
             return 0, ln, ln
         r = sharding.encode_sharded(enc, comm, d_in.data_ptr() if device_resident else h_in.data_ptr(), device_resident, n, n, bounds, span,
                                     d_out.data_ptr() if device_resident else h_out.data_ptr(), device_resident, cap)
+        phases.append(r["phases_ms"])
         return r["byte_offset"], r["length"], r["total_length"]
 
     # ---- device-resident ("value") -------------------------------------------------------------------------
@@ -335,6 +338,14 @@ def main():
     t_dev = maxrank(st.call_ms / 1000.0)
     value = n * args.steps / 1e6 / t_wall
     dev_piece = d_out[:piece[1]].cpu().numpy().copy()
+    shard_phases = None
+    if world > 1:
+        mine = phases[-1]
+        keys = sorted(mine)
+        t = torch.tensor([mine[k] for k in keys], dtype=torch.float64, device=dev)
+        allp = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allp, t)
+        shard_phases = {k: [round(float(a[i]), 1) for a in allp] for i, k in enumerate(keys)}
     # ---- end to end through the C ABI with host buffers ----------------------------------------------------
     e_piece = step(False)
     barrier()
@@ -390,6 +401,20 @@ def main():
     parity = {"device_path_equals_host_path": same_paths, "output_sha256": sha, "golden_key": gkey,
               "golden_sha256": g["sha256"] if g else None,
               "timed_output_equals_oracle_golden": (bool(g["sha256"] == sha and g["bytes"] == int(total_len)) if g else None)}
+    # the same stream decoded on the device (b2_verify_stream: every block at once, block and stream CRCs, and at
+    # N = 1 the bytes against the input)
+    try:
+        if world == 1:
+            vr = enc.verify_ptr(d_out.data_ptr(), True, int(total_len), d_in.data_ptr(), True, n)
+        else:
+            d_stream = torch.from_numpy(stream).to(dev)
+            vr = enc.verify_ptr(d_stream.data_ptr(), True, int(total_len))
+            del d_stream
+        parity["device_verify"] = {"ok": bool(vr.ok), "blocks": int(vr.blocks), "decoded_bytes": int(vr.decoded_bytes), "ms": round(vr.ms, 1),
+                                   "compared_with_input": world == 1, "stream_crc": "%08x" % vr.stored_stream_crc,
+                                   "decode_MBps": round(vr.decoded_bytes / 1e6 / max(1e-9, vr.ms / 1000.0), 1)}
+    except Exception as ex:
+        parity["device_verify"] = {"ok": False, "error": str(ex)}
     decode_thread = None
     if not args.no_decode and n <= 2 * GiB:
         def decode():
@@ -457,6 +482,8 @@ def main():
             "parity": parity}
     if stage_ms:
         line["stage_ms"] = stage_ms
+    if shard_phases:
+        line["shard_phases_ms_per_rank"] = shard_phases
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -178,6 +178,29 @@ B2_API int b2_zip_create(b2_encoder *enc, uint32_t n_entries, const uint8_t *in,
 /* Zip CRC-32 of a host buffer, computed on the device (zip-crc_crypto.adb:31-61: Init, Update, Final). */
 B2_API int b2_zip_crc32(b2_encoder *enc, const uint8_t *in, uint64_t n, uint32_t *crc);
 
+/* ---- Decode / verify on the device ---------------------------------------------------
+ * The reference decodes a method-12 entry with BZip2.Decoding.Decompress (bzip2-decoding.adb:34-640, hooked at
+ * unzip-decompress.adb:1898-1915), one block after the other, checking every block CRC and the combined CRC.
+ * b2_verify_stream decodes ALL blocks of a stream at the same time (the block starts are found by their 48-bit
+ * magic at any bit offset and validated by following the chain of block ends), checks the same CRCs and,
+ * when `expect` is given, compares the decoded bytes with it.  Accepts any BZip2 stream without randomised
+ * blocks (e.g. libbz2's), not only this encoder's. */
+typedef struct b2_verify_result {
+  uint64_t blocks;               /* blocks decoded on the chain from the header to the footer */
+  uint64_t decoded_bytes;
+  uint64_t mismatch_at;          /* first decoded byte that differs from `expect` (or a length difference); ~0 = none */
+  uint64_t candidates;           /* occurrences of the block / footer magics in the stream (>= blocks + 1) */
+  uint32_t level;                /* '1'..'9' of the stream header */
+  uint32_t stored_stream_crc, computed_stream_crc;
+  int32_t ok;                    /* 1: header, every block CRC, the combined CRC, the end of the stream and `expect` all agree */
+  int32_t first_bad_block;       /* index of the first block that failed, -1 = none */
+  uint32_t first_bad_status;     /* 1 bad header; 2 randomised block; 3-13 malformed block; 20 no block where one must start;
+                                    21 bytes behind the footer; 22 no footer; 30 block CRC mismatch */
+  double ms;                     /* CUDA-event time of the call */
+} b2_verify_result;
+B2_API int b2_verify_stream(b2_encoder *enc, const uint8_t *stream, int stream_is_device, uint64_t n,
+                            const uint8_t *expect, int expect_is_device, uint64_t expect_n, b2_verify_result *result);
+
 /* Feedback and abort (zip.ads:301-306 Feedback_Proc; zip-compress-bzip2_e.adb:78-96 fires it from Read_Byte and
  * raises User_abort).  The batched calls read no bytes through callbacks, so the hook moves here: `fn` is called
  * on the CALLING thread (never from a library thread) after every device batch of b2_encode_stream* /

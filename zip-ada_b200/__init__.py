@@ -40,6 +40,12 @@ class BlockInfo(C.Structure):
                  "sample_width", "cost", "pad")] + [("bits", C.c_uint64)]
 
 
+class VerifyResult(C.Structure):
+    _fields_ = [("blocks", C.c_uint64), ("decoded_bytes", C.c_uint64), ("mismatch_at", C.c_uint64), ("candidates", C.c_uint64),
+                ("level", C.c_uint32), ("stored_stream_crc", C.c_uint32), ("computed_stream_crc", C.c_uint32), ("ok", C.c_int32),
+                ("first_bad_block", C.c_int32), ("first_bad_status", C.c_uint32), ("ms", C.c_double)]
+
+
 class ShardLink(C.Structure):
     _fields_ = [("total_bits", C.c_uint64 * 8), ("crc_rot", C.c_uint32 * 8), ("crc_fold", C.c_uint32 * 8)]
 
@@ -56,7 +62,7 @@ EXPORTS = ["b2_create", "b2_destroy", "b2_bound", "b2_encode_stream", "b2_encode
            "b2_set_timing", "b2_get_stats", "b2_reset_stats", "b2_dbg_block", "b2_get_trace", "b2_get_segments",
            "b2_zip_bound", "b2_zip_create", "b2_zip_crc32",
            "b2_shard_margin", "b2_shard_plan", "b2_shard_open", "b2_shard_cut", "b2_shard_encode", "b2_shard_resolve",
-           "b2_shard_finish", "b2_encode_stream_multi", "b2_set_progress"]
+           "b2_shard_finish", "b2_encode_stream_multi", "b2_set_progress", "b2_verify_stream"]
 
 _lib = None
 
@@ -93,6 +99,7 @@ def lib():
         _lib.b2_get_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
         _lib.b2_get_segments.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
         _lib.b2_set_progress.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.b2_verify_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_int, C.c_uint64, C.POINTER(VerifyResult)]
         _lib.b2_shard_margin.restype = C.c_uint64
         _lib.b2_shard_margin.argtypes = [C.c_int]
         _lib.b2_shard_plan.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_void_p]
@@ -269,6 +276,24 @@ class Encoder:
             buf.append(read_byte())
         for b in self.encode(bytes(buf), size_hint).tobytes():
             write_byte(b)
+
+    # -- decode / verify on the device ----------------------------------------
+    def verify(self, stream, expect=None):
+        """Decodes a BZip2 stream on the device (all blocks at once), checks block and stream CRCs and, when
+        `expect` is given, the decoded bytes.  Returns a VerifyResult (`.ok` == 1 when everything agrees)."""
+        a = _u8(stream)
+        res = VerifyResult()
+        if expect is None:
+            _check(lib().b2_verify_stream(self._h, a.ctypes.data, 0, a.size, None, 0, 0, C.byref(res)))
+        else:
+            x = _u8(expect)
+            _check(lib().b2_verify_stream(self._h, a.ctypes.data, 0, a.size, x.ctypes.data if x.size else None, 0, x.size, C.byref(res)))
+        return res
+
+    def verify_ptr(self, stream_ptr, stream_is_device, n, expect_ptr=None, expect_is_device=False, expect_n=0):
+        res = VerifyResult()
+        _check(lib().b2_verify_stream(self._h, stream_ptr, int(stream_is_device), n, expect_ptr, int(expect_is_device), expect_n, C.byref(res)))
+        return res
 
     def set_progress(self, fn):
         """fn (done_bytes, total_bytes) -> truthy to abort (B2Error with code 12); None switches it off."""

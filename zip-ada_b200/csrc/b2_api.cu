@@ -169,6 +169,11 @@ struct b2_encoder {
   DevBuf<B2ZipEntry> d_zents;
   DevBuf<B2ZipCopy> d_zcopies;
   DevBuf<u32> d_zpartial, d_zcrc;
+  // decode / verify (b2_verify_stream)
+  DevBuf<u8> d_vstream, d_vlcol, d_vrle, d_vsel;
+  DevBuf<u32> d_vlink, d_vchain, d_vscal;
+  DevBuf<u64> d_vcand;
+  DevBuf<B2VBlock> d_vblocks;
   std::vector<Workspace *> ws;
   // host state of the last call
   std::vector<B2Chunk> chunks;
@@ -178,6 +183,7 @@ struct b2_encoder {
   b2_stats stats;
   B2SortStats sort_stats;
   size_t batch_positions = 1536ull << 20;  // positions per batch (env B2GPU_BATCH_POSITIONS); big batches amortise the latency-bound kernels (about 45 B of device memory per position)
+  size_t first_batch_positions = ~(size_t)0;     // optional smaller first batch of a single large stream (env B2GPU_FIRST_BATCH_POSITIONS; measured: not a gain)
   size_t batch_jobs_max = 65535;        // blocks per batch    (env B2GPU_BATCH_JOBS)
   int n_workspaces = 1;                 // batches in flight   (env B2GPU_PIPELINE)
   u64 launches_other = 0;
@@ -756,9 +762,11 @@ int encode_chunks(b2_encoder *e, const u8 *d_in, std::vector<StreamDesc> &stream
   int plan_rc = 0;
   std::string plan_msg;
   {
+    u32 published = 0;
     auto publish = [&](Batch &&bt) {
       { std::lock_guard<std::mutex> lk(bmu); batches.push_back(std::move(bt)); }
       bcv.notify_all();
+      published++;
     };
     Batch cur; cur.c0 = 0;
     u64 positions = 0;
@@ -770,7 +778,10 @@ int encode_chunks(b2_encoder *e, const u8 *d_in, std::vector<StreamDesc> &stream
       u64 addpos = 0;
       if ((plan_rc = fetch_seg(c + 1))) break;                 // may wait for the segmentation of this chunk
       if ((plan_rc = plan_chunk(e, c, P, add, cur.jobs.size(), addpos))) break;
-      if (!cur.jobs.empty() && (positions + addpos > e->batch_positions || cur.jobs.size() + add.size() > e->batch_jobs_max)) {
+      // While the segmentation is still following the chunk chain the device has nothing else to do: the
+      // first batch is kept small so that it starts as soon as its few chunks are cut and segmented.
+      const size_t limit = (followed && published == 0) ? std::min(e->first_batch_positions, e->batch_positions) : e->batch_positions;
+      if (!cur.jobs.empty() && (positions + addpos > limit || cur.jobs.size() + add.size() > e->batch_jobs_max)) {
         cur.c1 = c;
         publish(std::move(cur));
         cur = Batch(); cur.c0 = c; positions = 0;
@@ -906,6 +917,7 @@ int b2_create(int level, int device, b2_encoder **out) {
   memset(&e->sort_stats, 0, sizeof e->sort_stats);
   // arena offsets are 32-bit: a batch plus one more chunk's worth of blocks must stay below 2^32 positions
   if (const char *s = getenv("B2GPU_BATCH_POSITIONS")) { long long v = atoll(s); if (v >= (1 << 20)) e->batch_positions = (size_t)std::min<long long>(v, 3ll << 30); }
+  if (const char *s = getenv("B2GPU_FIRST_BATCH_POSITIONS")) { long long v = atoll(s); if (v >= (1 << 20)) e->first_batch_positions = (size_t)v; }
   if (const char *s = getenv("B2GPU_BATCH_JOBS")) { long long v = atoll(s); if (v >= 8) e->batch_jobs_max = (size_t)std::min<long long>(v, 65535); }   // grid.y of the per-(triple, block) kernels
   if (const char *s = getenv("B2GPU_PIPELINE")) { int v = atoi(s); if (v >= 1 && v <= 8) e->n_workspaces = v; }
   auto init = [&]() -> int {
@@ -953,6 +965,8 @@ void b2_destroy(b2_encoder *e) {
   e->d_ct.release(); e->d_T.release(); e->d_in.release(); e->d_out.release(); e->d_chunks.release();
   e->d_scalars.release(); e->d_seg.release(); e->d_nseg.release(); e->d_ends.release(); e->d_packitems.release(); e->d_packed.release(); e->d_cut_first.release(); e->d_cut_last.release();
   e->d_cut_tsum.release(); e->d_cut_carry.release(); e->d_cut_tincl.release();
+  e->d_vstream.release(); e->d_vlcol.release(); e->d_vrle.release(); e->d_vsel.release(); e->d_vlink.release(); e->d_vchain.release();
+  e->d_vscal.release(); e->d_vcand.release(); e->d_vblocks.release();
   e->d_zt.release(); e->d_ztiles.release(); e->d_zents.release(); e->d_zcopies.release(); e->d_zpartial.release(); e->d_zcrc.release();
   if (e->ev[0]) cudaEventDestroy(e->ev[0]);
   if (e->ev[1]) cudaEventDestroy(e->ev[1]);
@@ -1337,6 +1351,139 @@ int b2_encode_stream_multi(b2_encoder **encs, int n_encs, const uint8_t *in, uin
   }
   for (auto &kv : edge) out[kv.first] = kv.second;
   *out_len = (bit_off[ns] + 80 + 7) >> 3;
+  return 0;
+}
+
+// ---- decode / verify on the device ---------------------------------------------------------
+int b2_verify_stream(b2_encoder *e, const uint8_t *stream, int stream_is_device, uint64_t n, const uint8_t *expect,
+                     int expect_is_device, uint64_t expect_n, b2_verify_result *res) {
+  if (!e || !res || (n && !stream)) B2_FAIL(B2_ERR_ARGUMENT, "bad argument");
+  memset(res, 0, sizeof *res);
+  res->first_bad_block = -1; res->mismatch_at = ~0ull;
+  B2_CUDA_CHECK(cudaSetDevice(e->device));
+  cudaStream_t st = e->st;
+  if (n < 14) { res->first_bad_status = 1; return 0; }                      // "BZh9" + footer is the shortest stream
+  B2_TRY(e->d_vstream.ensure(n + 128));
+  B2_CUDA_CHECK(cudaEventRecord(e->ev[0], st));
+  B2_CUDA_CHECK(cudaMemcpyAsync(e->d_vstream.p, stream, n, stream_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+  B2_CUDA_CHECK(cudaMemsetAsync(e->d_vstream.p + n, 0, 128, st));
+  u8 head[4];
+  B2_CUDA_CHECK(cudaMemcpyAsync(head, e->d_vstream.p, 4, cudaMemcpyDeviceToHost, st));
+  B2_CUDA_CHECK(cudaStreamSynchronize(st));
+  if (head[0] != 'B' || head[1] != 'Z' || head[2] != 'h' || head[3] < '1' || head[3] > '9') { res->first_bad_status = 1; return 0; }
+  const u32 level = head[3] - '0';
+  res->level = level;
+  const u32 max_n = level * 100000u;
+  // candidates: every occurrence of the two magics, at any bit offset
+  const u32 cap = (u32)std::min<u64>(n / 32 + 4096, 1u << 26);
+  B2_TRY(e->d_vcand.ensure(cap));
+  B2_TRY(e->d_vscal.ensure(8));
+  B2_CUDA_CHECK(cudaMemsetAsync(e->d_vscal.p, 0, 8 * sizeof(u32), st));
+  B2_TRY(b2k_verify_find(st, e->d_vstream.p, n, e->d_vcand.p, e->d_vscal.p, cap));
+  u32 n_cand = 0;
+  B2_CUDA_CHECK(cudaMemcpyAsync(&n_cand, e->d_vscal.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
+  B2_CUDA_CHECK(cudaStreamSynchronize(st));
+  if (n_cand > cap) B2_FAIL(B2_ERR_INTERNAL, "too many block-magic candidates");
+  std::vector<u64> cand(n_cand);
+  if (n_cand) B2_CUDA_CHECK(cudaMemcpy(cand.data(), e->d_vcand.p, n_cand * sizeof(u64), cudaMemcpyDeviceToHost));
+  std::sort(cand.begin(), cand.end());
+  res->candidates = n_cand;
+  // device copy of the expected bytes
+  const u8 *d_expect = nullptr;
+  if (expect) {
+    if (expect_is_device) d_expect = expect;
+    else {
+      B2_TRY(e->d_in.ensure(expect_n + 256));
+      if (expect_n) B2_CUDA_CHECK(cudaMemcpyAsync(e->d_in.p, expect, expect_n, cudaMemcpyHostToDevice, st));
+      d_expect = e->d_in.p;
+    }
+    const unsigned long long none = ~0ull;
+    B2_CUDA_CHECK(cudaMemcpyAsync(e->d_vscal.p + 2, &none, sizeof none, cudaMemcpyHostToDevice, st));
+  }
+  // waves of candidates in stream order; the chain "next block starts where this one ended" is followed as the
+  // results arrive
+  size_t wave = 2048;
+  if (const char *sv = getenv("B2GPU_VERIFY_WAVE")) { long v = atol(sv); if (v >= 1) wave = (size_t)v; }
+  u64 cur = 32, raw_total = 0;
+  u32 combined = 0;
+  bool done = false, failed = false;
+  u64 n_chain = 0;
+  std::vector<B2VBlock> blk;
+  std::vector<u32> chain;
+  for (size_t c0 = 0; c0 < cand.size() && !done && !failed;) {
+    // skip candidates the chain has already passed (magic look-alikes inside a block)
+    while (c0 < cand.size() && (cand[c0] >> 1) < cur) c0++;
+    if (c0 >= cand.size()) break;
+    const size_t c1 = std::min(cand.size(), c0 + wave);
+    const u32 nb = (u32)(c1 - c0);
+    blk.assign(nb, B2VBlock{});
+    for (u32 k = 0; k < nb; k++) { blk[k].start_bit = cand[c0 + k] >> 1; blk[k].status = (cand[c0 + k] & 1) ? 0xFFu : 0u; }
+    B2_TRY(e->d_vblocks.ensure(nb));
+    B2_TRY(e->d_vlink.ensure((size_t)nb * (max_n + 32)));
+    B2_TRY(e->d_vlcol.ensure((size_t)nb * (max_n + 32)));
+    B2_TRY(e->d_vrle.ensure((size_t)nb * (max_n + 32)));
+    B2_TRY(e->d_vsel.ensure((size_t)nb * 18016));
+    B2_CUDA_CHECK(cudaMemcpyAsync(e->d_vblocks.p, blk.data(), nb * sizeof(B2VBlock), cudaMemcpyHostToDevice, st));
+    B2_TRY(b2k_verify_decode(st, e->d_vstream.p, n, e->d_vblocks.p, nb, max_n, e->d_vlink.p, e->d_vlcol.p, e->d_vrle.p, e->d_vsel.p,
+                             e->d_ct.p->byte_tab));
+    e->launches_other += 1;
+    B2_CUDA_CHECK(cudaMemcpyAsync(blk.data(), e->d_vblocks.p, nb * sizeof(B2VBlock), cudaMemcpyDeviceToHost, st));
+    B2_CUDA_CHECK(cudaStreamSynchronize(st));
+    chain.clear();
+    size_t k = 0;
+    while (k < nb) {
+      if (blk[k].start_bit < cur) { k++; continue; }
+      if (blk[k].start_bit > cur) { failed = true; res->first_bad_block = (int32_t)n_chain; res->first_bad_status = 20; break; }   // a gap: no block where one must start
+      if (cand[c0 + k] & 1) {                        // the stream footer (:1395-1407): 48-bit magic, combined CRC
+        u8 f[12];
+        B2_CUDA_CHECK(cudaMemcpy(f, e->d_vstream.p + ((cur + 48) >> 3), 8, cudaMemcpyDeviceToHost));
+        const u32 sh = (u32)((cur + 48) & 7);
+        u64 w = 0;
+        for (int q = 0; q < 8; q++) w = (w << 8) | f[q];
+        res->stored_stream_crc = (u32)((w << sh) >> 32);
+        res->computed_stream_crc = combined;
+        const u64 end_bytes = (cur + 80 + 7) >> 3;
+        done = true;
+        if (end_bytes != n) { failed = true; res->first_bad_status = 21; }          // bytes behind the footer
+        break;
+      }
+      const B2VBlock &b = blk[k];
+      if (b.status != 0 || b.computed_crc != b.stored_crc) {
+        failed = true; res->first_bad_block = (int32_t)n_chain; res->first_bad_status = b.status ? b.status : 30;
+        break;
+      }
+      blk[k].raw_off = raw_total;
+      raw_total += b.raw_len;
+      combined = rotl1(combined) ^ b.stored_crc;
+      cur = b.end_bit;
+      chain.push_back((u32)k);
+      n_chain++;
+      k++;
+    }
+    if (d_expect && !chain.empty()) {
+      B2_TRY(e->d_vchain.ensure(chain.size()));
+      B2_CUDA_CHECK(cudaMemcpyAsync(e->d_vblocks.p, blk.data(), nb * sizeof(B2VBlock), cudaMemcpyHostToDevice, st));
+      B2_CUDA_CHECK(cudaMemcpyAsync(e->d_vchain.p, chain.data(), chain.size() * sizeof(u32), cudaMemcpyHostToDevice, st));
+      B2_TRY(b2k_verify_compare(st, e->d_vblocks.p, e->d_vchain.p, (u32)chain.size(), max_n, e->d_vrle.p, d_expect, expect_n,
+                                (unsigned long long *)(e->d_vscal.p + 2)));
+      e->launches_other += 1;
+      B2_CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+    c0 = c1;
+  }
+  if (!done && !failed) { failed = true; res->first_bad_block = (int32_t)n_chain; res->first_bad_status = 22; }   // no footer
+  res->blocks = n_chain;
+  res->decoded_bytes = raw_total;
+  if (d_expect) {
+    unsigned long long bad = ~0ull;
+    B2_CUDA_CHECK(cudaMemcpy(&bad, e->d_vscal.p + 2, sizeof bad, cudaMemcpyDeviceToHost));
+    res->mismatch_at = bad;
+    if (bad == ~0ull && !failed && raw_total != expect_n) res->mismatch_at = std::min<u64>(raw_total, expect_n);
+  }
+  B2_CUDA_CHECK(cudaEventRecord(e->ev[1], st));
+  B2_CUDA_CHECK(cudaStreamSynchronize(st));
+  { float ms = 0; cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]); res->ms = ms; }
+  res->ok = (!failed && done && res->stored_stream_crc == res->computed_stream_crc && (!d_expect || res->mismatch_at == ~0ull)) ? 1 : 0;
   return 0;
 }
 

@@ -110,3 +110,17 @@ void b2k_make_zipcrc_tables(B2ZipCrcTables *t);
 int b2k_zipcrc(cudaStream_t st, const u8 *d_in, const B2ZipTile *d_tiles, u32 n_tiles, const B2ZipEntry *d_ents, u32 n_entries,
                const B2ZipCrcTables *d_zt, u32 *d_partial, u32 *d_crc);
 int b2k_zip_gather(cudaStream_t st, const B2ZipCopy *d_items, u32 n, const u8 *d_src0, const u8 *d_src1, u8 *d_dst);
+
+// ---- decode / verify (b2_verify.cu) -----------------------------------------------------------------------
+struct B2VBlock {
+  u64 start_bit;      // position of the block's 48-bit magic in the stream
+  u64 end_bit;        // (out) first bit behind the block
+  u64 raw_len;        // (out) raw bytes of the block (after RLE1 decoding)
+  u64 raw_off;        // (in, for the comparison) where the block's raw bytes start in the decoded stream
+  u32 stored_crc, computed_crc, n_rle, orig_ptr, status, pad;
+};
+int b2k_verify_find(cudaStream_t st, const u8 *d_stream, u64 n_bytes, u64 *d_cand, u32 *d_n_cand, u32 cap);
+int b2k_verify_decode(cudaStream_t st, const u8 *d_stream, u64 n_bytes, B2VBlock *d_blocks, u32 n_blocks, u32 max_n, u32 *d_link, u8 *d_lcol,
+                      u8 *d_rle, u8 *d_sel, const u32 *d_crc_tab);
+int b2k_verify_compare(cudaStream_t st, const B2VBlock *d_blocks, const u32 *d_chain, u32 n_chain, u32 max_n, const u8 *d_rle,
+                       const u8 *d_expect, u64 expect_n, unsigned long long *d_first_bad);

@@ -86,19 +86,28 @@ def resolve(rows):
 def encode_sharded(engine, comm, slice_ptr, in_is_device, n, size_hint, bounds, span, out_ptr, out_is_device, out_cap):
     """This rank's part of one stream.  slice_ptr points at stream byte span[0]; the rank holds the bytes
     [span[0], span[1]).  Returns dict(byte_offset, length, first_byte, last_byte, total_length)."""
+    import time
     r, w = comm.rank, comm.world
     lo, hi = span
+    t0 = time.perf_counter()
     engine.shard_open(slice_ptr, in_is_device, lo, hi - lo, n, size_hint, bounds[r + 1])
     entry = 0 if r == 0 else comm.recv_u64(r - 1)
+    t1 = time.perf_counter()
     handoff = engine.shard_cut(entry)
     if r + 1 < w:
         comm.send_u64(r + 1, handoff)
+    t2 = time.perf_counter()
     link = engine.shard_encode()
+    t3 = time.perf_counter()
     rows = comm.all_gather_i64(_link_to_list(link))
     bit, crc = resolve(rows)
+    t4 = time.perf_counter()
     off, ln, fb, lb = engine.shard_finish(bit[r], crc[r], out_ptr, out_is_device, out_cap)
+    t5 = time.perf_counter()
     return dict(byte_offset=off, length=ln, first_byte=fb, last_byte=lb, total_length=(bit[w] + 80 + 7) >> 3,
-                entry=entry, handoff=handoff)
+                entry=entry, handoff=handoff,
+                phases_ms=dict(open_and_wait_for_entry=1000 * (t1 - t0), cut=1000 * (t2 - t1), encode=1000 * (t3 - t2),
+                               wait_for_links=1000 * (t4 - t3), finish=1000 * (t5 - t4)))
 
 
 class OracleShardEngine:
