@@ -163,6 +163,8 @@ struct b2_encoder {
   DevBuf<u8> d_packed;
   DevBuf<u32> d_cut_first, d_cut_last, d_cut_tsum;
   DevBuf<u64> d_cut_carry, d_cut_tincl;
+  DevBuf<u8> d_cut_gs;
+  DevBuf<u16> d_cut_gm;
   // archive side (b2_zip_create)
   DevBuf<B2ZipCrcTables> d_zt;
   DevBuf<B2ZipTile> d_ztiles;
@@ -503,7 +505,8 @@ int encode_streams(b2_encoder *e, const u8 *d_in, std::vector<StreamDesc> &strea
         const size_t ct = (size_t)(S.n / 2048 + 2);
         B2_TRY(e->d_cut_first.ensure(ct)); B2_TRY(e->d_cut_last.ensure(ct)); B2_TRY(e->d_cut_tsum.ensure(ct));
         B2_TRY(e->d_cut_carry.ensure(ct)); B2_TRY(e->d_cut_tincl.ensure(ct));
-        B2CutWork cw{e->d_cut_first.p, e->d_cut_last.p, e->d_cut_tsum.p, e->d_cut_carry.p, e->d_cut_tincl.p};
+        B2_TRY(e->d_cut_gs.ensure(ct * 128)); B2_TRY(e->d_cut_gm.ensure(ct * 128));
+        B2CutWork cw{e->d_cut_first.p, e->d_cut_last.p, e->d_cut_tsum.p, e->d_cut_carry.p, e->d_cut_tincl.p, e->d_cut_gs.p, e->d_cut_gm.p};
         // A single large stream: the segmentation of a chunk starts as soon as the chain has cut it
         // (k_segment on a second stream follows the chain's progress counter) instead of after the
         // whole chain, which is one warp walking from chunk to chunk.
@@ -964,7 +967,7 @@ void b2_destroy(b2_encoder *e) {
   e->ws.clear();
   e->d_ct.release(); e->d_T.release(); e->d_in.release(); e->d_out.release(); e->d_chunks.release();
   e->d_scalars.release(); e->d_seg.release(); e->d_nseg.release(); e->d_ends.release(); e->d_packitems.release(); e->d_packed.release(); e->d_cut_first.release(); e->d_cut_last.release();
-  e->d_cut_tsum.release(); e->d_cut_carry.release(); e->d_cut_tincl.release();
+  e->d_cut_tsum.release(); e->d_cut_carry.release(); e->d_cut_tincl.release(); e->d_cut_gs.release(); e->d_cut_gm.release();
   e->d_vstream.release(); e->d_vlcol.release(); e->d_vrle.release(); e->d_vsel.release(); e->d_vlink.release(); e->d_vchain.release();
   e->d_vscal.release(); e->d_vcand.release(); e->d_vblocks.release();
   e->d_zt.release(); e->d_ztiles.release(); e->d_zents.release(); e->d_zcopies.release(); e->d_zpartial.release(); e->d_zcrc.release();
@@ -1121,7 +1124,8 @@ int b2_shard_open(b2_encoder *e, const uint8_t *in, int in_is_device, uint64_t b
   const size_t ct = (size_t)(n_local / 2048 + 2);
   B2_TRY(e->d_cut_first.ensure(ct)); B2_TRY(e->d_cut_last.ensure(ct)); B2_TRY(e->d_cut_tsum.ensure(ct));
   B2_TRY(e->d_cut_carry.ensure(ct)); B2_TRY(e->d_cut_tincl.ensure(ct));
-  B2CutWork cw{e->d_cut_first.p, e->d_cut_last.p, e->d_cut_tsum.p, e->d_cut_carry.p, e->d_cut_tincl.p};
+        B2_TRY(e->d_cut_gs.ensure(ct * 128)); B2_TRY(e->d_cut_gm.ensure(ct * 128));
+  B2CutWork cw{e->d_cut_first.p, e->d_cut_last.p, e->d_cut_tsum.p, e->d_cut_carry.p, e->d_cut_tincl.p, e->d_cut_gs.p, e->d_cut_gm.p};
   B2_TRY(b2k_cut_scans(e->st, sh.d_in, n_local, &cw));
   e->launches_other += 4;
   sh.open = true;
@@ -1142,7 +1146,7 @@ int b2_shard_cut(b2_encoder *e, uint64_t entry, uint64_t *handoff) {
   const u64 own = sh.own_end > entry ? sh.own_end - entry : 0;
   const u32 max_chunks = (u32)(own / (40000ull * level) + 16);
   B2_TRY(e->d_chunks.ensure(max_chunks));
-  B2CutWork cw{e->d_cut_first.p, e->d_cut_last.p, e->d_cut_tsum.p, e->d_cut_carry.p, e->d_cut_tincl.p};
+  B2CutWork cw{e->d_cut_first.p, e->d_cut_last.p, e->d_cut_tsum.p, e->d_cut_carry.p, e->d_cut_tincl.p, e->d_cut_gs.p, e->d_cut_gm.p};
   const bool follow = level == 9 && e->timing < 2;
   if (level == 9) {
     B2_TRY(e->d_seg.ensure((size_t)max_chunks * 2 * B2_MAX_SEG));

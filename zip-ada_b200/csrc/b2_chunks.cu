@@ -98,7 +98,7 @@ __device__ __forceinline__ u32 gstep(bool first_of_stream, bool chg, u32 &m) {
 __device__ __forceinline__ u32 mod259(u64 d) { return (d >> 32) ? (u32)(d % 259ull) : ((u32)d % 259u); }
 
 __global__ void __launch_bounds__(CT_THREADS)
-k_cut_b(const u8 *__restrict__ in, u64 n, const u64 *__restrict__ carry_r, u32 *__restrict__ tsum) {
+k_cut_b(const u8 *__restrict__ in, u64 n, const u64 *__restrict__ carry_r, u32 *__restrict__ tsum, u8 *__restrict__ gs, u16 *__restrict__ gm) {
   __shared__ i32 sm_i[40];
   __shared__ u32 sm_u[40];
   const u64 t0 = (u64)blockIdx.x * CT_TILE;
@@ -124,6 +124,7 @@ k_cut_b(const u8 *__restrict__ in, u64 n, const u64 *__restrict__ carry_r, u32 *
   u32 local = 0;
   {
     u32 m = (base > 0 && base <= n) ? mod259(base - 1 - r) : 0;   // index of byte base-1 inside its piece
+    gm[(size_t)blockIdx.x * CT_THREADS + tid] = (u16)m;
     u8 pv = prev;
 #pragma unroll
     for (int k = 0; k < 16; k++) {
@@ -132,9 +133,67 @@ k_cut_b(const u8 *__restrict__ in, u64 n, const u64 *__restrict__ carry_r, u32 *
       pv = b[k];
     }
   }
+  gs[(size_t)blockIdx.x * CT_THREADS + tid] = (u8)local;          // at most 16 x 5
   u32 total;
   block_excl_add(local, sm_u, &total);
   if (tid == 0) tsum[blockIdx.x] = total;
+}
+
+// The two in-tile questions of the chain, answered from the granule sums: one 128-byte load and a warp scan
+// find the granule, at most 16 bytes are then stepped through.
+//  mode 0: inclusive in-tile prefix of g at global position q          -> returns the prefix
+//  mode 1: first global position p in the tile with excl + prefix(p) >= target   -> position or ~0
+__device__ u64 warp_tile_g(const u8 *__restrict__ in, u64 n, const u8 *__restrict__ gs, const u16 *__restrict__ gm, u64 t, int mode,
+                           u64 q, u64 excl, u64 target) {
+  const u32 l = lane_id();
+  const u64 t0 = t * CT_TILE;
+  const u32 w = *reinterpret_cast<const u32 *>(gs + t * CT_THREADS + 4 * l);      // granules 4l .. 4l+3
+  const u32 s0 = w & 255u, s1 = (w >> 8) & 255u, s2 = (w >> 16) & 255u, s3 = w >> 24;
+  const u32 c0 = s0, c1 = c0 + s1, c2 = c1 + s2, c3 = c2 + s3;                     // inclusive inside my four
+  const u32 incl = warp_incl_add(c3);
+  const u32 before = incl - c3;                                                    // granules of the lanes before me
+  u32 gq;                                                                          // the granule to step through
+  u64 run;                                                                         // prefix before that granule (mode 0: in-tile; mode 1: global)
+  u64 need = 0;
+  if (mode == 0) {
+    gq = (u32)((q - t0) >> 4);
+    const u32 k = gq & 3u;
+    const u32 mine = before + (k == 0 ? 0u : k == 1 ? c0 : k == 2 ? c1 : c2);
+    run = __shfl_sync(0xffffffffu, mine, gq >> 2);
+  } else {
+    if (target <= excl) need = 0; else need = target - excl;
+    // (need == 0 cannot happen: the chain asks for a position strictly behind the chunk's first run)
+    const u32 tot = __shfl_sync(0xffffffffu, incl, 31);
+    if (need > tot) return ~0ull;
+    const u32 nd = (u32)need;
+    int k = -1;
+    if (before + c0 >= nd) k = 0; else if (before + c1 >= nd) k = 1; else if (before + c2 >= nd) k = 2; else if (before + c3 >= nd) k = 3;
+    const u32 bm = __ballot_sync(0xffffffffu, k >= 0);
+    if (!bm) return ~0ull;
+    const int src = __ffs(bm) - 1;
+    const int ks = __shfl_sync(0xffffffffu, k, src);
+    const u32 pre = __shfl_sync(0xffffffffu, before + (ks == 0 ? 0u : ks == 1 ? c0 : ks == 2 ? c1 : c2), src);
+    gq = 4u * (u32)src + (u32)ks;
+    run = excl + pre;
+  }
+  // step through granule gq (every lane does the same: uniform)
+  const u64 base = t0 + 16ull * gq;
+  u8 b[16];
+  load16(in, base, n, b);
+  u8 pv = (base > 0 && base < n) ? in[base - 1] : 0;
+  u32 m = gm[t * CT_THREADS + gq];
+  u64 res = ~0ull;
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    const u64 p = base + k;
+    if (p < n && res == ~0ull) {
+      run += gstep(p == 0, b[k] != pv, m);
+      if (mode == 0 && p == q) res = run;
+      if (mode == 1 && run >= target) res = p;
+    }
+    pv = b[k];
+  }
+  return res;
 }
 
 __global__ void __launch_bounds__(1024)
@@ -245,6 +304,7 @@ __device__ u64 warp_tile(const u8 *__restrict__ in, u64 n, const u64 *__restrict
 __global__ void __launch_bounds__(32)
 k_cut_chain(const u8 *__restrict__ in, u64 n, i64 size_hint, int level, i64 win_lo, i64 win_hi,
             const u32 *__restrict__ firstchg, const u64 *__restrict__ carry_r, const u64 *__restrict__ tincl, u64 ntiles,
+            const u8 *__restrict__ gs, const u16 *__restrict__ gm,
             B2Chunk *chunks, u32 *n_chunks, u32 max_chunks, u32 *progress, u64 gbase, u64 pos0, u64 stop) {
   // progress[0] = chunks published so far, progress[1] = 1 when the chain is complete: k_segment may be
   // following on another stream and starts on a chunk as soon as it is there
@@ -272,7 +332,14 @@ k_cut_chain(const u8 *__restrict__ in, u64 n, i64 size_hint, int level, i64 win_
       u64 e1 = ~0ull;
       {
         u64 t = s / CT_TILE;
-        e1 = warp_tile(in, n, carry_r, t, 2, s, 0, 0);
+        {
+          // the usual case: the byte changes within the next 32 positions
+          const u64 p = s + 1 + l;
+          const bool chg = p < n && in[p] != in[p - 1];
+          const u32 bm = __ballot_sync(0xffffffffu, chg);
+          if (bm) e1 = s + 1 + (u64)(__ffs(bm) - 1);
+        }
+        if (e1 == ~0ull) e1 = warp_tile(in, n, carry_r, t, 2, s, 0, 0);
         if (e1 == ~0ull) {
           // skip tiles without any change, 32 at a time
           for (u64 tb = t + 1; tb < ntiles && e1 == ~0ull; tb += 32) {
@@ -297,7 +364,7 @@ k_cut_chain(const u8 *__restrict__ in, u64 n, i64 size_hint, int level, i64 win_
         else {
           const u64 te = e1 / CT_TILE;
           const u64 excl_e = te ? tincl[te - 1] : 0;
-          const u64 Ge1 = excl_e + warp_tile(in, n, carry_r, te, 0, e1, excl_e, 0);
+          const u64 Ge1 = excl_e + warp_tile_g(in, n, gs, gm, te, 0, e1, 0, 0);
           const u64 Gt = Ge1 + (need - A);
           // first tile whose inclusive prefix reaches Gt
           // (32 probes per trip, one per lane; tiles at or beyond the end of the window need not be looked at)
@@ -315,7 +382,7 @@ k_cut_chain(const u8 *__restrict__ in, u64 n, i64 size_hint, int level, i64 win_
           }
           if (lo < ntiles && lo * CT_TILE < end_max) {
             const u64 excl = lo ? tincl[lo - 1] : 0;
-            const u64 p = warp_tile(in, n, carry_r, lo, 1, 0, excl, Gt);
+            const u64 p = warp_tile_g(in, n, gs, gm, lo, 1, 0, excl, Gt);
             if (p != ~0ull && p < end_max) len = p - s + 1;  // (iv)
           }
         }
@@ -340,7 +407,7 @@ int b2k_cut_scans(cudaStream_t st, const u8 *d_in, u64 n, B2CutWork *w) {
   if (ntiles) {
     k_cut_a<<<(u32)ntiles, CT_THREADS, 0, st>>>(d_in, n, w->firstchg, w->lastchg);
     k_cut_s1<<<1, 1024, 0, st>>>(w->lastchg, ntiles, w->carry_r);
-    k_cut_b<<<(u32)ntiles, CT_THREADS, 0, st>>>(d_in, n, w->carry_r, w->tsum);
+    k_cut_b<<<(u32)ntiles, CT_THREADS, 0, st>>>(d_in, n, w->carry_r, w->tsum, w->gs, w->gm);
     k_cut_s2<<<1, 1024, 0, st>>>(w->tsum, ntiles, w->tincl);
     B2_CUDA_CHECK(cudaGetLastError());
   }
@@ -353,7 +420,7 @@ int b2k_cut_chain(cudaStream_t st, const u8 *d_in, u64 n, i64 size_hint, int lev
   const u64 ntiles = (n + CT_TILE - 1) / CT_TILE;
   if (d_progress) B2_CUDA_CHECK(cudaMemsetAsync(d_progress, 0, 2 * sizeof(u32), st));
   if (ev_chain_starts) B2_CUDA_CHECK(cudaEventRecord(ev_chain_starts, st));
-  k_cut_chain<<<1, 32, 0, st>>>(d_in, n, size_hint, level, win_lo, win_hi, w->firstchg, w->carry_r, w->tincl, ntiles,
+  k_cut_chain<<<1, 32, 0, st>>>(d_in, n, size_hint, level, win_lo, win_hi, w->firstchg, w->carry_r, w->tincl, ntiles, w->gs, w->gm,
                                 d_chunks, d_n_chunks, max_chunks, d_progress, gbase, pos0, stop);
   B2_CUDA_CHECK(cudaGetLastError());
   return 0;

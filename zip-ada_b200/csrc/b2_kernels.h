@@ -29,7 +29,7 @@ struct B2SortStats {
 };
 
 // b2_chunks.cu  (per 2048-byte tile work arrays of the chunk cutter)
-struct B2CutWork { u32 *firstchg, *lastchg, *tsum; u64 *carry_r, *tincl; };
+struct B2CutWork { u32 *firstchg, *lastchg, *tsum; u64 *carry_r, *tincl; u8 *gs; u16 *gm; };   // gs / gm: per 16-byte granule
 int b2k_cut(cudaStream_t st, const u8 *d_in, u64 n, i64 size_hint, int level, i64 win_lo, i64 win_hi,
             B2Chunk *d_chunks, u32 *d_n_chunks, u32 max_chunks, B2CutWork *w, u32 *d_progress, cudaEvent_t ev_chain_starts);
 int b2k_cut_scans(cudaStream_t st, const u8 *d_in, u64 n, B2CutWork *w);

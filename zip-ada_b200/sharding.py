@@ -21,25 +21,29 @@ import numpy as np
 
 # ---- communication: the two exchanges, over torch.distributed (nccl on the GPU box, gloo in the CPU tests) ----
 class TorchComm:
-    def __init__(self, dist, rank, world, device=None):
-        self.dist, self.rank, self.world, self.device = dist, rank, world, device
+    """group: the process group of the exchanges.  On a GPU box pass a gloo group with device=None: the scalars
+    then travel through the host and no exchange has to wait for a free SM (a NCCL point-to-point kernel queues
+    behind whatever the device is running)."""
+
+    def __init__(self, dist, rank, world, device=None, group=None):
+        self.dist, self.rank, self.world, self.device, self.group = dist, rank, world, device, group
 
     def _t(self, values):
         import torch
         return torch.tensor(values, dtype=torch.int64, device=self.device)
 
     def send_u64(self, dst, v):
-        self.dist.send(self._t([int(v)]), dst)
+        self.dist.send(self._t([int(v)]), dst, group=self.group)
 
     def recv_u64(self, src):
         t = self._t([0])
-        self.dist.recv(t, src)
+        self.dist.recv(t, src, group=self.group)
         return int(t.item())
 
     def all_gather_i64(self, values):
         t = self._t([int(v) for v in values])
         outs = [self._t([0] * len(values)) for _ in range(self.world)]
-        self.dist.all_gather(outs, t)
+        self.dist.all_gather(outs, t, group=self.group)
         return [[int(x) for x in o.tolist()] for o in outs]
 
 
