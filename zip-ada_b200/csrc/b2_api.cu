@@ -1073,7 +1073,7 @@ int b2_shard_plan(uint64_t n, int n_shards, int level, int stagger_permille, uin
   // Shard r can only start once shard r-1 has cut its chunks, so its share is smaller by the factor
   // (1 - stagger): all shards then finish together (stagger = encode rate / cutting rate of one device).
   if (stagger_permille < 0) {
-    stagger_permille = 30;
+    stagger_permille = 12;
     if (const char *sv = getenv("B2GPU_SHARD_STAGGER")) { int v = atoi(sv); if (v >= 0 && v < 500) stagger_permille = v; }
   }
   const double q = 1.0 - stagger_permille / 1000.0;

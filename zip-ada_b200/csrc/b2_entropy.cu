@@ -109,11 +109,12 @@ k_group_hist(const B2Job *__restrict__ jobs, const u16 *__restrict__ mtf, u16 *_
 // (its tie order is the point); one thread per array, array staged in shared memory.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32)
-k_rank_sort(const B2Job *__restrict__ jobs, u32 *__restrict__ rank3, u32 *__restrict__ rank4) {
+k_rank_sort(const B2Job *__restrict__ jobs, u32 *__restrict__ rank3, u32 *__restrict__ rank4, u32 g_lo, u32 g_hi) {
   extern __shared__ __align__(16) u32 a[];   // 1-based: a[1..G]
   const B2Job &job = jobs[blockIdx.x >> 1];
   u32 *arr = ((blockIdx.x & 1) ? rank4 : rank3) + job.grp_off;
   const i32 G = (i32)job.n_groups;
+  if ((u32)G <= g_lo || (u32)G > g_hi) return;     // launched once per size class (shared memory per sort)
   for (i32 i = threadIdx.x; i < G; i += 32) a[i + 1] = arr[i];
   __syncwarp();
   if (threadIdx.x == 0) {
@@ -459,12 +460,24 @@ k_ent_qsort(EntArgs a, u32 nq, u32 alpha_max, u32 n_lo, u32 n_hi) {
 #define LL_BITWORDS 17
 #define PM_WARPS 4
 
+// Scratch of one warp, carved out of dynamic shared memory sized by the largest alphabet of the batch (a text
+// batch needs 4.4 KB per warp instead of 7.3 KB: more warps per SM for a latency-bound kernel).
 struct LLScratch {
-  u32 leaf[B2_MAX_ALPHA + 2];              // (weight << 9) | symbol, sorted
-  u32 lvl[2][LL_MAXITEMS];                 // merged weights of two consecutive lists
-  u32 pk[B2_MAX_ALPHA + 2];                // pair sums of the list below
-  u32 pkgbits[LL_MAXBITS][LL_BITWORDS];    // bit p set <=> item p of the list is a package
+  u32 *leaf;                               // [alpha + 2]     (weight << 9) | symbol, sorted
+  u32 *lvl[2];                             // [2 * alpha]     merged weights of two consecutive lists
+  u32 *pk;                                 // [alpha + 2]     pair sums of the list below
+  u32 (*pkgbits)[LL_BITWORDS];             // [LL_MAXBITS]    bit p set <=> item p of the list is a package
 };
+__host__ __device__ inline u32 ll_scratch_words(u32 alpha) { return (alpha + 2) * 2 + 4 * alpha + LL_MAXBITS * LL_BITWORDS; }
+__device__ __forceinline__ LLScratch ll_scratch_at(u32 *base, u32 alpha) {
+  LLScratch S;
+  S.leaf = base; base += alpha + 2;
+  S.lvl[0] = base; base += 2 * alpha;
+  S.lvl[1] = base; base += 2 * alpha;
+  S.pk = base; base += alpha + 2;
+  S.pkgbits = reinterpret_cast<u32 (*)[LL_BITWORDS]>(base);
+  return S;
+}
 
 __device__ void ll_package_merge_warp(LLScratch &S, int ns, int max_bits, u8 *lens) {
   const u32 l = lane_id();
@@ -530,20 +543,21 @@ __device__ void ll_package_merge_warp(LLScratch &S, int ns, int max_bits, u8 *le
 }
 
 __global__ void __launch_bounds__(32 * PM_WARPS)
-k_ent_pm(EntArgs a, u32 nq) {
-  __shared__ LLScratch S[PM_WARPS];
+k_ent_pm(EntArgs a, u32 nq, u32 alpha_max) {
+  extern __shared__ u32 pm_smem[];
   const u32 w = warp_id(), l = lane_id();
   const u32 slot = blockIdx.x * PM_WARPS + w;
   if (slot >= min(*a.wl_count, nq)) return;
+  LLScratch S = ll_scratch_at(pm_smem + (size_t)w * ll_scratch_words(alpha_max), alpha_max);
   const u32 q = a.wl[slot];
   const u32 p = q / B2_MAX_CODERS, c = q % B2_MAX_CODERS;
   const u32 jb = p / B2_N_TRIPLES, t = p % B2_N_TRIPLES;
   int max_len, sw, ec;
   b2_triple(a.level, (int)t, max_len, sw, ec);
   const int ns = (int)a.jobs[jb].n_used + 2;
-  for (int e = l; e < ns; e += 32) S[w].leaf[e] = a.leaves[leaf_index(slot, (u32)e)];
+  for (int e = l; e < ns; e += 32) S.leaf[e] = a.leaves[leaf_index(slot, (u32)e)];
   __syncwarp();
-  ll_package_merge_warp(S[w], ns, max_len, a.lens + ((size_t)p * B2_MAX_CODERS + c) * B2_MAX_ALPHA);
+  ll_package_merge_warp(S, ns, max_len, a.lens + ((size_t)p * B2_MAX_CODERS + c) * B2_MAX_ALPHA);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -591,10 +605,15 @@ k_ent_cost(EntArgs a) {
     __syncwarp();
     const u32 g = gw + ln;
     if (g >= G) continue;
-    const u16 *e = reinterpret_cast<const u16 *>(rows[wid]) + ln * B2_GROUP_SIZE;
+    const u32 *e2 = rows[wid] + ln * (B2_GROUP_SIZE / 2);            // two entries per word
     const u32 D = gd[g];
     unsigned long long acc = 0;
-    for (u32 k = 0; k < D; k++) { const u32 v = e[k]; acc += lenpack[v & 511u] * (unsigned long long)(v >> 9); }
+    for (u32 k = 0; k + 1 < D; k += 2) {
+      const u32 v = e2[k >> 1];
+      acc += lenpack[v & 511u] * (unsigned long long)((v >> 9) & 127u);
+      acc += lenpack[(v >> 16) & 511u] * (unsigned long long)(v >> 25);
+    }
+    if (D & 1u) { const u32 v = e2[D >> 1] & 0xFFFFu; acc += lenpack[v & 511u] * (unsigned long long)(v >> 9); }
     // Only cost differences matter to the reclassification, and a coder 7 or more bits above the
     // cheapest can never win (places cost 1..6, :683-695): keep six clipped excesses in 4-bit fields
     // (coders beyond ec get 7 and, in the sweep, place 7).
@@ -836,11 +855,20 @@ int b2k_entropy(cudaStream_t st, B2Job *d_jobs, u32 n_jobs, u32 max_groups_per_j
   if (max_alpha < 2) max_alpha = 2;
   if (max_alpha > HSTRIDE) max_alpha = HSTRIDE;
   const size_t qs_smem = ((size_t)max_alpha + 16) * 32 * 4;
+  const size_t pm_smem = (size_t)PM_WARPS * ll_scratch_words(max_alpha) * 4;
   const int n_triples = level == 9 ? 20 : 5;
   k_group_keys<<<n_jobs, 256, 0, st>>>(d_jobs, d_mtf, d_rank3, d_rank4);
   k_group_hist<<<n_jobs, 256, 0, st>>>(d_jobs, d_mtf, d_ghist, d_gdist);
-  size_t sort_smem = ((size_t)max_groups_per_job + 2) * 4;
-  k_rank_sort<<<n_jobs * 2, 32, sort_smem, st>>>(d_jobs, d_rank3, d_rank4);
+  // small blocks (the four parts, segments, archive entries) do not pay for the shared memory of a full block
+  {
+    u32 lo = 0;
+    for (u32 hi = 2304; lo < max_groups_per_job; hi *= 2) {
+      const u32 top = hi >= max_groups_per_job ? max_groups_per_job : hi;
+      k_rank_sort<<<n_jobs * 2, 32, ((size_t)top + 2) * 4, st>>>(d_jobs, d_rank3, d_rank4, lo, top);
+      *launches += 1;
+      lo = top;
+    }
+  }
   EntArgs a;
   a.jobs = d_jobs; a.mtf = d_mtf; a.ghist = d_ghist; a.gdist = d_gdist; a.rank3 = d_rank3; a.rank4 = d_rank4; a.sel = d_sel; a.selprev = d_selprev;
   a.gpack = d_gpack; a.gselcost = d_gselcost; a.hist = d_hist; a.leaves = d_leaves; a.wl = d_wl; a.wl_count = d_activated + 1; a.pl_count = d_activated + 2; a.wl_off = d_wl + (size_t)n_jobs * B2_N_TRIPLES * B2_MAX_CODERS + 32;
@@ -868,7 +896,7 @@ int b2k_entropy(cudaStream_t st, B2Job *d_jobs, u32 n_jobs, u32 max_groups_per_j
       } else {
         k_ent_qsort<<<(nq + 31) / 32, 32, qs_smem, st>>>(a, nq, max_alpha, 0, HSTRIDE);
       }
-      k_ent_pm<<<(nq + PM_WARPS - 1) / PM_WARPS, 32 * PM_WARPS, 0, st>>>(a, nq);
+      k_ent_pm<<<(nq + PM_WARPS - 1) / PM_WARPS, 32 * PM_WARPS, pm_smem, st>>>(a, nq, max_alpha);
       k_ent_cost<<<grid, 256, 0, st>>>(a);
       *launches += 7;
       if (it < 10) { k_ent_sweep<<<(np + 31) / 32, 32, 0, st>>>(a); *launches += 1; }
