@@ -121,34 +121,7 @@ k_scan_jobs(const B2SortJob *__restrict__ sj, u32 *__restrict__ jobhist) {
   h[threadIdx.x] = base;
 }
 
-// The scatter has its own tile geometry (env-free compile-time choice): larger tiles give longer output
-// runs per digit and fewer look-back states.
-#ifndef SC_THREADS
-#define SC_THREADS 512
-#endif
-#define SC_ITEMS 8
-#define SC_TILE (SC_THREADS * SC_ITEMS)
-#define SC_WARPS (SC_THREADS / 32)
-#define SC_WCHUNK (32 * SC_ITEMS)
-#define SC_MINCTAS (1536 / SC_THREADS)
-// ---- stable scatter of one digit ---------------------------------------------------------------
-struct ScatterSmem {
-  u64 keys[SC_TILE];
-  u32 vals[SC_TILE];
-  u32 warp_cnt[SC_WARPS][256];
-  u32 tile_start[256];
-  u32 g_off[256];
-  u32 scan[40];
-};
-
-// Tile states of the decoupled look-back: [31:30] 1 = this tile's count, 2 = count of this tile and all
-// tiles of the block before it; [29:22] pass tag (states of other passes read as "not there yet");
-// [21:0] the count (a block has at most 1 125 000 rows).
-#define LB_AGG 0x40000000u
-#define LB_INC 0x80000000u
-// tile states are single self-describing words: relaxed device-scope accesses are all that is needed
-__device__ __forceinline__ void lb_store(u32 *p, u32 v) { asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
-__device__ __forceinline__ u32 lb_load(const u32 *p) { u32 v; asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+#include "b2_scatter2.cuh"   // tile geometry, shared-memory layout and look-back states of the scatter; k_scatter2
 
 __global__ void __launch_bounds__(SC_THREADS, SC_MINCTAS)
 k_scatter(const B2SortTileRR *__restrict__ tiles, const B2Job *__restrict__ jobs,
@@ -287,6 +260,21 @@ k_scatter(const B2SortTileRR *__restrict__ tiles, const B2Job *__restrict__ jobs
       keys_out[dst] = kk;
       vals_out[dst] = S.vals[q];
     }
+  }
+}
+
+typedef void (*sc_kernel_t)(const B2SortTileRR *, const B2Job *, const u64 *, const u32 *, u64 *, u32 *, int, u32 *, const u32 *, u32 *, u32);
+// B2GPU_SCATTER = 1: round 1's k_scatter; 2 (default): k_scatter2, ballots, three CTAs per SM; 22: two CTAs;
+// 3 / 32: match.any; 24: two CTAs, keys loaded once and kept in registers; 34: the same with match.any
+static sc_kernel_t sc_pick(int v) {
+  switch (v) {
+    case 1: return k_scatter;
+    case 22: return k_scatter2<2, 0>;
+    case 3: return k_scatter2<3, SC2_MATCHANY>;
+    case 32: return k_scatter2<2, SC2_MATCHANY>;
+    case 24: return k_scatter2<2, SC2_EARLY>;
+    case 34: return k_scatter2<2, SC2_EARLY | SC2_MATCHANY>;
+    default: return k_scatter2<3, 0>;
   }
 }
 
@@ -492,8 +480,11 @@ struct EvPair { cudaEvent_t a, b; };
 // job_n[k] = post-RLE1 size of block job_ids[k]; the device copies have na == n on entry.
 int b2k_bwt_batch(B2SortCtx *cx, cudaStream_t st, B2Job *d_jobs, const std::vector<u32> &job_ids,
                   const std::vector<u32> &job_n, const u8 *d_text, u8 *d_bwt) {
+  int sc_variant = 2;
+  if (const char *e = getenv("B2GPU_SCATTER")) sc_variant = atoi(e);
+  const sc_kernel_t sc_kernel = sc_pick(sc_variant);
   // per device and cheap; set on every call so that handles on several devices / threads all have it
-  B2_CUDA_CHECK(cudaFuncSetAttribute(k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
+  B2_CUDA_CHECK(cudaFuncSetAttribute(sc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
   std::vector<B2SortTile> tiles;
   std::vector<B2SortTileRR> tiles_rr;
   size_t rr_group = 128;
@@ -542,8 +533,8 @@ int b2k_bwt_batch(B2SortCtx *cx, cudaStream_t st, B2Job *d_jobs, const std::vect
     const u32 tag = (pass_no & 255u) << 22;
     EvPair ev{nullptr, nullptr};
     if (cx->timing) { cudaEventCreate(&ev.a); cudaEventCreate(&ev.b); cudaEventRecord(ev.a, st); }
-    k_scatter<<<(u32)tiles_rr.size(), SC_THREADS, sizeof(ScatterSmem), st>>>(cx->d_tiles_rr, d_jobs, kA, vA, kB, vB, shift, cx->d_hist, cx->d_digit_base,
-                                                           cx->d_ticket, tag);
+    sc_kernel<<<(u32)tiles_rr.size(), SC_THREADS, sizeof(ScatterSmem), st>>>(cx->d_tiles_rr, d_jobs, kA, vA, kB, vB, shift, cx->d_hist, cx->d_digit_base,
+                                                                               cx->d_ticket, tag);
     pass_no++;
     if (cx->timing) { cudaEventRecord(ev.b, st); evs.push_back(ev); }
     B2_CUDA_CHECK(cudaGetLastError());
