@@ -110,3 +110,9 @@ inline void emu_launch(unsigned grid, unsigned block, size_t smem_bytes, unsigne
   for (unsigned i = 0; i < window; i++) ws.emplace_back(worker);
   for (auto &x : ws) x.join();
 }
+
+inline bool __any_sync(unsigned, bool p) { return __ballot_sync(0xffffffffu, p) != 0u; }
+inline uint32_t atomicOr(uint32_t *p, uint32_t v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
+inline uint32_t atomicAdd(uint32_t *p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+using std::max;
+using std::min;

@@ -442,108 +442,10 @@ k_ent_qsort(EntArgs a, u32 nq, u32 alpha_max, u32 n_lo, u32 n_hi) {
   for (u32 e = 0; e < nmax; e++) g[e * 32 + l] = s[e * 32 + l];
 }
 
-// ---------------------------------------------------------------------------------------------
-// Length-limited code lengths (huffman-encoding-length_limited_coding.adb:46-280).
-//
-// The reference runs the *boundary* package-merge (lazy, recursive, :131-163).  What it computes is
-// the classic package-merge: list 1 = the sorted leaves; list l+1 = merge (leaves, pair sums of
-// consecutive items of list l); take the first 2n-2 items of the last list, then walk down: if p of
-// the first k items of a list are packages, the first 2p items of the list below are taken; a leaf
-// gets one bit per list in which it is taken (Extract_Bit_Lengths, :180-189).  The boundary
-// version's tie rule "new leaf iff sum > leaf weight" (:151) means a package goes BEFORE a leaf of
-// equal weight.  Each list is built here by one warp as a parallel merge (binary searches); the
-// equality of both formulations is checked on the CPU against the oracle's literal restatement
-// (tests/test_oracle.py::test_forward_package_merge_equals_boundary).
-// ---------------------------------------------------------------------------------------------
-#define LL_MAXBITS 17
-#define LL_MAXITEMS (2 * B2_MAX_ALPHA)
-#define LL_BITWORDS 17
-#define PM_WARPS 4
-
-// Scratch of one warp, carved out of dynamic shared memory sized by the largest alphabet of the batch (a text
-// batch needs 4.4 KB per warp instead of 7.3 KB: more warps per SM for a latency-bound kernel).
-struct LLScratch {
-  u32 *leaf;                               // [alpha + 2]     (weight << 9) | symbol, sorted
-  u32 *lvl[2];                             // [2 * alpha]     merged weights of two consecutive lists
-  u32 *pk;                                 // [alpha + 2]     pair sums of the list below
-  u32 (*pkgbits)[LL_BITWORDS];             // [LL_MAXBITS]    bit p set <=> item p of the list is a package
-};
-__host__ __device__ inline u32 ll_scratch_words(u32 alpha) { return (alpha + 2) * 2 + 4 * alpha + LL_MAXBITS * LL_BITWORDS; }
-__device__ __forceinline__ LLScratch ll_scratch_at(u32 *base, u32 alpha) {
-  LLScratch S;
-  S.leaf = base; base += alpha + 2;
-  S.lvl[0] = base; base += 2 * alpha;
-  S.lvl[1] = base; base += 2 * alpha;
-  S.pk = base; base += alpha + 2;
-  S.pkgbits = reinterpret_cast<u32 (*)[LL_BITWORDS]>(base);
-  return S;
-}
-
-__device__ void ll_package_merge_warp(LLScratch &S, int ns, int max_bits, u8 *lens) {
-  const u32 l = lane_id();
-  const int need = 2 * ns - 2;
-  for (int i = l; i < ns; i += 32) S.lvl[0][i] = S.leaf[i] >> 9;
-  if (l < LL_BITWORDS) S.pkgbits[0][l] = 0;
-  int len_prev = ns;
-  __syncwarp();
-  for (int lev = 1; lev < max_bits; lev++) {
-    const u32 *prev = S.lvl[(lev - 1) & 1];
-    u32 *cur = S.lvl[lev & 1];
-    const int npk = len_prev >> 1;
-    if (l < LL_BITWORDS) S.pkgbits[lev][l] = 0;
-    for (int b = l; b < npk; b += 32) S.pk[b] = prev[2 * b] + prev[2 * b + 1];      // the packages of the list below
-    __syncwarp();
-    bool changed = false;
-    for (int a = l; a < ns; a += 32) {
-      const u32 w = S.leaf[a] >> 9;
-      int lo = 0, hi = npk;                                 // packages with sum <= w go before this leaf
-      while (lo < hi) { int mid = (lo + hi) >> 1; if (S.pk[mid] <= w) lo = mid + 1; else hi = mid; }
-      const int pos = a + lo;
-      if (pos < need) { changed |= (pos >= len_prev) || prev[pos] != w; cur[pos] = w; }
-    }
-    for (int b = l; b < npk; b += 32) {
-      const u32 pk = S.pk[b];
-      int lo = 0, hi = ns;                                  // leaves with weight < sum go before this package
-      while (lo < hi) { int mid = (lo + hi) >> 1; if ((S.leaf[mid] >> 9) < pk) lo = mid + 1; else hi = mid; }
-      const int pos = b + lo;
-      if (pos < need) { changed |= (pos >= len_prev) || prev[pos] != pk; cur[pos] = pk; atomicOr(&S.pkgbits[lev][pos >> 5], 1u << (pos & 31)); }
-    }
-    const int len_cur = min(need, ns + npk);
-    changed = __any_sync(0xffffffffu, changed) || len_cur != len_prev;
-    len_prev = len_cur;
-    __syncwarp();
-    if (!changed) {
-      // the list repeats the one below: every list above is built from the same packages, hence equal
-      // to this one, items and package flags alike
-      if (l < LL_BITWORDS) { const u32 v = S.pkgbits[lev][l]; for (int q = lev + 1; q < max_bits; q++) S.pkgbits[q][l] = v; }
-      __syncwarp();
-      break;
-    }
-  }
-  // walk down from the last list
-  u32 cnt[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-  int k = need;
-  for (int lev = max_bits - 1; lev >= 0; lev--) {
-    const u32 wv = (l < LL_BITWORDS) ? S.pkgbits[lev][l] : 0u;
-    const int lo = (int)l * 32;
-    const u32 msk = (k >= lo + 32) ? 0xFFFFFFFFu : (k <= lo ? 0u : ((1u << (k - lo)) - 1u));
-    u32 p = __popc(wv & msk);
-#pragma unroll
-    for (int o = 16; o; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
-    const int a = k - (int)p;                               // leaves taken in this list
-#pragma unroll
-    for (int j = 0; j < 9; j++) cnt[j] += ((int)l + 32 * j < a);
-    k = 2 * (int)p;
-  }
-#pragma unroll
-  for (int j = 0; j < 9; j++) {
-    const int i = (int)l + 32 * j;
-    if (i < ns) lens[S.leaf[i] & 511u] = (u8)cnt[j];
-  }
-}
+#include "b2_pm.cuh"    // length-limited code lengths: the package-merge of one warp
 
 __global__ void __launch_bounds__(32 * PM_WARPS)
-k_ent_pm(EntArgs a, u32 nq, u32 alpha_max) {
+k_ent_pm(EntArgs a, u32 nq, u32 alpha_max, int variant) {
   extern __shared__ u32 pm_smem[];
   const u32 w = warp_id(), l = lane_id();
   const u32 slot = blockIdx.x * PM_WARPS + w;
@@ -557,7 +459,9 @@ k_ent_pm(EntArgs a, u32 nq, u32 alpha_max) {
   const int ns = (int)a.jobs[jb].n_used + 2;
   for (int e = l; e < ns; e += 32) S.leaf[e] = a.leaves[leaf_index(slot, (u32)e)];
   __syncwarp();
-  ll_package_merge_warp(S, ns, max_len, a.lens + ((size_t)p * B2_MAX_CODERS + c) * B2_MAX_ALPHA);
+  u8 *lens = a.lens + ((size_t)p * B2_MAX_CODERS + c) * B2_MAX_ALPHA;
+  if (variant == 0) ll_package_merge_warp(S, ns, max_len, lens);
+  else ll_package_merge_warp_mp(S, ns, max_len, lens);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -856,6 +760,8 @@ int b2k_entropy(cudaStream_t st, B2Job *d_jobs, u32 n_jobs, u32 max_groups_per_j
   if (max_alpha > HSTRIDE) max_alpha = HSTRIDE;
   const size_t qs_smem = ((size_t)max_alpha + 16) * 32 * 4;
   const size_t pm_smem = (size_t)PM_WARPS * ll_scratch_words(max_alpha) * 4;
+  int pm_variant = 1;                    // B2GPU_PM = 0: lists merged by binary searches (round 1); 1: by a merge path
+  if (const char *e = getenv("B2GPU_PM")) pm_variant = atoi(e) ? 1 : 0;
   const int n_triples = level == 9 ? 20 : 5;
   k_group_keys<<<n_jobs, 256, 0, st>>>(d_jobs, d_mtf, d_rank3, d_rank4);
   k_group_hist<<<n_jobs, 256, 0, st>>>(d_jobs, d_mtf, d_ghist, d_gdist);
@@ -896,7 +802,7 @@ int b2k_entropy(cudaStream_t st, B2Job *d_jobs, u32 n_jobs, u32 max_groups_per_j
       } else {
         k_ent_qsort<<<(nq + 31) / 32, 32, qs_smem, st>>>(a, nq, max_alpha, 0, HSTRIDE);
       }
-      k_ent_pm<<<(nq + PM_WARPS - 1) / PM_WARPS, 32 * PM_WARPS, pm_smem, st>>>(a, nq, max_alpha);
+      k_ent_pm<<<(nq + PM_WARPS - 1) / PM_WARPS, 32 * PM_WARPS, pm_smem, st>>>(a, nq, max_alpha, pm_variant);
       k_ent_cost<<<grid, 256, 0, st>>>(a);
       *launches += 7;
       if (it < 10) { k_ent_sweep<<<(np + 31) / 32, 32, 0, st>>>(a); *launches += 1; }
