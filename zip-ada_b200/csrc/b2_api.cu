@@ -328,6 +328,7 @@ int run_batch(b2_encoder *e, Workspace *w, const u8 *d_in, std::vector<B2Job> &j
       for (u32 j = 0; j < J; j++) max_used = std::max(max_used, w->batch_jobs[j].n_used);
       cx.sym_bits = 1;
       while ((1u << cx.sym_bits) < max_used) cx.sym_bits++;
+      cx.max_used = max_used;
     }
     if (e->timing >= 1) cudaEventRecord(w->ev_sort[0], st);
     int rc = b2k_bwt_batch(&cx, st, w->d_jobs.p, ids, ns, w->d_text.p, w->d_bwt.p);

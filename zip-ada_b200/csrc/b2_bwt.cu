@@ -37,7 +37,7 @@
 // distinct bytes sorts round 0 in `bits` radix passes instead of 8.  bits = 8 keeps the bytes as they are.
 __global__ void __launch_bounds__(ST_THREADS)
 k_keys0(const B2SortTile *__restrict__ tiles, const B2Job *__restrict__ jobs, const u8 *__restrict__ text,
-        u64 *__restrict__ keys, u32 *__restrict__ vals, int bits) {
+        u64 *__restrict__ keys, u32 *__restrict__ vals, int bits, u32 base, u32 q8) {
   __shared__ u8 code[256];
   const B2SortTile tl = tiles[blockIdx.x];
   const B2Job &job = jobs[tl.job];
@@ -46,7 +46,7 @@ k_keys0(const B2SortTile *__restrict__ tiles, const B2Job *__restrict__ jobs, co
   {
     const u32 t = threadIdx.x, wd = t >> 5;
     u32 c = t;
-    if (bits < 8) {
+    if (bits < 8 || base) {
       c = __popc(job.in_use[wd] & ((1u << (t & 31u)) - 1u));
       for (u32 q = 0; q < wd; q++) c += __popc(job.in_use[q]);
     }
@@ -58,7 +58,18 @@ k_keys0(const B2SortTile *__restrict__ tiles, const B2Job *__restrict__ jobs, co
     u32 i = tl.start + threadIdx.x + k * ST_THREADS;
     if (i < n) {
       u64 key = 0;
-      if (i + 8 <= n) {
+      if (base) {
+        // seven characters in radix `base` and the eighth cut down to q8 order-preserving buckets: fewer than
+        // 2^56 values, seven passes.  Equal keys share (at least) seven characters: the doubling goes on from 7.
+        u32 p = i, c8 = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const u32 cj = code[tx[p]];
+          if (j < 7) key = key * base + cj; else c8 = cj;
+          p++; if (p >= n) p = 0;
+        }
+        key = key * q8 + (c8 * q8) / base;
+      } else if (i + 8 <= n) {
 #pragma unroll
         for (int j = 0; j < 8; j++) key = (key << bits) | code[tx[i + j]];
       } else {
@@ -382,7 +393,9 @@ k_ranks(const B2SortTile *__restrict__ tiles, const B2Job *__restrict__ jobs, co
       const u32 headslot = slot_in ? slot_in[off + (u32)headc] : (u32)headc;
       const u32 v = vals[off + i];
       sa_full[off + slot] = v;
-      rank[off + v] = headslot;
+      // later rounds: the key carries the class the row came from (k_keys); a row that stays in the first part of
+      // its class keeps its rank, and the random store is skipped
+      if (!slot_in || headslot != (u32)(kp[i] >> 20)) rank[off + v] = headslot;
       if ((am >> l) & 1u) {
         const u32 o = off + cbase + __popc(am & lt_mask);
         slot_out[o] = slot;
@@ -572,14 +585,29 @@ int b2k_bwt_batch(B2SortCtx *cx, cudaStream_t st, B2Job *d_jobs, const std::vect
     cx->stats.sorted_elems_round0 += el;
   }
   const int sym_bits = (cx->sym_bits >= 1 && cx->sym_bits <= 8) ? cx->sym_bits : 8;   // 8 characters of sym_bits bits = sym_bits passes
-  k_keys0<<<(u32)tiles.size(), ST_THREADS, 0, st>>>(cx->d_tiles, d_jobs, d_text, kA, vA, sym_bits);
+  // Alphabets of more than 128 bytes (sym_bits = 8): seven characters in radix B = the largest alphabet of the batch plus
+  // the eighth cut down to floor (2^56 / B^7) buckets make a key below 2^56: seven passes instead of eight, and the
+  // doubling goes on from a prefix of 7 (B2GPU_R0 = 8 keeps the eight full characters).
+  u32 r0_base = 0, r0_q8 = 0;
+  {
+    int r0 = 7;
+    if (const char *e = getenv("B2GPU_R0")) r0 = atoi(e);
+    if (r0 == 7 && sym_bits == 8 && cx->max_used > 128 && cx->max_used <= 256) {
+      u64 b7 = 1;
+      for (int j = 0; j < 7; j++) b7 *= cx->max_used;                 // <= 2^56
+      r0_base = cx->max_used;
+      r0_q8 = (u32)((1ull << 56) / b7);                                // >= 1
+    }
+  }
+  const int r0_passes = r0_base ? 7 : sym_bits;
+  k_keys0<<<(u32)tiles.size(), ST_THREADS, 0, st>>>(cx->d_tiles, d_jobs, d_text, kA, vA, sym_bits, r0_base, r0_q8);
   cx->stats.launches += 1;
   if ((rc = upload_rr())) return rc;
-  if ((rc = round_hist(sym_bits))) return rc;
-  for (int p = 0; p < sym_bits; p++) if ((rc = radix_pass(8 * p))) return rc;
+  if ((rc = round_hist(r0_passes))) return rc;
+  for (int p = 0; p < r0_passes; p++) if ((rc = radix_pass(8 * p))) return rc;
   if ((rc = ranks(true))) return rc;
   cx->stats.rounds++;
-  u64 reflect = 8;
+  u64 reflect = r0_base ? 7 : 8;          // characters that rows of one class are known to share
   for (;;) {
     // split finished / unfinished
     std::vector<u32> fin_ids, fin_n, go_ids, go_n, go_na;
