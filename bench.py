@@ -443,7 +443,9 @@ def main():
     # SURVEY 8(d) stage figure: (24 p + 12) n per round, summed = 24 * (rows moved by all passes) + 12 * (rows entering all rounds)
     stage_bytes = 24.0 * tot["scatter_elems"] + 12.0 * (tot["sort_elems_round0"] + tot["sort_elems_later"])
     stage_gbs = stage_bytes / (tot["sort_ms"] / 1000.0) / 1e9 if tot["sort_ms"] > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "k_scatter (one LSD radix pass of the BWT rotation sort: ranking, decoupled look-back and scatter in one kernel)",
+    sc_variant = os.environ.get("B2GPU_SCATTER", "2")
+    sc_name = "k_scatter" if sc_variant == "1" else "k_scatter2 (variant %s)" % sc_variant
+    roofline = {"bound": "hbm", "kernel": sc_name + ": one LSD radix pass of the BWT rotation sort (ranking, decoupled look-back and scatter in one kernel)",
                 "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                 "peak_source": peak_src, "traffic": None,
                 "traffic_note": "not measured in this run; the ncu --set full capture of the kernel is under profiles/",
