@@ -469,7 +469,7 @@ def main():
     line = {"metric": "bzip2_encode_MBps_900k", "value": round(value, 2), "unit": "MB/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(1000 * t_wall / args.steps, 2), "higher_is_better": True, "scaling": scaling_of(cfg),
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": workload_desc(cfg, n, world), "stream_bytes": n, "streams": 1, "ranks": world,
+            "config": {"workload": workload_desc(cfg, n, world), "knobs": {k: v for k, v in sorted(os.environ.items()) if k.startswith("B2GPU_")}, "stream_bytes": n, "streams": 1, "ranks": world,
                        "bytes_per_rank": [b - a for a, b in zip(bounds, bounds[1:])],
                        "l2": "inputs (>= 0.5 GiB per GPU and step) and sort state are far larger than the 126 MB L2; no flush needed"},
             "device_event_ms_per_step": round(1000 * t_dev / args.steps, 2),

@@ -1,6 +1,7 @@
 // Host emulation of k_scatter2 (zip-ada_b200/csrc/b2_scatter2.cuh) against a plain stable counting sort.
 // Test infrastructure (tests/test_emu_scatter.py builds and runs it); usage: emu_scatter <mode> <rr_group> <window> <seed> <shift_step>
-//   mode: template MODE of the kernel (bit 0 match.any, bit 1 keys loaded early)
+//   mode: 0..3 = template MODE of k_scatter2 (bit 0 match.any, bit 1 keys loaded early); 40 / 42 = k_scatter3 with tiles of
+//   4096 / 2048 rows
 // Blocks of several sizes (empty tail tiles, exactly one tile, one row, several tiles), digits of every pass
 // position, skewed and uniform digit distributions; every block must come out as the stable sort of its rows by
 // the digit, all other arena positions untouched.
@@ -32,10 +33,28 @@ static void tiles_rr(const std::vector<Block> &blocks, size_t group, std::vector
   }
 }
 
+// the same dispatch order with the self-contained tile records of k_scatter3 (build_tiles_sc of b2_bwt.cu)
+static void tiles_sc(const std::vector<Block> &blocks, size_t group, u32 sc_tile, std::vector<B2ScTile> &out) {
+  out.clear();
+  std::vector<u32> last(blocks.size(), 0xFFFFFFFFu);
+  for (size_t g0 = 0; g0 < blocks.size(); g0 += group) {
+    const size_t g1 = std::min(blocks.size(), g0 + group);
+    u32 max_nt = 0;
+    for (size_t j = g0; j < g1; j++) max_nt = std::max(max_nt, (blocks[j].n + sc_tile - 1) / sc_tile);
+    for (u32 k = 0; k < max_nt; k++)
+      for (size_t j = g0; j < g1; j++)
+        if ((blocks[j].n + sc_tile - 1) / sc_tile > k) {
+          const u32 pos = (u32)out.size(), start = k * sc_tile, cnt = std::min(sc_tile, blocks[j].n - start);
+          out.push_back(B2ScTile{(u32)j | ((cnt - 1) << 16), blocks[j].off + start, last[j], blocks[j].off});
+          last[j] = pos;
+        }
+  }
+}
+
 template <int MODE>
 static int run(size_t group, unsigned window, unsigned seed, int shift_step) {
   std::mt19937_64 rng(seed);
-  const u32 sizes[] = {1, 31, 4095, 4096, 4097, 3 * 4096, 2 * 4096 + 777, 9000, 300, 5 * 4096 + 1};
+  const u32 sizes[] = {1, 31, 4095, 4096, 4097, 3 * 4096, 2 * 4096 + 777, 9000, 300, 5 * 4096 + 1, 2047, 2048, 2049};
   std::vector<Block> blocks;
   u32 pos = 64;
   for (u32 n : sizes) { blocks.push_back(Block{n, pos}); pos += (n + 255u) & ~255u; pos += 256; }
@@ -43,8 +62,11 @@ static int run(size_t group, unsigned window, unsigned seed, int shift_step) {
   std::vector<B2Job> jobs(blocks.size());
   for (size_t j = 0; j < blocks.size(); j++) { std::memset(&jobs[j], 0, sizeof(B2Job)); jobs[j].na = blocks[j].n; jobs[j].n = blocks[j].n + 5; jobs[j].pos_off = blocks[j].off; }
   std::vector<B2SortTileRR> rr;
-  tiles_rr(blocks, group, rr);
-  std::vector<u32> state(rr.size() * 256, 0);
+  std::vector<B2ScTile> sc;
+  constexpr int THREADS3 = (MODE & 2) ? 256 : 512;           // MODE 40..47: k_scatter3; bit 1 = tiles of 2048 rows, bit 2 = rotation indices requested early
+  if (MODE >= 40) tiles_sc(blocks, group, THREADS3 * SC_ITEMS, sc); else tiles_rr(blocks, group, rr);
+  const size_t ntile = MODE >= 40 ? sc.size() : rr.size();
+  std::vector<u32> state(ntile * 256, 0);
   int bad = 0;
   u32 pass_no = 0;
   for (int shift = 0; shift < 64; shift += shift_step) {
@@ -70,9 +92,16 @@ static int run(size_t group, unsigned window, unsigned seed, int shift_step) {
       u32 lb_error = 0;
       const u32 tag = (pass_no & 255u) << 22;
       pass_no++;
-      emu_launch((unsigned)rr.size(), SC_THREADS, sizeof(ScatterSmem), window, [&]() {
-        k_scatter2<3, MODE>(rr.data(), jobs.data(), kin.data(), vin.data(), kout.data(), vout.data(), shift, state.data(), jobhist.data(), &lb_error, tag);
-      });
+      if constexpr (MODE >= 40) {
+        const u32 pfd = (shift & 8) ? 3u : 0u;                // with and without the prefetch of a later tile (a no-op here but for its addressing)
+        emu_launch((unsigned)sc.size(), THREADS3, sizeof(ScatterSmemT<THREADS3>), window, [&]() {
+          k_scatter3<THREADS3, 3, (MODE & 4) != 0>(sc.data(), kin.data(), vin.data(), kout.data(), vout.data(), shift, state.data(), jobhist.data(), &lb_error, tag, pfd);
+        });
+      } else {
+        emu_launch((unsigned)rr.size(), SC_THREADS, sizeof(ScatterSmem), window, [&]() {
+          k_scatter2<3, MODE>(rr.data(), jobs.data(), kin.data(), vin.data(), kout.data(), vout.data(), shift, state.data(), jobhist.data(), &lb_error, tag);
+        });
+      }
       if (lb_error) { printf("look-back error flag set (shift %d)\n", shift); bad++; }
       // reference: stable sort by digit per block; untouched elsewhere
       std::vector<u64> kref(total, 0x1111111111111111ull);
@@ -102,6 +131,10 @@ int main(int argc, char **argv) {
     case 0: bad = run<0>(group, window, seed, step); break;
     case 1: bad = run<SC2_MATCHANY>(group, window, seed, step); break;
     case 2: bad = run<SC2_EARLY>(group, window, seed, step); break;
+    case 40: bad = run<40>(group, window, seed, step); break;
+    case 42: bad = run<42>(group, window, seed, step); break;
+    case 44: bad = run<44>(group, window, seed, step); break;
+    case 46: bad = run<46>(group, window, seed, step); break;
     default: bad = run<SC2_EARLY | SC2_MATCHANY>(group, window, seed, step); break;
   }
   printf(bad ? "FAILED\n" : "OK\n");

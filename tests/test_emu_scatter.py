@@ -1,4 +1,4 @@
-"""k_scatter2 (the radix pass of the BWT rotation sort, zip-ada_b200/csrc/b2_scatter2.cuh) on the host: the
+"""k_scatter2 / k_scatter3 (the radix pass of the BWT rotation sort, zip-ada_b200/csrc/b2_scatter2.cuh) on the host: the
 kernel source is compiled with g++ against tests/emu/cuda_emu.h (one OS thread per CUDA thread, barriers for
 __syncthreads / __syncwarp / the warp collectives) and must produce, for blocks of many shapes, the stable sort of
 every block by the digit - with the blocks of the grid run one at a time (the look-back always finds its
@@ -23,7 +23,10 @@ def emu(tmp_path_factory):
 
 
 # (kernel MODE, blocks interleaved in the dispatch order, resident blocks, seed, shift step)
-@pytest.mark.parametrize("args", [(0, 128, 1, 1, 8), (0, 1, 3, 2, 24), (1, 2, 3, 3, 24), (2, 128, 2, 4, 24), (3, 1, 3, 5, 24)])
-def test_scatter2_emulated(emu, args):
+# modes 0..3: k_scatter2 (bit 0 match.any, bit 1 keys loaded early); 40..47: k_scatter3 (bit 1 tiles of 2048 rows, bit 2 rotation
+# indices requested early; the prefetch distance alternates between 0 and 3 inside the run)
+@pytest.mark.parametrize("args", [(0, 128, 1, 1, 24), (0, 1, 3, 2, 24), (1, 2, 3, 3, 24), (2, 128, 2, 4, 24), (3, 1, 3, 5, 24),
+                                  (40, 128, 1, 6, 8), (40, 1, 3, 7, 24), (42, 2, 4, 8, 24), (44, 1, 3, 9, 24), (46, 128, 2, 10, 24)])
+def test_scatter_emulated(emu, args):
     r = subprocess.run([emu] + [str(a) for a in args], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout[-2000:]

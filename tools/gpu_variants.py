@@ -23,7 +23,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 OUT = os.path.join(ROOT, "gpurun_out")
 LOG = os.path.join(OUT, "variants.jsonl")
-KNOBS = ("B2GPU_SCATTER", "B2GPU_PM", "B2GPU_R0", "B2GPU_RR_GROUP", "B2GPU_PIPELINE", "B2GPU_BATCH_POSITIONS")
+KNOBS = ("B2GPU_SCATTER", "B2GPU_PM", "B2GPU_R0", "B2GPU_RR_GROUP", "B2GPU_SC_PFD", "B2GPU_PIPELINE", "B2GPU_BATCH_POSITIONS")
 
 
 def log(rec):
@@ -114,41 +114,49 @@ def main():
     def better(a, b):
         return a.get("ok") and "ms_per_step" in a and (not (b and b.get("ok")) or a["ms_per_step"] < b["ms_per_step"])
 
-    # round 1's path as the control, then the package-merge by merge path and the seven-pass round 0 one at a time
-    control = {"B2GPU_SCATTER": 1, "B2GPU_PM": 0, "B2GPU_R0": 8}
-    best = run(control)
-    if not best.get("ok"):
-        print("the control configuration did not produce the golden stream")
-        best = None
-    base = dict(control)
-    for knob, v in (("B2GPU_PM", 1), ("B2GPU_R0", 7)):
-        r = run(dict(control, **{knob: v}))
-        if r.get("ok") and (best is None or r["ms_per_step"] < best["ms_per_step"] * 1.003):
-            base[knob] = v
-    for sc in (1, 2, 22, 24, 3, 32, 34):
-        r = run(dict(base, B2GPU_SCATTER=sc))
+    mode = sys.argv[3] if len(sys.argv) > 3 else "full"
+    best = None
+    if mode == "full":
+        # round 1's path as the control, then the package-merge by merge path and the seven-pass round 0 one at a time
+        control = {"B2GPU_SCATTER": 1, "B2GPU_PM": 0, "B2GPU_R0": 8}
+        best = run(control)
+        if not best.get("ok"):
+            print("the control configuration did not produce the golden stream")
+            best = None
+        base = dict(control)
+        for knob, v in (("B2GPU_PM", 1), ("B2GPU_R0", 7)):
+            r = run(dict(control, **{knob: v}))
+            if r.get("ok") and (best is None or r["ms_per_step"] < best["ms_per_step"] * 1.003):
+                base[knob] = v
+        scatters = (1, 2, 22, 24, 3, 32, 34, 40, 41, 43, 45, 47)
+    else:
+        # second run: the package-merge and round-0 knobs are settled (profiles/r02b_variants.jsonl); k_scatter2 against k_scatter3
+        base = {"B2GPU_PM": 1, "B2GPU_R0": 7}
+        scatters = (2, 40, 41, 42, 43, 45, 47, (41, 148), (43, 296))
+    for sc in scatters:
+        r = run(dict(base, B2GPU_SCATTER=sc) if isinstance(sc, int) else dict(base, B2GPU_SCATTER=sc[0], B2GPU_SC_PFD=sc[1]))
         if better(r, best):
             best = r
     if best is None:
         print("no variant produced the golden stream")
         return 1
     env = dict(best["env"])
-    for extra in ({"B2GPU_RR_GROUP": 64}, {"B2GPU_RR_GROUP": 256}, {"B2GPU_RR_GROUP": 32}):
+    sc = env.get("B2GPU_SCATTER")
+    extras = [{"B2GPU_RR_GROUP": 64}, {"B2GPU_RR_GROUP": 256}]
+    if sc in (41, 43, 45, 47) and "B2GPU_SC_PFD" not in env:
+        d0 = 592 if sc in (43, 47) else 296
+        extras += [{"B2GPU_SC_PFD": d0 * 2}]
+    for extra in extras:
         r = run(dict(env, **extra))
         if better(r, best):
             best = r
-    env = dict(best["env"])
-    # two batches in flight, half the batch each (the same device memory); against the same batch size alone
-    half = 805306368
-    r1 = run(dict(env, B2GPU_BATCH_POSITIONS=half))
-    r2 = run(dict(env, B2GPU_BATCH_POSITIONS=half, B2GPU_PIPELINE=2))
-    for r in (r1, r2):
-        if better(r, best):
-            best = r
-    # the two-CTA scatter leaves room for the latency-bound kernels of the other batch
-    if best["env"].get("B2GPU_SCATTER") not in (22, 24):
-        for sc in (22, 24):
-            r = run(dict(env, B2GPU_SCATTER=sc, B2GPU_BATCH_POSITIONS=half, B2GPU_PIPELINE=2))
+    if mode == "full":
+        env = dict(best["env"])
+        # two batches in flight, half the batch each (the same device memory); against the same batch size alone
+        half = 805306368
+        r1 = run(dict(env, B2GPU_BATCH_POSITIONS=half))
+        r2 = run(dict(env, B2GPU_BATCH_POSITIONS=half, B2GPU_PIPELINE=2))
+        for r in (r1, r2):
             if better(r, best):
                 best = r
     with open(os.path.join(OUT, "best_env.sh"), "w") as f:

@@ -329,6 +329,7 @@ int run_batch(b2_encoder *e, Workspace *w, const u8 *d_in, std::vector<B2Job> &j
       cx.sym_bits = 1;
       while ((1u << cx.sym_bits) < max_used) cx.sym_bits++;
       cx.max_used = max_used;
+      cx.h_jobs = w->batch_jobs.data();
     }
     if (e->timing >= 1) cudaEventRecord(w->ev_sort[0], st);
     int rc = b2k_bwt_batch(&cx, st, w->d_jobs.p, ids, ns, w->d_text.p, w->d_bwt.p);

@@ -488,16 +488,55 @@ static void build_tiles_rr(const std::vector<B2SortJob> &sj, std::vector<B2SortT
   }
 }
 
+// the same order for k_scatter3, whose tile records are self-contained (first row in the arena, rows, block offset)
+static void build_tiles_sc(const std::vector<u32> &ids, const std::vector<u32> &nas, const B2Job *h_jobs, std::vector<B2ScTile> &out,
+                           size_t group, u32 sc_tile) {
+  out.clear();
+  std::vector<u32> jid, jn;
+  for (size_t k = 0; k < ids.size(); k++) if (nas[k] > 0) { jid.push_back(ids[k]); jn.push_back(nas[k]); }
+  std::vector<u32> last(jid.size(), 0xFFFFFFFFu);
+  for (size_t g0 = 0; g0 < jid.size(); g0 += group) {
+    const size_t g1 = std::min(jid.size(), g0 + group);
+    u32 max_nt = 0;
+    for (size_t j = g0; j < g1; j++) max_nt = std::max(max_nt, (jn[j] + sc_tile - 1) / sc_tile);
+    for (u32 k = 0; k < max_nt; k++)
+      for (size_t j = g0; j < g1; j++)
+        if ((jn[j] + sc_tile - 1) / sc_tile > k) {
+          const u32 pos = (u32)out.size(), start = k * sc_tile, cnt = std::min(sc_tile, jn[j] - start), off = h_jobs[jid[j]].pos_off;
+          out.push_back(B2ScTile{jid[j] | ((cnt - 1) << 16), off + start, last[j], off});
+          last[j] = pos;
+        }
+  }
+}
+
 struct EvPair { cudaEvent_t a, b; };
 
 // job_n[k] = post-RLE1 size of block job_ids[k]; the device copies have na == n on entry.
 int b2k_bwt_batch(B2SortCtx *cx, cudaStream_t st, B2Job *d_jobs, const std::vector<u32> &job_ids,
                   const std::vector<u32> &job_n, const u8 *d_text, u8 *d_bwt) {
+  // B2GPU_SCATTER: see sc_pick; 40..47 = k_scatter3: bit 0 = L2 prefetch of the tile B2GPU_SC_PFD places ahead, bit 1 = tiles of
+  // 2048 rows (six CTAs per SM) instead of 4096, bit 2 = rotation indices requested before the scan
   int sc_variant = 2;
   if (const char *e = getenv("B2GPU_SCATTER")) sc_variant = atoi(e);
+  const bool sc3 = sc_variant >= 40 && sc_variant <= 47;
+  const u32 sc_tile = (sc3 && (sc_variant & 2)) ? 2048u : (u32)SC_TILE;
+  const bool sc_vearly = sc3 && (sc_variant & 4);
+  u32 sc_pfd = 0;
+  if (sc3 && (sc_variant & 1)) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    sc_pfd = (u32)sms * (sc_tile == 2048u ? 4u : 2u);        // two thirds of the tiles resident on the device
+    if (const char *e = getenv("B2GPU_SC_PFD")) { long v = atol(e); if (v >= 1 && v < (1 << 20)) sc_pfd = (u32)v; }
+  }
   const sc_kernel_t sc_kernel = sc_pick(sc_variant);
+  typedef void (*sc3_kernel_t)(const B2ScTile *, const u64 *, const u32 *, u64 *, u32 *, int, u32 *, const u32 *, u32 *, u32, u32);
+  const sc3_kernel_t sc3_kernel = sc_tile == 2048u ? (sc_vearly ? k_scatter3<256, 6, true> : k_scatter3<256, 6, false>)
+                                                   : (sc_vearly ? k_scatter3<512, 3, true> : k_scatter3<512, 3, false>);
+  const size_t sc3_smem = sc_tile == 2048u ? sizeof(ScatterSmemT<256>) : sizeof(ScatterSmemT<512>);
   // per device and cheap; set on every call so that handles on several devices / threads all have it
-  B2_CUDA_CHECK(cudaFuncSetAttribute(sc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
+  if (!sc3) B2_CUDA_CHECK(cudaFuncSetAttribute(sc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
+  else B2_CUDA_CHECK(cudaFuncSetAttribute(sc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc3_smem));
+  std::vector<B2ScTile> tiles_sc;
   std::vector<B2SortTile> tiles;
   std::vector<B2SortTileRR> tiles_rr;
   size_t rr_group = 128;
@@ -519,6 +558,13 @@ int b2k_bwt_batch(B2SortCtx *cx, cudaStream_t st, B2Job *d_jobs, const std::vect
     return 0;
   };
   auto upload_rr = [&]() -> int {
+    if (sc3) {
+      build_tiles_sc(ids, nas, cx->h_jobs, tiles_sc, rr_group, sc_tile);
+      if (tiles_sc.size() > cx->max_tiles) { b2_set_error(__FILE__, __LINE__, "sort workspace too small"); return 11; }
+      static_assert(sizeof(B2ScTile) == sizeof(B2SortTileRR), "the two tile records share a buffer");
+      B2_CUDA_CHECK(cudaMemcpyAsync(cx->d_tiles_rr, tiles_sc.data(), tiles_sc.size() * sizeof(B2ScTile), cudaMemcpyHostToDevice, st));
+      return 0;
+    }
     build_tiles_rr(sj, tiles_rr, rr_group);
     B2_CUDA_CHECK(cudaMemcpyAsync(cx->d_tiles_rr, tiles_rr.data(), tiles_rr.size() * sizeof(B2SortTileRR), cudaMemcpyHostToDevice, st));
     return 0;
@@ -546,8 +592,12 @@ int b2k_bwt_batch(B2SortCtx *cx, cudaStream_t st, B2Job *d_jobs, const std::vect
     const u32 tag = (pass_no & 255u) << 22;
     EvPair ev{nullptr, nullptr};
     if (cx->timing) { cudaEventCreate(&ev.a); cudaEventCreate(&ev.b); cudaEventRecord(ev.a, st); }
-    sc_kernel<<<(u32)tiles_rr.size(), SC_THREADS, sizeof(ScatterSmem), st>>>(cx->d_tiles_rr, d_jobs, kA, vA, kB, vB, shift, cx->d_hist, cx->d_digit_base,
-                                                                               cx->d_ticket, tag);
+    if (!sc3)
+      sc_kernel<<<(u32)tiles_rr.size(), SC_THREADS, sizeof(ScatterSmem), st>>>(cx->d_tiles_rr, d_jobs, kA, vA, kB, vB, shift, cx->d_hist, cx->d_digit_base,
+                                                                                 cx->d_ticket, tag);
+    else
+      sc3_kernel<<<(u32)tiles_sc.size(), sc_tile / SC_ITEMS, sc3_smem, st>>>(reinterpret_cast<const B2ScTile *>(cx->d_tiles_rr), kA, vA, kB, vB, shift,
+                                                                              cx->d_hist, cx->d_digit_base, cx->d_ticket, tag, sc_pfd);
     pass_no++;
     if (cx->timing) { cudaEventRecord(ev.b, st); evs.push_back(ev); }
     B2_CUDA_CHECK(cudaGetLastError());

@@ -59,6 +59,7 @@ struct B2SortCtx {
   u32 *d_hist, *d_digit_base;    // look-back tile states [tile][256]; digit bases [block][8 passes][256]
   B2SortTileRR *d_tiles_rr;
   u32 *d_ticket;                 // error flag of the look-back
+  const B2Job *h_jobs;           // host copy of the batch's blocks (pos_off), indexed by block id
   u32 max_used;                  // the largest alphabet (bytes in use) of the batch
   int sym_bits;                  // bits per character of the round-0 keys (ceil log2 of the largest alphabet of the batch)
   i32 *d_tile_head, *d_carry;
