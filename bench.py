@@ -303,6 +303,7 @@ def main():
     h_in.copy_(d_in[:n_local])
     h_out = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
     torch.cuda.synchronize()
+    torch.cuda.empty_cache()          # the generator's temporaries go back to the device: the encoder sizes its batches by the free memory
     # the two scalar exchanges of a sharded stream go through the host (gloo): no GPU kernel, no wait for an SM
     comm = sharding.TorchComm(dist, rank, world, None, dist.new_group(backend="gloo")) if world > 1 else None
 
@@ -443,8 +444,8 @@ def main():
     # SURVEY 8(d) stage figure: (24 p + 12) n per round, summed = 24 * (rows moved by all passes) + 12 * (rows entering all rounds)
     stage_bytes = 24.0 * tot["scatter_elems"] + 12.0 * (tot["sort_elems_round0"] + tot["sort_elems_later"])
     stage_gbs = stage_bytes / (tot["sort_ms"] / 1000.0) / 1e9 if tot["sort_ms"] > 0 else 0.0
-    sc_variant = os.environ.get("B2GPU_SCATTER", "2")
-    sc_name = "k_scatter" if sc_variant == "1" else "k_scatter2 (variant %s)" % sc_variant
+    sc_variant = os.environ.get("B2GPU_SCATTER", "45")
+    sc_name = "k_scatter" if sc_variant == "1" else ("k_scatter3" if sc_variant[:1] == "4" else "k_scatter2") + " (B2GPU_SCATTER = %s)" % sc_variant
     roofline = {"bound": "hbm", "kernel": sc_name + ": one LSD radix pass of the BWT rotation sort (ranking, decoupled look-back and scatter in one kernel)",
                 "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                 "peak_source": peak_src, "traffic": None,

@@ -116,6 +116,12 @@ def main():
 
     mode = sys.argv[3] if len(sys.argv) > 3 else "full"
     best = None
+    if mode == "third":
+        # third run: the defaults as built (k_scatter3 variant 45, dispatch groups of 64, prefetch one SM count ahead, the
+        # batch sized by the free memory) against their neighbours
+        for env in ({}, {"B2GPU_SC_PFD": 296}, {"B2GPU_SC_PFD": 74}, {"B2GPU_BATCH_POSITIONS": 1610612736}):
+            run(env)
+        return 0
     if mode == "full":
         # round 1's path as the control, then the package-merge by merge path and the seven-pass round 0 one at a time
         control = {"B2GPU_SCATTER": 1, "B2GPU_PM": 0, "B2GPU_R0": 8}

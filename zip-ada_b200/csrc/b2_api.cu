@@ -184,6 +184,7 @@ struct b2_encoder {
   std::vector<b2_chunk_trace> trace;
   b2_stats stats;
   B2SortStats sort_stats;
+  bool batch_positions_fixed = false;   // B2GPU_BATCH_POSITIONS was given: the adaptive single-batch rule below is off
   size_t batch_positions = 1536ull << 20;  // positions per batch (env B2GPU_BATCH_POSITIONS); big batches amortise the latency-bound kernels (about 45 B of device memory per position)
   size_t first_batch_positions = ~(size_t)0;     // optional smaller first batch of a single large stream (env B2GPU_FIRST_BATCH_POSITIONS; measured: not a gain)
   size_t batch_jobs_max = 65535;        // blocks per batch    (env B2GPU_BATCH_JOBS)
@@ -762,6 +763,25 @@ int encode_chunks(b2_encoder *e, const u8 *d_in, std::vector<StreamDesc> &stream
       cv.notify_all();
     }
   };
+  // One batch instead of two is worth 4 % on a 1 GiB text stream (the latency-bound kernels run once over all the
+  // blocks; profiles/r02c_variants.jsonl).  When the whole call is expected to fit - about 2.8 positions per input byte,
+  // 52 bytes of workspace per position including the slack of the buffers - into what the workspace already holds
+  // plus the device memory that is free right now (less a margin for the caller), the batch limit is raised to that.
+  // An estimate that turns out too low just starts a second batch.
+  size_t batch_limit = e->batch_positions;
+  if (!e->batch_positions_fixed && W == 1) {
+    u64 total_len = 0;
+    for (u32 c = 0; c < n_chunks; c++) total_len += e->chunks[c].len;
+    const u64 est = (u64)((double)total_len * 2.8) + (u64)n_chunks * 4096;
+    size_t free_b = 0, total_b = 0;
+    if (est > batch_limit && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+      const size_t have = e->ws[0]->d_keysA.cap;                       // positions the workspace holds already
+      const size_t margin = (size_t)12 << 30;
+      size_t can = have + (free_b > margin ? (size_t)((double)(free_b - margin) / 52.0) : 0);
+      can = std::min<size_t>(can, 4200000000ull);                      // 32-bit arena offsets: below 2^32 less one chunk's worst case
+      if (est <= can) batch_limit = can;
+    }
+  }
   std::vector<std::thread> th;
   for (int i = 0; i < W; i++) th.emplace_back(worker, i);
   int plan_rc = 0;
@@ -785,7 +805,7 @@ int encode_chunks(b2_encoder *e, const u8 *d_in, std::vector<StreamDesc> &stream
       if ((plan_rc = plan_chunk(e, c, P, add, cur.jobs.size(), addpos))) break;
       // While the segmentation is still following the chunk chain the device has nothing else to do: the
       // first batch is kept small so that it starts as soon as its few chunks are cut and segmented.
-      const size_t limit = (followed && published == 0) ? std::min(e->first_batch_positions, e->batch_positions) : e->batch_positions;
+      const size_t limit = (followed && published == 0) ? std::min(e->first_batch_positions, batch_limit) : batch_limit;
       if (!cur.jobs.empty() && (positions + addpos > limit || cur.jobs.size() + add.size() > e->batch_jobs_max)) {
         cur.c1 = c;
         publish(std::move(cur));
@@ -921,7 +941,7 @@ int b2_create(int level, int device, b2_encoder **out) {
   memset(&e->stats, 0, sizeof e->stats);
   memset(&e->sort_stats, 0, sizeof e->sort_stats);
   // arena offsets are 32-bit: a batch plus one more chunk's worth of blocks must stay below 2^32 positions
-  if (const char *s = getenv("B2GPU_BATCH_POSITIONS")) { long long v = atoll(s); if (v >= (1 << 20)) e->batch_positions = (size_t)std::min<long long>(v, 3ll << 30); }
+  if (const char *s = getenv("B2GPU_BATCH_POSITIONS")) { long long v = atoll(s); if (v >= (1 << 20)) { e->batch_positions = (size_t)std::min<long long>(v, 3ll << 30); e->batch_positions_fixed = true; } }
   if (const char *s = getenv("B2GPU_FIRST_BATCH_POSITIONS")) { long long v = atoll(s); if (v >= (1 << 20)) e->first_batch_positions = (size_t)v; }
   if (const char *s = getenv("B2GPU_BATCH_JOBS")) { long long v = atoll(s); if (v >= 8) e->batch_jobs_max = (size_t)std::min<long long>(v, 65535); }   // grid.y of the per-(triple, block) kernels
   if (const char *s = getenv("B2GPU_PIPELINE")) { int v = atoi(s); if (v >= 1 && v <= 8) e->n_workspaces = v; }

@@ -516,7 +516,7 @@ int b2k_bwt_batch(B2SortCtx *cx, cudaStream_t st, B2Job *d_jobs, const std::vect
                   const std::vector<u32> &job_n, const u8 *d_text, u8 *d_bwt) {
   // B2GPU_SCATTER: see sc_pick; 40..47 = k_scatter3: bit 0 = L2 prefetch of the tile B2GPU_SC_PFD places ahead, bit 1 = tiles of
   // 2048 rows (six CTAs per SM) instead of 4096, bit 2 = rotation indices requested before the scan
-  int sc_variant = 2;
+  int sc_variant = 45;                                       // measured best (profiles/r02c_variants.jsonl)
   if (const char *e = getenv("B2GPU_SCATTER")) sc_variant = atoi(e);
   const bool sc3 = sc_variant >= 40 && sc_variant <= 47;
   const u32 sc_tile = (sc3 && (sc_variant & 2)) ? 2048u : (u32)SC_TILE;
@@ -525,7 +525,7 @@ int b2k_bwt_batch(B2SortCtx *cx, cudaStream_t st, B2Job *d_jobs, const std::vect
   if (sc3 && (sc_variant & 1)) {
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    sc_pfd = (u32)sms * (sc_tile == 2048u ? 4u : 2u);        // two thirds of the tiles resident on the device
+    sc_pfd = (u32)sms * (sc_tile == 2048u ? 2u : 1u);        // a third of the tiles resident on the device (148 measured better than 296 and 592)
     if (const char *e = getenv("B2GPU_SC_PFD")) { long v = atol(e); if (v >= 1 && v < (1 << 20)) sc_pfd = (u32)v; }
   }
   const sc_kernel_t sc_kernel = sc_pick(sc_variant);
@@ -539,7 +539,7 @@ int b2k_bwt_batch(B2SortCtx *cx, cudaStream_t st, B2Job *d_jobs, const std::vect
   std::vector<B2ScTile> tiles_sc;
   std::vector<B2SortTile> tiles;
   std::vector<B2SortTileRR> tiles_rr;
-  size_t rr_group = 128;
+  size_t rr_group = 64;                    // 64 measured best for k_scatter3 (128 for k_scatter2)
   if (const char *e = getenv("B2GPU_RR_GROUP")) { long v = atol(e); if (v >= 1) rr_group = (size_t)v; }
   std::vector<B2SortJob> sj;
   std::vector<u32> ids, ns, nas;             // active blocks: id, size, active rows
