@@ -1,7 +1,7 @@
 // Host emulation of k_scatter2 (zip-ada_b200/csrc/b2_scatter2.cuh) against a plain stable counting sort.
 // Test infrastructure (tests/test_emu_scatter.py builds and runs it); usage: emu_scatter <mode> <rr_group> <window> <seed> <shift_step>
-//   mode: 0..3 = template MODE of k_scatter2 (bit 0 match.any, bit 1 keys loaded early); 40 / 42 = k_scatter3 with tiles of
-//   4096 / 2048 rows
+//   mode: 0..3 = template MODE of k_scatter2 (bit 0 match.any, bit 1 keys loaded early); 40..71 = k_scatter3 (40 + bits: 2 = tiles
+//   of 2048 rows, 4 = rotation indices early, 8 = digit from the key registers, 16 = second early look at the predecessor)
 // Blocks of several sizes (empty tail tiles, exactly one tile, one row, several tiles), digits of every pass
 // position, skewed and uniform digit distributions; every block must come out as the stable sort of its rows by
 // the digit, all other arena positions untouched.
@@ -63,7 +63,7 @@ static int run(size_t group, unsigned window, unsigned seed, int shift_step) {
   for (size_t j = 0; j < blocks.size(); j++) { std::memset(&jobs[j], 0, sizeof(B2Job)); jobs[j].na = blocks[j].n; jobs[j].n = blocks[j].n + 5; jobs[j].pos_off = blocks[j].off; }
   std::vector<B2SortTileRR> rr;
   std::vector<B2ScTile> sc;
-  constexpr int THREADS3 = (MODE & 2) ? 256 : 512;           // MODE 40..47: k_scatter3; bit 1 = tiles of 2048 rows, bit 2 = rotation indices requested early
+  constexpr int THREADS3 = ((MODE - 40) & 2) ? 256 : 512;           // MODE 40..71: k_scatter3; 40 + bits: 2 = tiles of 2048 rows, 4 / 8 / 16 = SC3_VEARLY / LEAN / MIDLOOK
   if (MODE >= 40) tiles_sc(blocks, group, THREADS3 * SC_ITEMS, sc); else tiles_rr(blocks, group, rr);
   const size_t ntile = MODE >= 40 ? sc.size() : rr.size();
   std::vector<u32> state(ntile * 256, 0);
@@ -95,7 +95,7 @@ static int run(size_t group, unsigned window, unsigned seed, int shift_step) {
       if constexpr (MODE >= 40) {
         const u32 pfd = (shift & 8) ? 3u : 0u;                // with and without the prefetch of a later tile (a no-op here but for its addressing)
         emu_launch((unsigned)sc.size(), THREADS3, sizeof(ScatterSmemT<THREADS3>), window, [&]() {
-          k_scatter3<THREADS3, 3, (MODE & 4) != 0>(sc.data(), kin.data(), vin.data(), kout.data(), vout.data(), shift, state.data(), jobhist.data(), &lb_error, tag, pfd);
+          k_scatter3<THREADS3, 3, ((MODE - 40) >> 2)>(sc.data(), kin.data(), vin.data(), kout.data(), vout.data(), shift, state.data(), jobhist.data(), &lb_error, tag, pfd);
         });
       } else {
         emu_launch((unsigned)rr.size(), SC_THREADS, sizeof(ScatterSmem), window, [&]() {
@@ -135,6 +135,10 @@ int main(int argc, char **argv) {
     case 42: bad = run<42>(group, window, seed, step); break;
     case 44: bad = run<44>(group, window, seed, step); break;
     case 46: bad = run<46>(group, window, seed, step); break;
+    case 52: bad = run<52>(group, window, seed, step); break;
+    case 60: bad = run<60>(group, window, seed, step); break;
+    case 68: bad = run<68>(group, window, seed, step); break;
+    case 70: bad = run<70>(group, window, seed, step); break;
     default: bad = run<SC2_EARLY | SC2_MATCHANY>(group, window, seed, step); break;
   }
   printf(bad ? "FAILED\n" : "OK\n");

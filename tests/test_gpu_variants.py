@@ -1,6 +1,7 @@
 """Every switchable variant of the CUDA path gives the oracle's bytes (`-m gpu`): the radix pass (B2GPU_SCATTER: round 1's
 k_scatter, k_scatter2 with ballots / match.any, two or three CTAs per SM, keys loaded early or late, k_scatter3 with tiles
-of 4096 / 2048 rows, with and without the L2 prefetch and the early rotation indices), the package-merge
+of 4096 / 2048 rows, with and without the L2 prefetch, the early rotation indices, the digit from the key registers and the
+second early look at the predecessor), the package-merge
 lists (B2GPU_PM: binary searches / merge path) and round 0 of the rotation sort in eight or seven passes (B2GPU_R0).
 The knobs are read per call, so one handle serves all of them."""
 import os
@@ -14,7 +15,7 @@ from test_gpu_parity import _cmp_block
 
 pytestmark = pytest.mark.gpu
 KNOBS = ("B2GPU_SCATTER", "B2GPU_PM", "B2GPU_R0")
-VARIANTS = [{"B2GPU_SCATTER": s} for s in (1, 2, 22, 24, 3, 32, 34, 40, 41, 42, 43, 44, 45, 46, 47)] + [{"B2GPU_PM": 0}, {"B2GPU_PM": 1}, {"B2GPU_R0": 8}, {"B2GPU_R0": 7},
+VARIANTS = [{"B2GPU_SCATTER": s} for s in (1, 2, 22, 24, 3, 32, 34, 40, 41, 42, 43, 44, 45, 46, 47, 53, 61, 69, 71)] + [{"B2GPU_PM": 0}, {"B2GPU_PM": 1}, {"B2GPU_R0": 8}, {"B2GPU_R0": 7},
                                                                         {"B2GPU_SCATTER": 1, "B2GPU_PM": 0, "B2GPU_R0": 8}]
 
 

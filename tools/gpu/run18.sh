@@ -14,5 +14,5 @@ timeout 170 python bench.py --steps 3 --warmup 3 --stage-times --no-decode > gpu
 grep "^{" gpurun_out/bench_s4_text.json | python -c "
 import sys, json
 d = json.loads(sys.stdin.read()); print(d['value'], d['e2e']['value'], d['ms_per_step'], d['roofline']['frac'], d['roofline']['sort_stage']['frac'], d['parity']['timed_output_equals_oracle_golden'], d['parity']['device_verify'], d.get('stage_ms'))"
-timeout 300 python -m pytest tests -m gpu -q --maxfail=6 2>&1 | tail -8
+timeout 330 python -m pytest tests -m gpu -q --maxfail=6 2>&1 | tail -8
 nvidia-smi --query-gpu=memory.used,memory.total --format=csv,noheader

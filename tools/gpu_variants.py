@@ -119,7 +119,8 @@ def main():
     if mode == "third":
         # third run: the defaults as built (k_scatter3 variant 45, dispatch groups of 64, prefetch one SM count ahead, the
         # batch sized by the free memory) against their neighbours
-        for env in ({}, {"B2GPU_SC_PFD": 296}, {"B2GPU_SC_PFD": 74}, {"B2GPU_BATCH_POSITIONS": 1610612736}):
+        for env in ({}, {"B2GPU_SCATTER": 53}, {"B2GPU_SCATTER": 61}, {"B2GPU_SCATTER": 69}, {"B2GPU_SC_PFD": 296}, {"B2GPU_SC_PFD": 74},
+                    {"B2GPU_BATCH_POSITIONS": 1610612736}):
             run(env)
         return 0
     if mode == "full":

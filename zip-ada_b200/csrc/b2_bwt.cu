@@ -514,15 +514,16 @@ struct EvPair { cudaEvent_t a, b; };
 // job_n[k] = post-RLE1 size of block job_ids[k]; the device copies have na == n on entry.
 int b2k_bwt_batch(B2SortCtx *cx, cudaStream_t st, B2Job *d_jobs, const std::vector<u32> &job_ids,
                   const std::vector<u32> &job_n, const u8 *d_text, u8 *d_bwt) {
-  // B2GPU_SCATTER: see sc_pick; 40..47 = k_scatter3: bit 0 = L2 prefetch of the tile B2GPU_SC_PFD places ahead, bit 1 = tiles of
-  // 2048 rows (six CTAs per SM) instead of 4096, bit 2 = rotation indices requested before the scan
+  // B2GPU_SCATTER: see sc_pick; 40..71 = k_scatter3, 40 + bits: 1 = L2 prefetch of the tile B2GPU_SC_PFD places ahead, 2 = tiles of
+  // 2048 rows (six CTAs per SM) instead of 4096, 4 = rotation indices requested before the scan, 8 = digit of the output phase
+  // from the key registers, 16 = second early look at the predecessor's state
   int sc_variant = 45;                                       // measured best (profiles/r02c_variants.jsonl)
   if (const char *e = getenv("B2GPU_SCATTER")) sc_variant = atoi(e);
-  const bool sc3 = sc_variant >= 40 && sc_variant <= 47;
-  const u32 sc_tile = (sc3 && (sc_variant & 2)) ? 2048u : (u32)SC_TILE;
-  const bool sc_vearly = sc3 && (sc_variant & 4);
+  const bool sc3 = sc_variant >= 40 && sc_variant <= 71;
+  const int sc_bits = sc3 ? sc_variant - 40 : 0;
+  const u32 sc_tile = (sc_bits & 2) ? 2048u : (u32)SC_TILE;
   u32 sc_pfd = 0;
-  if (sc3 && (sc_variant & 1)) {
+  if (sc_bits & 1) {
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     sc_pfd = (u32)sms * (sc_tile == 2048u ? 2u : 1u);        // a third of the tiles resident on the device (148 measured better than 296 and 592)
@@ -530,8 +531,15 @@ int b2k_bwt_batch(B2SortCtx *cx, cudaStream_t st, B2Job *d_jobs, const std::vect
   }
   const sc_kernel_t sc_kernel = sc_pick(sc_variant);
   typedef void (*sc3_kernel_t)(const B2ScTile *, const u64 *, const u32 *, u64 *, u32 *, int, u32 *, const u32 *, u32 *, u32, u32);
-  const sc3_kernel_t sc3_kernel = sc_tile == 2048u ? (sc_vearly ? k_scatter3<256, 6, true> : k_scatter3<256, 6, false>)
-                                                   : (sc_vearly ? k_scatter3<512, 3, true> : k_scatter3<512, 3, false>);
+  sc3_kernel_t sc3_kernel = nullptr;
+  {
+    const int fl = ((sc_bits & 4) ? SC3_VEARLY : 0) | ((sc_bits & 8) ? SC3_LEAN : 0) | ((sc_bits & 16) ? SC3_MIDLOOK : 0);
+    static const sc3_kernel_t k512[8] = {k_scatter3<512, 3, 0>, k_scatter3<512, 3, 1>, k_scatter3<512, 3, 2>, k_scatter3<512, 3, 3>,
+                                         k_scatter3<512, 3, 4>, k_scatter3<512, 3, 5>, k_scatter3<512, 3, 6>, k_scatter3<512, 3, 7>};
+    static const sc3_kernel_t k256[8] = {k_scatter3<256, 6, 0>, k_scatter3<256, 6, 1>, k_scatter3<256, 6, 2>, k_scatter3<256, 6, 3>,
+                                         k_scatter3<256, 6, 4>, k_scatter3<256, 6, 5>, k_scatter3<256, 6, 6>, k_scatter3<256, 6, 7>};
+    sc3_kernel = sc_tile == 2048u ? k256[fl] : k512[fl];
+  }
   const size_t sc3_smem = sc_tile == 2048u ? sizeof(ScatterSmemT<256>) : sizeof(ScatterSmemT<512>);
   // per device and cheap; set on every call so that handles on several devices / threads all have it
   if (!sc3) B2_CUDA_CHECK(cudaFuncSetAttribute(sc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));

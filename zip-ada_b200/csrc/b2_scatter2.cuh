@@ -238,7 +238,8 @@ k_scatter2(const B2SortTileRR *__restrict__ tiles, const B2Job *__restrict__ job
 //    order (prefetch.global.L2, one 128-byte line per thread): when that tile starts, its loads are L2 hits, and the
 //    DRAM reads of a tile are in flight one tile lifetime before they are needed;
 //  * THREADS = 256 makes tiles of 2048 rows, six resident per SM instead of three (finer interleaving of the phases);
-//  * VEARLY requests the rotation indices before the scan / look-back phase instead of after it.
+//  * flags (SC3_*): rotation indices requested before the scan / look-back phase; digit of the output phase from the key
+//    registers; a second early look at the predecessor's look-back state.
 struct B2ScTile { u32 jobcnt; u32 row0; u32 prev; u32 off; };   // jobcnt = block | (rows - 1) << 16; row0 = arena index of the first row
 
 template <int THREADS> struct ScatterSmemT {
@@ -258,12 +259,17 @@ __device__ __forceinline__ void sc_prefetch_l2(const void *p) {
 #endif
 }
 
-template <bool FULL, int THREADS, bool VEARLY>
+#define SC3_VEARLY 1      // rotation indices requested before the scan / look-back phase
+#define SC3_LEAN 2        // output phase: the digit comes out of the key registers instead of another shared-memory load
+#define SC3_MIDLOOK 4     // a second look at the predecessor's state right after the ranking (the first one, at the start, is too early
+                          // when the dispatch groups are small)
+template <bool FULL, int THREADS, int FLAGS>
 __device__ __forceinline__ void sc3_body(ScatterSmemT<THREADS> &S, const u32 cnt, const u32 row0, const u32 prev, const u32 off,
                                          const B2ScTile *__restrict__ tiles, const u64 *__restrict__ keys_in, const u32 *__restrict__ vals_in,
                                          u64 *__restrict__ keys_out, u32 *__restrict__ vals_out, const int shift, u32 *__restrict__ state,
-                                         u32 *__restrict__ lb_error, const u32 tag, const u32 v_early, const bool pf, const uint4 rec2) {
+                                         u32 *__restrict__ lb_error, const u32 tag, u32 v_early, const bool pf, const uint4 rec2) {
   constexpr int TILE = THREADS * SC_ITEMS, WARPS = THREADS / 32;
+  constexpr bool VEARLY = (FLAGS & SC3_VEARLY) != 0, LEAN = (FLAGS & SC3_LEAN) != 0, MIDLOOK = (FLAGS & SC3_MIDLOOK) != 0;
   const u32 tid = threadIdx.x, w = tid >> 5, l = tid & 31u;
   const u32 tix = blockIdx.x;
   const u32 lt_mask = (1u << l) - 1u;
@@ -295,6 +301,10 @@ __device__ __forceinline__ void sc3_body(ScatterSmemT<THREADS> &S, const u32 cnt
     if (valid && r == 0) wc[d[k]] = base + __popc(peers);
     __syncwarp();
     rk[k] = base + r;                                           // < 256: a warp holds 256 rows
+  }
+  if (MIDLOOK) {
+    // the tile before mine was dispatched one group of blocks earlier: by now it has usually published its inclusive count
+    if (tid < 256 && prev != 0xFFFFFFFFu && (v_early & 0xFFC00000u) != (LB_INC | tag)) v_early = lb_load(state + (size_t)prev * 256 + tid);
   }
   // VEARLY: the rotation indices are requested before the scan and the look-back, whose time hides their latency
   u32 val[SC_ITEMS];
@@ -364,7 +374,7 @@ __device__ __forceinline__ void sc3_body(ScatterSmemT<THREADS> &S, const u32 cnt
     const u32 q = tid + k * THREADS;
     if (FULL || q < cnt) {
       const u64 kk = S.keys[q];
-      const u32 dg = sdig[(size_t)k * THREADS * 8];
+      const u32 dg = LEAN ? ((u32)(kk >> shift) & 255u) : (u32)sdig[(size_t)k * THREADS * 8];
       const u32 dst = S.g_off[dg] + q;
       keys_out[dst] = kk;
       vals_out[dst] = S.vals[q];
@@ -372,7 +382,7 @@ __device__ __forceinline__ void sc3_body(ScatterSmemT<THREADS> &S, const u32 cnt
   }
 }
 
-template <int THREADS, int MINCTAS, bool VEARLY>
+template <int THREADS, int MINCTAS, int FLAGS>
 __global__ void __launch_bounds__(THREADS, MINCTAS)
 k_scatter3(const B2ScTile *__restrict__ tiles, const u64 *__restrict__ keys_in, const u32 *__restrict__ vals_in,
            u64 *__restrict__ keys_out, u32 *__restrict__ vals_out, int shift, u32 *__restrict__ state,
@@ -402,6 +412,6 @@ k_scatter3(const B2ScTile *__restrict__ tiles, const u64 *__restrict__ keys_in, 
     if (prev != 0xFFFFFFFFu) v_early = lb_load(state + (size_t)prev * 256 + tid);   // only trusted when final
   }
   __syncwarp();
-  if (cnt == TILE) sc3_body<true, THREADS, VEARLY>(S, cnt, row0, prev, off, tiles, keys_in, vals_in, keys_out, vals_out, shift, state, lb_error, tag, v_early, pf, rec2);
-  else sc3_body<false, THREADS, VEARLY>(S, cnt, row0, prev, off, tiles, keys_in, vals_in, keys_out, vals_out, shift, state, lb_error, tag, v_early, pf, rec2);
+  if (cnt == TILE) sc3_body<true, THREADS, FLAGS>(S, cnt, row0, prev, off, tiles, keys_in, vals_in, keys_out, vals_out, shift, state, lb_error, tag, v_early, pf, rec2);
+  else sc3_body<false, THREADS, FLAGS>(S, cnt, row0, prev, off, tiles, keys_in, vals_in, keys_out, vals_out, shift, state, lb_error, tag, v_early, pf, rec2);
 }
