@@ -351,12 +351,16 @@ def main():
     # ---- end to end through the C ABI with host buffers ----------------------------------------------------
     e_piece = step(False)
     barrier()
+    enc.reset_stats()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         e_piece = step(False)
     barrier()
     e_wall = maxrank(time.perf_counter() - t0)
     e2e = n * args.steps / 1e6 / e_wall
+    st_e = enc.stats()
+    e2e_detail = {"ms_per_step": round(1000 * e_wall / args.steps, 2), "device_event_ms_per_step": round(st_e.call_ms / args.steps, 2),
+                  "gpu_launches_per_step": int(st_e.kernel_launches // args.steps), "free_device_GiB": round(torch.cuda.mem_get_info()[0] / 2 ** 30, 1)}
     host_piece = h_out[:e_piece[1]].numpy()
     same_paths = bool(piece == e_piece and np.array_equal(dev_piece, host_piece))
     # ---- statistics over all ranks ----------------------------------------------------------------------------
@@ -444,8 +448,8 @@ def main():
     # SURVEY 8(d) stage figure: (24 p + 12) n per round, summed = 24 * (rows moved by all passes) + 12 * (rows entering all rounds)
     stage_bytes = 24.0 * tot["scatter_elems"] + 12.0 * (tot["sort_elems_round0"] + tot["sort_elems_later"])
     stage_gbs = stage_bytes / (tot["sort_ms"] / 1000.0) / 1e9 if tot["sort_ms"] > 0 else 0.0
-    sc_variant = os.environ.get("B2GPU_SCATTER", "45")
-    sc_name = "k_scatter" if sc_variant == "1" else ("k_scatter3" if sc_variant[:1] == "4" else "k_scatter2") + " (B2GPU_SCATTER = %s)" % sc_variant
+    sc_variant = os.environ.get("B2GPU_SCATTER", "53")
+    sc_name = "k_scatter" if sc_variant == "1" else ("k_scatter3" if 40 <= int(sc_variant) <= 71 else "k_scatter2") + " (B2GPU_SCATTER = %s)" % sc_variant
     roofline = {"bound": "hbm", "kernel": sc_name + ": one LSD radix pass of the BWT rotation sort (ranking, decoupled look-back and scatter in one kernel)",
                 "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                 "peak_source": peak_src, "traffic": None,
@@ -474,7 +478,7 @@ def main():
                        "bytes_per_rank": [b - a for a, b in zip(bounds, bounds[1:])],
                        "l2": "inputs (>= 0.5 GiB per GPU and step) and sort state are far larger than the 126 MB L2; no flush needed"},
             "device_event_ms_per_step": round(1000 * t_dev / args.steps, 2),
-            "e2e": {"value": round(e2e, 2), "unit": "MB/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "e2e": dict({"value": round(e2e, 2), "unit": "MB/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}, **e2e_detail),
             "gpu_launches": int(tot["kernel_launches"]),
             "roofline": roofline,
             "cpu_baseline": {"value": round(mbps, 3), "unit": "MB/s", "cores": 1, "kind": "port",

@@ -517,7 +517,7 @@ int b2k_bwt_batch(B2SortCtx *cx, cudaStream_t st, B2Job *d_jobs, const std::vect
   // B2GPU_SCATTER: see sc_pick; 40..71 = k_scatter3, 40 + bits: 1 = L2 prefetch of the tile B2GPU_SC_PFD places ahead, 2 = tiles of
   // 2048 rows (six CTAs per SM) instead of 4096, 4 = rotation indices requested before the scan, 8 = digit of the output phase
   // from the key registers, 16 = second early look at the predecessor's state
-  int sc_variant = 45;                                       // measured best (profiles/r02c_variants.jsonl)
+  int sc_variant = 53;                                       // measured best (profiles/r02c_variants.jsonl, r02d_variants.jsonl)
   if (const char *e = getenv("B2GPU_SCATTER")) sc_variant = atoi(e);
   const bool sc3 = sc_variant >= 40 && sc_variant <= 71;
   const int sc_bits = sc3 ? sc_variant - 40 : 0;
