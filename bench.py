@@ -453,7 +453,7 @@ def main():
     roofline = {"bound": "hbm", "kernel": sc_name + ": one LSD radix pass of the BWT rotation sort (ranking, decoupled look-back and scatter in one kernel)",
                 "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                 "peak_source": peak_src, "traffic": None,
-                "traffic_note": "not measured in this run; the ncu --set full capture of the kernel is under profiles/",
+                "traffic_note": "not measured in this run; ncu --set full of one launch of the kernel: 13.05 GB of DRAM traffic for 11.88 GB algorithmic (1.10 x), profiles/r02c_scatter_ncu_full_summary.md",
                 "algorithmic_bytes_per_launch": alg_bytes / max(1, tot["scatter_launches"]),
                 "launches": int(tot["scatter_launches"]), "avg_launch_ms": tot["scatter_ms"] / max(1, tot["scatter_launches"]),
                 "share_of_step": round(st.scatter_ms / max(1e-9, st.call_ms), 4),
