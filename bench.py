@@ -410,6 +410,10 @@ def main():
     # the same stream decoded on the device (b2_verify_stream: every block at once, block and stream CRCs, and at
     # N = 1 the bytes against the input)
     try:
+        # the encoder's workspace (one batch for the whole call when it fits) stays allocated: the decoder takes smaller
+        # waves of blocks when little device memory is left (6 bytes x 900 000 positions per block of a wave)
+        if "B2GPU_VERIFY_WAVE" not in os.environ and torch.cuda.mem_get_info()[0] < (24 << 30):
+            os.environ["B2GPU_VERIFY_WAVE"] = "512"
         if world == 1:
             vr = enc.verify_ptr(d_out.data_ptr(), True, int(total_len), d_in.data_ptr(), True, n)
         else:
