@@ -6,7 +6,9 @@
 //
 // Here: cyclic prefix doubling with filtering.  Round 0 sorts every rotation by its first 8 bytes,
 // each byte replaced by its rank among the bytes in use and packed with b = ceil (log2 (largest
-// alphabet of the batch)) bits: b LSD radix passes of 8 bits (5 for plain text, 8 for binary data).  A
+// alphabet of the batch)) bits: b LSD radix passes of 8 bits (5 for lower-case text) - or, when the
+// alphabet has more than 128 bytes, by seven characters in radix B and the eighth cut down to
+// floor (2^56 / B^7) order-preserving buckets: seven passes, and the doubling goes on from 7.  A
 // rank is the row index ("slot") of the first row of a class, so equal prefixes share a rank.  After
 // every round the rows that are alone in their class are final; only the others ("active" rows) are
 // compacted and re-sorted in round r >= 1 by the 40-bit key (rank[i] << 20 | rank[(i+h) mod n]) with 5
@@ -18,10 +20,11 @@
 // offset 0, :254, :276-279).  All blocks of a batch are sorted together: every radix pass is segmented
 // by block through a tile table, so no block id is needed in the key.
 //
-// Radix pass = ONE kernel (k_scatter): 12 B/row read, 12 B/row written, staged through shared memory so
-// that the writes leave as runs.  The digit totals of all passes of a round come from one read of the
-// keys (k_hist_all: LSD passes only permute the rows of a block), the per-tile offsets from a decoupled
-// look-back inside the scatter (see k_scatter).
+// Radix pass = ONE kernel (k_scatter3 in b2_scatter2.cuh; k_scatter below and k_scatter2 are its earlier
+// versions, kept switchable by B2GPU_SCATTER): 12 B/row read, 12 B/row written, staged through shared
+// memory so that the writes leave as runs.  The digit totals of all passes of a round come from one read
+// of the keys (k_hist_all: LSD passes only permute the rows of a block), the per-tile offsets from a
+// decoupled look-back inside the scatter (see k_scatter).
 #include "b2_common.cuh"
 #include "b2_kernels.h"
 
