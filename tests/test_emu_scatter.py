@@ -26,9 +26,8 @@ def emu(tmp_path_factory):
 # modes 0..3: k_scatter2 (bit 0 match.any, bit 1 keys loaded early); 40..71: k_scatter3 (40 + bits: 2 = tiles of 2048 rows, 4 = rotation
 # indices requested early, 8 = digit from the key registers, 16 = second early look; the prefetch distance alternates between 0 and 3
 # inside the run)
-@pytest.mark.parametrize("args", [(0, 128, 1, 1, 24), (0, 1, 3, 2, 24), (1, 2, 3, 3, 24), (2, 128, 2, 4, 24), (3, 1, 3, 5, 24),
-                                  (40, 128, 1, 6, 24), (40, 1, 3, 7, 24), (42, 2, 4, 8, 24), (44, 64, 1, 9, 8), (46, 128, 2, 10, 24),
-                                  (68, 64, 3, 11, 24), (70, 2, 4, 12, 24)])
+@pytest.mark.parametrize("args", [(0, 128, 1, 1, 24), (0, 1, 3, 2, 24), (1, 2, 3, 3, 24), (2, 128, 2, 4, 24),
+                                  (40, 64, 1, 6, 24), (52, 1, 3, 7, 24), (52, 64, 1, 9, 8), (70, 2, 4, 12, 24)])
 def test_scatter_emulated(emu, args):
     r = subprocess.run([emu] + [str(a) for a in args], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout[-2000:]
