@@ -6,7 +6,9 @@ literal sequential algorithms in pure Python (no GPU, no oracle):
  * k_mtf_seq / k_mtf_seq8: move-to-front kept as the PLACE of every symbol instead of the list
    (zip-ada_b200/csrc/b2_mtf.cu; bzip2-encoding.adb:384-396);
  * k_ent_pm: the forward package-merge may stop as soon as a list repeats the one below
-   (zip-ada_b200/csrc/b2_entropy.cu; huffman-encoding-length_limited_coding.adb:131-163).
+   (zip-ada_b200/csrc/b2_pm.cuh; huffman-encoding-length_limited_coding.adb:131-163);
+ * k_keys0: round 0 of the rotation sort by seven characters in radix B plus a bucketed eighth, doubling from 7
+   (zip-ada_b200/csrc/b2_bwt.cu; the order of bzip2-encoding.adb:229-255).
 """
 import math
 import random
@@ -286,3 +288,62 @@ def test_scatter_dispatch_order_and_lookback_offsets():
             inclusive[pos] = [e + c for e, c in zip(excl, counts[pos])]
             want = [sum(counts[p][d] for p, (jj, kk, _) in enumerate(rr) if jj == j and kk < k) for d in range(4)]
             assert excl == want
+
+
+# ---------------------------------------------------------------------------------------------------
+# Round 0 of the rotation sort in seven passes (k_keys0, b2_bwt.cu): seven characters in radix B and the
+# eighth cut down to q order-preserving buckets make a key below 2^56; equal keys share seven characters,
+# the doubling goes on from 7, and the sorted rotations - hence the BWT string and the origin pointer
+# (bzip2-encoding.adb:229-255, :273-280) - are those of the plain sort.
+# ---------------------------------------------------------------------------------------------------
+def _doubling_sort(text, key0, h0):
+    """Cyclic prefix doubling: ranks from the round-0 key, then (rank[i], rank[i + h]) with h = h0, 2 h0, ..."""
+    n = len(text)
+    order = sorted(range(n), key=lambda i: key0[i])
+    rank = [0] * n
+    for pos, i in enumerate(order):
+        rank[i] = pos if pos == 0 or key0[i] != key0[order[pos - 1]] else rank[order[pos - 1]]
+    h = h0
+    while h < n and len(set(rank)) < n:
+        pair = [(rank[i], rank[(i + h) % n]) for i in range(n)]
+        order = sorted(range(n), key=lambda i: pair[i])
+        new = [0] * n
+        for pos, i in enumerate(order):
+            new[i] = pos if pos == 0 or pair[i] != pair[order[pos - 1]] else new[order[pos - 1]]
+        rank = new
+        h *= 2
+    return rank
+
+
+def test_seven_pass_round0_key_orders_like_the_rotations():
+    rng = random.Random(20260117)
+    for trial in range(60):
+        B = rng.choice([129, 137, 200, 256])
+        q = (1 << 56) // B ** 7
+        assert q >= 1 and B ** 7 * q <= 1 << 56
+        n = rng.choice([1, 2, 5, 7, 8, 9, 40, 300])
+        kind = trial % 3
+        if kind == 0:
+            text = [rng.randrange(B) for _ in range(n)]
+        elif kind == 1:
+            unit = [rng.randrange(B) for _ in range(rng.choice([1, 2, 3]))]           # periodic: equal rotations
+            text = (unit * n)[:n]
+        else:
+            text = [rng.choice([0, 1, B - 2, B - 1]) for _ in range(n)]                 # long common prefixes, extreme codes
+        key0 = []
+        for i in range(n):
+            k = 0
+            for j in range(7):
+                k = k * B + text[(i + j) % n]
+            c8 = text[(i + 7) % n]
+            k = k * q + (c8 * q) // B
+            assert k < 1 << 56
+            key0.append(k)
+        rank = _doubling_sort(text, key0, 7)
+        rot = lambda i: text[i:] + text[:i]
+        plain = sorted(range(n), key=lambda i: (rot(i), i))
+        # rotations in rank order are in lexicographic order, equal ranks = equal rotations
+        by_rank = sorted(range(n), key=lambda i: (rank[i], i))
+        assert [rot(i) for i in by_rank] == [rot(i) for i in plain], (trial, B, n)
+        for a, b in zip(by_rank, by_rank[1:]):
+            assert (rank[a] == rank[b]) == (rot(a) == rot(b)), (trial, a, b)
